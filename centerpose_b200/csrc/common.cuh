@@ -1,0 +1,91 @@
+// Shared declarations for libcenterpose_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/centerpose_b200.h"
+
+namespace cp {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define CP_CUDA_CHECK(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return ::cp::fail(CP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+#define CP_LAUNCH_CHECK(what)                                                            \
+  do {                                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess)                                                               \
+      return ::cp::fail(CP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(_e));  \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// Implicit-GEMM convolution, fp32 CUDA-core path (parity mode).
+//   out[m, n] = epilogue( sum_k A[m, k] * Wp[k, n] )
+//   m = (b, oy, ox) output pixel, n = output channel, k = (ky, kx, ci).
+// A is never materialised: it is gathered on the fly from up to 4 NHWC sources
+// (channel concatenation, Root nodes), from an NCHW tensor (stems), or by
+// bilinear deformable sampling driven by an offset/mask tensor (DCNv2).
+// ---------------------------------------------------------------------------
+enum IgemmMode {
+  IGEMM_NCHW_SCALAR = 0,  // generic k -> (tap, c) decode, NCHW input (7x7 stems, Cin = 1/3/8)
+  IGEMM_NHWC_VEC = 1,     // Cin of every source % 16 == 0, float4 gathers
+  IGEMM_DCN = 2           // 3x3 s1 p1 modulated deformable sampling, single NHWC source
+};
+
+struct IgemmParams {
+  const float* src[4];
+  int srcC[4];       // channels contributed by each source
+  int srcStride[4];  // pixel stride (floats) of each NHWC source (>= srcC)
+  int nsrc;
+  int B, Hin, Win, Cin;
+  int Hout, Wout, Cout, CoutPad;
+  int kh, kw, stride, pad;
+  int Kpad;              // rows of the packed weight matrix (multiple of 16)
+  const float* wgt;      // [Kpad][CoutPad], BN scale folded in
+  const float* bias;     // [CoutPad], conv bias + BN shift folded
+  const float* residual; // NHWC, Cout channels, pixel stride resStride; or null
+  int resStride;
+  int relu;
+  int res_after_relu;    // 1: out = relu(acc + bias) + residual  (tracking stems)
+  float* out;
+  int outStride;         // NHWC pixel stride
+  int out_nchw;          // 1: write NCHW [B, Cout, Hout, Wout]
+  const float* offmask;  // DCN: NHWC [.., omStride] raw conv_offset_mask output (27 used)
+  int omStride;
+  int mask_is_logit;     // 1: apply sigmoid to channels 18..26
+  int mode;
+};
+
+int launch_igemm_fp32(const IgemmParams& p, cudaStream_t stream);
+
+// elementwise / data-movement kernels (elementwise.cu)
+int launch_maxpool2(const float* in, float* out, int B, int H, int W, int C, cudaStream_t s);
+int launch_upsample_add(const float* in, const float* wgt_kkc, const float* skip, float* out, int B,
+                        int Hin, int Win, int C, int f, cudaStream_t s);
+// writes the [Kpad x CoutPad] block at column `colOff` of a row-major matrix with leading dimension `ld`
+int launch_pack_conv_weight(const float* w_oihw, const float* scale, float* out, int Cout, int Cin,
+                            int kh, int kw, int CoutPad, int Kpad, int ld, int colOff, cudaStream_t s,
+                            int CinPad = 0);
+int launch_pack_bias(const float* conv_bias, const float* bn_w, const float* bn_b, const float* bn_mean,
+                     const float* bn_var, float* scale_out, float* bias_out, int C, int CPad, float eps,
+                     cudaStream_t s);
+int launch_pack_up_weight(const float* w_c1kk, float* out_kkc, int C, int k, cudaStream_t s);
+int launch_nchw_to_nhwc(const float* in, float* out, int B, int C, int H, int W, int outStride,
+                        int chanOffset, cudaStream_t s);
+int launch_nhwc_to_nchw(const float* in, float* out, int B, int C, int H, int W, int inStride, cudaStream_t s);
+int launch_group_norm_relu(float* x, const float* gamma, const float* beta, int B, int HW, int C,
+                           int stride, int chanOffset, int groups, float eps, float* stats, cudaStream_t s);
+int launch_gru_gates(const float* xi, const float* hh, const float* hprev, float* hout, int B_HW, int C,
+                     int first_step, cudaStream_t s);
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace cp

@@ -1,0 +1,133 @@
+// Stand-alone entry points next to the plan:
+//   cp_dcn_v2_forward -- the `_ext.dcn_v2_forward` replacement (NCHW in / out), built from
+//                        the same implicit-GEMM deformable kernel the plan uses
+//                        (reference: DCNv2/src/cuda/dcn_v2_cuda.cu:42-172).
+//   cp_preprocess     -- batched uint8 HWC frames -> normalised fp32 NCHW network input
+//                        (reference: detectors/base_detector.py:91-148, fix_res branch).
+#include "common.cuh"
+
+namespace cp {
+namespace {
+
+// cv2.warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) with the reference's isotropic
+// fix_res affine, followed by ((v / 255) - mean) / std evaluated in double and
+// rounded once to float32 like the numpy expression at base_detector.py:132.
+// Source coordinates are quantised to 1/32 pixel and the blended value is rounded
+// to an integer, mirroring OpenCV's fixed-point remap (INTER_BITS = 5).
+__global__ void preprocess_kernel(const uint8_t* __restrict__ frames, float* __restrict__ out, int B, int sh,
+                                  int sw, int dh, int dw, float m0, float m1, float m2, float s0, float s1,
+                                  float s2) {
+  const double cx = (double)(float)(sw / 2.0), cy = (double)(float)(sh / 2.0);
+  const double s = (double)(sh > sw ? sh : sw);
+  const double a = s / (double)dw;  // src pixels per dst pixel
+  size_t total = (size_t)B * dh * dw;
+  const float mean[3] = {m0, m1, m2};
+  const float stdv[3] = {s0, s1, s2};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int x = i % dw;
+    size_t t = i / dw;
+    int y = t % dh;
+    int n = t / dh;
+    double sx = ((double)x - dw * 0.5) * a + cx;
+    double sy = ((double)y - dh * 0.5) * a + cy;
+    long qx = lrint(sx * 32.0), qy = lrint(sy * 32.0);
+    int ix = (int)(qx >> 5), iy = (int)(qy >> 5);
+    float fx = (float)(qx & 31) * (1.0f / 32.0f), fy = (float)(qy & 31) * (1.0f / 32.0f);
+    const uint8_t* img = frames + (size_t)n * sh * sw * 3;
+    for (int c = 0; c < 3; ++c) {
+      float v00 = 0, v01 = 0, v10 = 0, v11 = 0;
+      if (iy >= 0 && iy < sh) {
+        if (ix >= 0 && ix < sw) v00 = img[((size_t)iy * sw + ix) * 3 + c];
+        if (ix + 1 >= 0 && ix + 1 < sw) v01 = img[((size_t)iy * sw + ix + 1) * 3 + c];
+      }
+      if (iy + 1 >= 0 && iy + 1 < sh) {
+        if (ix >= 0 && ix < sw) v10 = img[((size_t)(iy + 1) * sw + ix) * 3 + c];
+        if (ix + 1 >= 0 && ix + 1 < sw) v11 = img[((size_t)(iy + 1) * sw + ix + 1) * 3 + c];
+      }
+      float v = (1.f - fy) * ((1.f - fx) * v00 + fx * v01) + fy * ((1.f - fx) * v10 + fx * v11);
+      double u8 = (double)(int)(v + 0.5f);
+      double r = (u8 / 255.0 - (double)mean[c]) / (double)stdv[c];
+      out[(((size_t)n * 3 + c) * dh + y) * dw + x] = (float)r;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace cp
+
+using namespace cp;
+
+extern "C" {
+
+int cp_dcn_v2_forward(const float* input, const float* weight, const float* bias, const float* offset,
+                      const float* mask, float* output, int32_t B, int32_t C, int32_t H, int32_t W, int32_t Co,
+                      void* stream_) {
+  if (!input || !weight || !bias || !offset || !mask || !output)
+    return fail(CP_ERR_INVALID, "cp_dcn_v2_forward: null argument");
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || Co <= 0) return fail(CP_ERR_INVALID, "cp_dcn_v2_forward: bad shape");
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int Cp = round_up(C, 16);
+  const int CoPad = round_up(Co, Co > 32 ? 64 : (Co > 16 ? 32 : 16));
+  const size_t npix = (size_t)B * H * W;
+  const size_t n_x = npix * Cp, n_om = npix * 32, n_w = (size_t)9 * Cp * CoPad, n_b = CoPad;
+  float* scratch = nullptr;
+  CP_CUDA_CHECK(cudaMallocAsync(&scratch, (n_x + n_om + n_w + n_b) * sizeof(float), s));
+  float* x = scratch;
+  float* om = x + n_x;
+  float* wp = om + n_om;
+  float* bp = wp + n_w;
+  int rc = CP_OK;
+  do {
+    if (Cp != C && cudaMemsetAsync(x, 0, n_x * sizeof(float), s) != cudaSuccess) {
+      rc = fail(CP_ERR_CUDA, "cp_dcn_v2_forward: memset");
+      break;
+    }
+    if ((rc = launch_nchw_to_nhwc(input, x, B, C, H, W, Cp, 0, s))) break;
+    if ((rc = launch_nchw_to_nhwc(offset, om, B, 18, H, W, 32, 0, s))) break;
+    if ((rc = launch_nchw_to_nhwc(mask, om, B, 9, H, W, 32, 18, s))) break;
+    if ((rc = launch_pack_conv_weight(weight, nullptr, wp, Co, C, 3, 3, CoPad, 9 * Cp, CoPad, 0, s, Cp))) break;
+    if ((rc = launch_pack_bias(bias, nullptr, nullptr, nullptr, nullptr, nullptr, bp, Co, CoPad, 0.f, s))) break;
+    IgemmParams p{};
+    p.nsrc = 1;
+    p.src[0] = x;
+    p.srcC[0] = Cp;
+    p.srcStride[0] = Cp;
+    p.B = B;
+    p.Hin = p.Hout = H;
+    p.Win = p.Wout = W;
+    p.Cin = Cp;
+    p.Cout = Co;
+    p.CoutPad = CoPad;
+    p.kh = p.kw = 3;
+    p.stride = 1;
+    p.pad = 1;
+    p.Kpad = 9 * Cp;
+    p.wgt = wp;
+    p.bias = bp;
+    p.out = output;
+    p.out_nchw = 1;
+    p.offmask = om;
+    p.omStride = 32;
+    p.mask_is_logit = 0;
+    p.mode = IGEMM_DCN;
+    rc = launch_igemm_fp32(p, s);
+  } while (0);
+  cudaFreeAsync(scratch, s);
+  return rc;
+}
+
+int cp_preprocess(const uint8_t* frames, float* out, int32_t B, int32_t src_h, int32_t src_w, int32_t dst_h,
+                  int32_t dst_w, const float mean[3], const float stdv[3], void* stream_) {
+  if (!frames || !out || !mean || !stdv) return fail(CP_ERR_INVALID, "cp_preprocess: null argument");
+  if (B <= 0 || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0)
+    return fail(CP_ERR_INVALID, "cp_preprocess: bad shape");
+  size_t total = (size_t)B * dst_h * dst_w;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  preprocess_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(frames, out, B, src_h, src_w, dst_h, dst_w, mean[0],
+                                                              mean[1], mean[2], stdv[0], stdv[1], stdv[2]);
+  CP_LAUNCH_CHECK("preprocess_kernel");
+  return CP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,535 @@
+// Per-detection double-precision math of the CenterPose post-network path,
+// written once as __host__ __device__ code: the CUDA decode kernel calls it
+// per thread, and tests/ compile the same header with g++ to check it on the
+// CPU against the oracle (no GPU needed for the math itself).
+//
+// Reference behaviour reproduced (paths relative to /root/reference/src/lib):
+//   utils/pnp/cuboid_objectron.py:83-109   cuboid vertices, float32 arithmetic
+//   utils/pnp/cuboid_pnp_solver.py:143-239 point filtering, cv2.solvePnPGeneric(ITERATIVE),
+//                                          OpenCV -> OpenGL frame change, z < 0 failure
+//   utils/pnp/cuboid_pnp_shell.py:24-93    kps_3d_cam, kps_pnp, visibility gates
+//   detectors/object_pose.py:27-124        soft_nms_nvidia(method=2)
+//   utils/gpfit.py:13-26                   moments()
+// OpenCV's SOLVEPNP_ITERATIVE (third party, see oracle/pnp_ref.py header) =
+// DLT start + Levenberg-Marquardt to the local least-squares minimum.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CP_HD __host__ __device__ __forceinline__
+#define CP_HDN __host__ __device__
+#else
+#define CP_HD inline
+#define CP_HDN inline
+#endif
+
+namespace cp {
+namespace pose {
+
+struct PnPOut {
+  int status;   // cp_pnp_status
+  int n_pts;
+  double loc[3];
+  double quat[4];     // xyzw
+  double reproj;
+  double proj[16];    // 8 x (u, v) projected cuboid, OpenCV pose
+  double kps3d[27];   // 9 x 3: centroid + 8 vertices in the returned frame
+  double kpspnp[18];  // 9 x 2: (mean, 8 projected) / (width, height)
+};
+
+// ---- small dense helpers -------------------------------------------------------
+CP_HD void mat3_mul(const double* A, const double* B, double* C) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+}
+
+CP_HD double mat3_det(const double* A) {
+  return A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
+}
+
+// inverse-transpose of a 3x3 (cofactor matrix / det)
+CP_HD void mat3_inv_t(const double* A, double* Bt) {
+  double d = mat3_det(A);
+  double id = 1.0 / d;
+  Bt[0] = (A[4] * A[8] - A[5] * A[7]) * id;
+  Bt[1] = (A[5] * A[6] - A[3] * A[8]) * id;
+  Bt[2] = (A[3] * A[7] - A[4] * A[6]) * id;
+  Bt[3] = (A[2] * A[7] - A[1] * A[8]) * id;
+  Bt[4] = (A[0] * A[8] - A[2] * A[6]) * id;
+  Bt[5] = (A[1] * A[6] - A[0] * A[7]) * id;
+  Bt[6] = (A[1] * A[5] - A[2] * A[4]) * id;
+  Bt[7] = (A[2] * A[3] - A[0] * A[5]) * id;
+  Bt[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+}
+
+// exp([w]x) -- Rodrigues
+CP_HD void rodrigues(const double* w, double* R) {
+  double th = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  if (th < 1e-300) {
+    for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    return;
+  }
+  double kx = w[0] / th, ky = w[1] / th, kz = w[2] / th;
+  double s = sin(th), c1 = 1.0 - cos(th);
+  double K[9] = {0, -kz, ky, kz, 0, -kx, -ky, kx, 0};
+  double K2[9];
+  mat3_mul(K, K, K2);
+  for (int i = 0; i < 9; ++i) R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + s * K[i] + c1 * K2[i];
+}
+
+// rotation matrix -> unit quaternion xyzw with w >= 0
+CP_HD void mat_to_quat(const double* R, double* q) {
+  double tr = R[0] + R[4] + R[8];
+  double c[4] = {R[0], R[4], R[8], tr};
+  int i = 0;
+  for (int t = 1; t < 4; ++t)
+    if (c[t] > c[i]) i = t;
+  if (i == 3) {
+    q[3] = 1 + tr;
+    q[0] = R[7] - R[5];
+    q[1] = R[2] - R[6];
+    q[2] = R[3] - R[1];
+  } else {
+    int j = (i + 1) % 3, k = (i + 2) % 3;
+    q[i] = 1 - tr + 2 * R[i * 3 + i];
+    q[j] = R[j * 3 + i] + R[i * 3 + j];
+    q[k] = R[k * 3 + i] + R[i * 3 + k];
+    q[3] = R[k * 3 + j] - R[j * 3 + k];
+  }
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  double s = (q[3] < 0 ? -1.0 : 1.0) / n;
+  for (int t = 0; t < 4; ++t) q[t] *= s;
+}
+
+CP_HD void quat_to_mat(const double* q, double* R) {
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  double x = q[0] / n, y = q[1] / n, z = q[2] / n, w = q[3] / n;
+  R[0] = 1 - 2 * (y * y + z * z);
+  R[1] = 2 * (x * y - z * w);
+  R[2] = 2 * (x * z + y * w);
+  R[3] = 2 * (x * y + z * w);
+  R[4] = 1 - 2 * (x * x + z * z);
+  R[5] = 2 * (y * z - x * w);
+  R[6] = 2 * (x * z - y * w);
+  R[7] = 2 * (y * z + x * w);
+  R[8] = 1 - 2 * (x * x + y * y);
+}
+
+// Cuboid3d(scale / scale[1]).get_vertices() -- float32 arithmetic, then widened
+CP_HD void cuboid_vertices(const float* scale, double* V /*[8][3]*/) {
+  float sy = scale[1];
+  float w = (1.0f * scale[0]) / sy, h = (1.0f * scale[1]) / sy, d = (1.0f * scale[2]) / sy;
+  float hx = w / 2.0f, hy = h / 2.0f, hz = d / 2.0f;
+  int t = 0;
+  for (int ix = 0; ix < 2; ++ix)
+    for (int iy = 0; iy < 2; ++iy)
+      for (int iz = 0; iz < 2; ++iz) {
+        V[t * 3 + 0] = (double)(ix ? hx : -hx);
+        V[t * 3 + 1] = (double)(iy ? hy : -hy);
+        V[t * 3 + 2] = (double)(iz ? hz : -hz);
+        ++t;
+      }
+}
+
+// cyclic Jacobi eigen-decomposition of a symmetric N x N matrix (row-major, destroyed);
+// returns the eigenvector of the smallest eigenvalue in `vmin`.
+template <int N>
+CP_HDN void jacobi_min_eigvec(double* A, double* V, double* vmin) {
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) V[i * N + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < N; ++i) {
+      diag += A[i * N + i] * A[i * N + i];
+      for (int j = i + 1; j < N; ++j) off += A[i * N + j] * A[i * N + j];
+    }
+    if (off <= 1e-60 * diag || off == 0.0) break;
+    for (int p = 0; p < N - 1; ++p)
+      for (int q = p + 1; q < N; ++q) {
+        double apq = A[p * N + q];
+        if (apq == 0.0) continue;
+        double app = A[p * N + p], aqq = A[q * N + q];
+        double theta = (aqq - app) / (2.0 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < N; ++k) {
+          double akp = A[k * N + p], akq = A[k * N + q];
+          A[k * N + p] = c * akp - s * akq;
+          A[k * N + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < N; ++k) {
+          double apk = A[p * N + k], aqk = A[q * N + k];
+          A[p * N + k] = c * apk - s * aqk;
+          A[q * N + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < N; ++k) {
+          double vkp = V[k * N + p], vkq = V[k * N + q];
+          V[k * N + p] = c * vkp - s * vkq;
+          V[k * N + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int m = 0;
+  for (int i = 1; i < N; ++i)
+    if (A[i * N + i] < A[m * N + m]) m = i;
+  for (int k = 0; k < N; ++k) vmin[k] = V[k * N + m];
+}
+
+// solve the symmetric positive-definite 6x6 system (A + lam*diag(A)) d = -g by Cholesky; false if not SPD
+CP_HDN bool solve6(const double* A, const double* g, double lam, double* d) {
+  double L[36];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = A[i * 6 + j];
+      if (i == j) s += lam * A[i * 6 + i];
+      for (int k = 0; k < j; ++k) s -= L[i * 6 + k] * L[j * 6 + k];
+      if (i == j) {
+        if (!(s > 0.0)) return false;
+        L[i * 6 + i] = sqrt(s);
+      } else {
+        L[i * 6 + j] = s / L[j * 6 + j];
+      }
+    }
+  double y[6];
+  for (int i = 0; i < 6; ++i) {
+    double s = -g[i];
+    for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * y[k];
+    y[i] = s / L[i * 6 + i];
+  }
+  for (int i = 5; i >= 0; --i) {
+    double s = y[i];
+    for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * d[k];
+    d[i] = s / L[i * 6 + i];
+  }
+  return true;
+}
+
+CP_HD double reproj_cost(const double* X, const double* uv, int n, const double* R, const double* t, double fx,
+                         double fy, double cx, double cy) {
+  double c = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double* x = X + 3 * i;
+    double px = R[0] * x[0] + R[1] * x[1] + R[2] * x[2] + t[0];
+    double py = R[3] * x[0] + R[4] * x[1] + R[5] * x[2] + t[1];
+    double pz = R[6] * x[0] + R[7] * x[1] + R[8] * x[2] + t[2];
+    double du = fx * px / pz + cx - uv[2 * i];
+    double dv = fy * py / pz + cy - uv[2 * i + 1];
+    c += du * du + dv * dv;
+  }
+  return c;
+}
+
+// DLT start (OpenCV findExtrinsicCameraParams2, non-planar branch)
+CP_HDN void dlt_init(const double* X, const double* uv, int n, double fx, double fy, double cx, double cy, double* R,
+                     double* t) {
+  double A[144];
+  for (int i = 0; i < 144; ++i) A[i] = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double x = (uv[2 * i] - cx) / fx, y = (uv[2 * i + 1] - cy) / fy;
+    double Xi = X[3 * i], Yi = X[3 * i + 1], Zi = X[3 * i + 2];
+    double r1[12] = {Xi, Yi, Zi, 1, 0, 0, 0, 0, -x * Xi, -x * Yi, -x * Zi, -x};
+    double r2[12] = {0, 0, 0, 0, Xi, Yi, Zi, 1, -y * Xi, -y * Yi, -y * Zi, -y};
+    for (int a = 0; a < 12; ++a)
+      for (int b = 0; b < 12; ++b) A[a * 12 + b] += r1[a] * r1[b] + r2[a] * r2[b];
+  }
+  double V[144], p[12];
+  jacobi_min_eigvec<12>(A, V, p);
+  double RR[9] = {p[0], p[1], p[2], p[4], p[5], p[6], p[8], p[9], p[10]};
+  double tt[3] = {p[3], p[7], p[11]};
+  if (mat3_det(RR) < 0) {
+    for (int i = 0; i < 9; ++i) RR[i] = -RR[i];
+    for (int i = 0; i < 3; ++i) tt[i] = -tt[i];
+  }
+  double sc = 0.0;
+  for (int i = 0; i < 9; ++i) sc += RR[i] * RR[i];
+  sc = sqrt(sc);
+  // orthogonal polar factor U V^T of RR by Newton iteration X <- (X + X^-T) / 2
+  double Xm[9];
+  for (int i = 0; i < 9; ++i) Xm[i] = RR[i] / sc * 1.7320508075688772;
+  for (int it = 0; it < 40; ++it) {
+    double Xit[9];
+    mat3_inv_t(Xm, Xit);
+    double diff = 0.0;
+    for (int i = 0; i < 9; ++i) {
+      double nx = 0.5 * (Xm[i] + Xit[i]);
+      diff += (nx - Xm[i]) * (nx - Xm[i]);
+      Xm[i] = nx;
+    }
+    if (diff < 1e-30) break;
+  }
+  for (int i = 0; i < 9; ++i) R[i] = Xm[i];
+  double f = 1.7320508075688772 / sc;  // ||R_orth||_F / ||RR||_F
+  for (int i = 0; i < 3; ++i) t[i] = tt[i] * f;
+}
+
+// Levenberg-Marquardt on the pixel reprojection error, update R <- exp([dw]x) R, t <- t + dt
+CP_HDN double refine_lm(const double* X, const double* uv, int n, double fx, double fy, double cx, double cy, double* R,
+                        double* t) {
+  double lam = 1e-3;
+  double cost = reproj_cost(X, uv, n, R, t, fx, fy, cx, cy);
+  for (int iter = 0; iter < 200; ++iter) {
+    double A[36], g[6];
+    for (int i = 0; i < 36; ++i) A[i] = 0.0;
+    for (int i = 0; i < 6; ++i) g[i] = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double* x = X + 3 * i;
+      double qx = R[0] * x[0] + R[1] * x[1] + R[2] * x[2];
+      double qy = R[3] * x[0] + R[4] * x[1] + R[5] * x[2];
+      double qz = R[6] * x[0] + R[7] * x[1] + R[8] * x[2];
+      double px = qx + t[0], py = qy + t[1], pz = qz + t[2];
+      double iz = 1.0 / pz;
+      double du[3] = {fx * iz, 0.0, -fx * px * iz * iz};
+      double dv[3] = {0.0, fy * iz, -fy * py * iz * iz};
+      // dP/dw = -[q]x  ->  row . (-[q]x) = (q x row)^T ... written out:
+      double Ju[6], Jv[6];
+      // -[q]x = [[0, qz, -qy], [-qz, 0, qx], [qy, -qx, 0]]
+      Ju[0] = du[1] * (-qz) + du[2] * qy;
+      Ju[1] = du[0] * qz + du[2] * (-qx);
+      Ju[2] = du[0] * (-qy) + du[1] * qx;
+      Jv[0] = dv[1] * (-qz) + dv[2] * qy;
+      Jv[1] = dv[0] * qz + dv[2] * (-qx);
+      Jv[2] = dv[0] * (-qy) + dv[1] * qx;
+      for (int k = 0; k < 3; ++k) {
+        Ju[3 + k] = du[k];
+        Jv[3 + k] = dv[k];
+      }
+      double ru = fx * px * iz + cx - uv[2 * i];
+      double rv = fy * py * iz + cy - uv[2 * i + 1];
+      for (int a = 0; a < 6; ++a) {
+        g[a] += Ju[a] * ru + Jv[a] * rv;
+        for (int b = 0; b <= a; ++b) A[a * 6 + b] += Ju[a] * Ju[b] + Jv[a] * Jv[b];
+      }
+    }
+    for (int a = 0; a < 6; ++a)
+      for (int b = a + 1; b < 6; ++b) A[a * 6 + b] = A[b * 6 + a];
+    bool improved = false;
+    double d[6], Rn[9], tn[3], cn = 0.0;
+    for (int tr = 0; tr < 30; ++tr) {
+      if (solve6(A, g, lam, d)) {
+        double E[9];
+        rodrigues(d, E);
+        mat3_mul(E, R, Rn);
+        for (int k = 0; k < 3; ++k) tn[k] = t[k] + d[3 + k];
+        cn = reproj_cost(X, uv, n, Rn, tn, fx, fy, cx, cy);
+        if (cn == cn && cn <= cost && fabs(cn) < 1e300) {
+          improved = true;
+          break;
+        }
+      }
+      lam *= 10.0;
+    }
+    if (!improved) break;
+    double step = 0.0;
+    for (int k = 0; k < 6; ++k) step += d[k] * d[k];
+    step = sqrt(step);
+    for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+    for (int k = 0; k < 3; ++k) t[k] = tn[k];
+    double dec = cost - cn;
+    cost = cn;
+    lam = lam * 0.1;
+    if (lam < 1e-12) lam = 1e-12;
+    if (step < 1e-13 || dec <= 1e-28 * (cost > 1e-300 ? cost : 1e-300)) break;
+  }
+  return cost;
+}
+
+// solve_pnp + pnp_shell for one detection.
+//   pts: n_in x 2 image points (n_in = 8 or 16; 3-D vertex of point i is V[i / (n_in/8)])
+//   Kc:  camera matrix row-major; width/height: image size for kps_pnp normalisation
+//   visible_thresh: 6 / 3 / 0 (see cp_decode_params)
+CP_HDN void solve_and_shell(const double* pts, int n_in, const float* obj_scale, const double* Kc, double width,
+                            double height, int visible_thresh, int opencv_return, PnPOut* o) {
+  double V[24];
+  cuboid_vertices(obj_scale, V);
+  double X[48], uv[32];
+  int n = 0;
+  const int per = n_in / 8;
+  for (int i = 0; i < n_in; ++i) {
+    if (pts[2 * i] < -5000.0 || pts[2 * i + 1] < -5000.0) continue;
+    uv[2 * n] = pts[2 * i];
+    uv[2 * n + 1] = pts[2 * i + 1];
+    const double* v = V + 3 * (i / per);
+    X[3 * n] = v[0];
+    X[3 * n + 1] = v[1];
+    X[3 * n + 2] = v[2];
+    ++n;
+  }
+  o->n_pts = n;
+  o->status = 4;  // CP_PNP_FEW_POINTS
+  if (n < 6) return;
+  const double fx = Kc[0], fy = Kc[4], cx = Kc[2], cy = Kc[5];
+  double R[9], t[3];
+  dlt_init(X, uv, n, fx, fy, cx, cy, R, t);
+  double cost = refine_lm(X, uv, n, fx, fy, cx, cy, R, t);
+  bool finite = (cost == cost) && fabs(cost) < 1e300;
+  for (int i = 0; i < 9; ++i) finite = finite && (R[i] == R[i]);
+  for (int i = 0; i < 3; ++i) finite = finite && (t[i] == t[i]);
+  if (!finite) {
+    o->status = 5;
+    return;
+  }
+  o->reproj = sqrt(cost / (2.0 * n));
+  for (int i = 0; i < 8; ++i) {
+    const double* x = V + 3 * i;
+    double px = R[0] * x[0] + R[1] * x[1] + R[2] * x[2] + t[0];
+    double py = R[3] * x[0] + R[4] * x[1] + R[5] * x[2] + t[1];
+    double pz = R[6] * x[0] + R[7] * x[1] + R[8] * x[2] + t[2];
+    o->proj[2 * i] = fx * px / pz + cx;
+    o->proj[2 * i + 1] = fy * py / pz + cy;
+  }
+  if (t[2] < 0.0) {
+    o->status = 3;  // CP_PNP_BEHIND
+    return;
+  }
+  double Rr[9], tr[3];
+  if (opencv_return) {
+    for (int i = 0; i < 9; ++i) Rr[i] = R[i];
+    for (int i = 0; i < 3; ++i) tr[i] = t[i];
+  } else {
+    // M = [[0,1,0],[1,0,0],[0,0,-1]]
+    for (int j = 0; j < 3; ++j) {
+      Rr[j] = R[3 + j];
+      Rr[3 + j] = R[j];
+      Rr[6 + j] = -R[6 + j];
+    }
+    tr[0] = t[1];
+    tr[1] = t[0];
+    tr[2] = -t[2];
+  }
+  mat_to_quat(Rr, o->quat);
+  for (int i = 0; i < 3; ++i) o->loc[i] = tr[i];
+  // kps_3d_cam = [mean, R(q) V + loc]
+  double Rq[9];
+  quat_to_mat(o->quat, Rq);
+  double m3[3] = {0, 0, 0};
+  for (int i = 0; i < 8; ++i) {
+    const double* x = V + 3 * i;
+    for (int k = 0; k < 3; ++k) {
+      double v = Rq[k * 3] * x[0] + Rq[k * 3 + 1] * x[1] + Rq[k * 3 + 2] * x[2] + tr[k];
+      o->kps3d[3 * (i + 1) + k] = v;
+      m3[k] += v;
+    }
+  }
+  for (int k = 0; k < 3; ++k) o->kps3d[k] = m3[k] / 8.0;
+  double mu = 0, mv = 0;
+  for (int i = 0; i < 8; ++i) {
+    mu += o->proj[2 * i];
+    mv += o->proj[2 * i + 1];
+  }
+  o->kpspnp[0] = (mu / 8.0) / width;
+  o->kpspnp[1] = (mv / 8.0) / height;
+  for (int i = 0; i < 8; ++i) {
+    o->kpspnp[2 * (i + 1)] = o->proj[2 * i] / width;
+    o->kpspnp[2 * (i + 1) + 1] = o->proj[2 * i + 1] / height;
+  }
+  o->status = 1;
+  if (visible_thresh > 0) {
+    int nv = 0;
+    for (int i = 0; i < 9; ++i) {
+      double a = o->kpspnp[2 * i], b = o->kpspnp[2 * i + 1];
+      if (a < 0 || a > 1 || b < 0 || b > 1) ++nv;
+    }
+    if (nv >= visible_thresh) o->status = 2;
+  }
+  if (!(o->kpspnp[0] > 0 && o->kpspnp[0] < 1 && o->kpspnp[1] > 0 && o->kpspnp[1] < 1)) o->status = 2;
+}
+
+// ---- Gaussian soft-NMS (object_pose.py:27-124, method=2, sigma=0.5) ----------------
+// bbox: n x 4 doubles, score: n doubles, perm: n ints (identity on entry).  On exit the
+// first return-value entries of perm/score are the survivors in the reference's order.
+CP_HDN int soft_nms(double* bbox, double* score, int* perm, int n, double threshold) {
+  int N = n;
+  for (int i = 0; i < N; ++i) {
+    int maxpos = i;
+    double maxscore = score[i];
+    for (int pos = i + 1; pos < N; ++pos)
+      if (maxscore < score[pos]) {
+        maxscore = score[pos];
+        maxpos = pos;
+      }
+    if (maxpos != i) {
+      for (int k = 0; k < 4; ++k) {
+        double tmp = bbox[4 * i + k];
+        bbox[4 * i + k] = bbox[4 * maxpos + k];
+        bbox[4 * maxpos + k] = tmp;
+      }
+      double ts = score[i];
+      score[i] = score[maxpos];
+      score[maxpos] = ts;
+      int tp = perm[i];
+      perm[i] = perm[maxpos];
+      perm[maxpos] = tp;
+    }
+    double tx1 = bbox[4 * i], ty1 = bbox[4 * i + 1], tx2 = bbox[4 * i + 2], ty2 = bbox[4 * i + 3];
+    int pos = i + 1;
+    while (pos < N) {
+      double x1 = bbox[4 * pos], y1 = bbox[4 * pos + 1], x2 = bbox[4 * pos + 2], y2 = bbox[4 * pos + 3];
+      double area = (x2 - x1 + 1) * (y2 - y1 + 1);
+      double iw = fmin(tx2, x2) - fmax(tx1, x1) + 1;
+      if (iw > 0) {
+        double ih = fmin(ty2, y2) - fmax(ty1, y1) + 1;
+        if (ih > 0) {
+          double ua = (tx2 - tx1 + 1) * (ty2 - ty1 + 1) + area - iw * ih;
+          double ov = iw * ih / ua;
+          double weight = exp(-(ov * ov) / 0.5);
+          score[pos] = weight * score[pos];
+          if (score[pos] < threshold) {
+            for (int k = 0; k < 4; ++k) bbox[4 * pos + k] = bbox[4 * (N - 1) + k];
+            score[pos] = score[N - 1];
+            int tp = perm[pos];
+            perm[pos] = perm[N - 1];
+            perm[N - 1] = tp;
+            N -= 1;
+            pos -= 1;
+          }
+        }
+      }
+      pos += 1;
+    }
+  }
+  return N;
+}
+
+// ---- gpfit.moments on a (nr x nc) window of doubles (row-major, ld = nc) ----------------
+// returns false when the reference would raise (empty window / NaN centroid)
+CP_HDN bool moments(const double* w, int nr, int nc, double* height, double* x, double* y, double* wx, double* wy) {
+  if (nr <= 0 || nc <= 0) return false;
+  double total = 0, sx = 0, sy = 0, mx = w[0];
+  for (int r = 0; r < nr; ++r)
+    for (int c = 0; c < nc; ++c) {
+      double v = w[r * nc + c];
+      total += v;
+      sx += r * v;
+      sy += c * v;
+      if (v > mx) mx = v;
+    }
+  double xc = sx / total, yc = sy / total;
+  if (!(xc == xc) || !(yc == yc)) return false;
+  int iy = (int)yc, ix = (int)xc;  // truncation toward zero like int()
+  if (iy < 0) iy += nc;            // python negative index
+  if (ix < 0) ix += nr;
+  if (iy < 0 || iy >= nc || ix < 0 || ix >= nr) return false;
+  double num = 0, den = 0;
+  for (int r = 0; r < nr; ++r) {
+    double v = w[r * nc + iy];
+    num += fabs((r - yc) * (r - yc) * v);
+    den += v;
+  }
+  *wx = sqrt(num / den);  // abs() is applied to the summed numerator in the reference; all terms share the sign of v
+  num = 0;
+  den = 0;
+  for (int c = 0; c < nc; ++c) {
+    double v = w[ix * nc + c];
+    num += fabs((c - xc) * (c - xc) * v);
+    den += v;
+  }
+  *wy = sqrt(num / den);
+  *height = mx;
+  *x = xc;
+  *y = yc;
+  return true;
+}
+
+}  // namespace pose
+}  // namespace cp

@@ -1,0 +1,301 @@
+"""`ObjectPoseDetector` on the B200-native hot path -- the drop-in for
+/root/reference/src/lib/detectors/{base_detector,object_pose,detector_factory}.py.
+
+`run()` keeps the reference's one-image semantics and its 12-key return dict
+(base_detector.py:390-772): load -> pre_process (cv2, identical to the
+reference) -> network -> decode -> post_process -> merge -> PnP.  Everything
+after pre_process runs in libcenterpose_b200.so; the only host work left is
+rebuilding the reference's Python result structures from the fixed-shape pose
+records (`records_to_results`).  `run_batch()` is the batched entry point the
+reference does not have (B = 32 / 256 configurations of BASELINE.json).
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import decode_params, decode_pnp, make_meta, preprocess
+from .model import create_model, load_model
+
+
+# ----------------------------------------------------------------------------- records -> reference structures
+def record_to_result(rec):
+    """One CP_POSE_RECORD row -> the reference's per-detection dict
+    (post_process.py:27-63 + cuboid_pnp_shell.py:27-54)."""
+    L = _lib
+    r = np.asarray(rec, np.float32)
+    d = {
+        "score": float(r[L.P_SCORE]),
+        "cls": int(r[L.P_CLS]),
+        "obj_scale": r[L.P_OBJ_SCALE:L.P_OBJ_SCALE + 3].copy(),
+        "obj_scale_uncertainty": r[L.P_OBJ_SCALE_UNC:L.P_OBJ_SCALE_UNC + 3].copy(),
+        "kps_displacement_std": r[L.P_KPS_DISP_STD:L.P_KPS_DISP_STD + 16].copy(),
+        "bbox": r[L.P_BBOX:L.P_BBOX + 4].astype(np.float64),
+        "ct": [float(r[L.P_CT]), float(r[L.P_CT + 1])],
+        "kps": r[L.P_KPS:L.P_KPS + 16].astype(np.float64),
+        "tracking": r[L.P_TRACKING:L.P_TRACKING + 2].copy(),
+        "tracking_hp": r[L.P_TRACKING_HP:L.P_TRACKING_HP + 16].copy(),
+        "kps_displacement_mean": r[L.P_KPS_DISP_MEAN:L.P_KPS_DISP_MEAN + 16].astype(np.float64),
+        "kps_heatmap_mean": r[L.P_KPS_HM_MEAN:L.P_KPS_HM_MEAN + 16].astype(np.float64),
+        "kps_heatmap_std": r[L.P_KPS_HM_STD:L.P_KPS_HM_STD + 16].copy(),
+        "kps_heatmap_height": r[L.P_KPS_HM_HEIGHT:L.P_KPS_HM_HEIGHT + 8].copy(),
+    }
+    st = int(r[L.P_STATUS])
+    d["pnp_status"] = st
+    if st in (L.PNP_OK, L.PNP_INVISIBLE):
+        d["location"] = [float(v) for v in r[L.P_LOCATION:L.P_LOCATION + 3]]
+        d["quaternion_xyzw"] = r[L.P_QUAT:L.P_QUAT + 4].astype(np.float64)
+        d["projected_cuboid"] = r[L.P_PROJ_CUBOID:L.P_PROJ_CUBOID + 16].astype(np.float64).reshape(8, 2)
+        d["kps_3d_cam"] = r[L.P_KPS_3D_CAM:L.P_KPS_3D_CAM + 27].astype(np.float64).reshape(9, 3)
+        d["kps_pnp"] = r[L.P_KPS_PNP:L.P_KPS_PNP + 18].astype(np.float64).reshape(9, 2)
+        d["reprojection_error"] = float(r[L.P_REPROJ])
+    return d
+
+
+def records_to_results(poses, n_valid, width, height):
+    """poses [K,192], n_valid -> (results ndarray-of-dicts, boxes list) exactly
+    shaped like base_detector.py:498,548-654."""
+    res = [record_to_result(poses[i]) for i in range(int(n_valid))]
+    boxes = []
+    for d in res:
+        if d["pnp_status"] == _lib.PNP_OK:
+            kp = d["kps"].reshape(-1, 2)
+            po = np.vstack([kp.mean(0, keepdims=True), kp]).copy()
+            po[:, 0] /= width
+            po[:, 1] /= height
+            boxes.append((d["kps_pnp"], d["kps_3d_cam"], np.array(d["obj_scale"]), po, d))
+    return np.array(res, dtype=object), boxes
+
+
+def dets_to_dict(dets):
+    """dets [B,K,128] -> the 13 arrays of decode.py:348-361."""
+    L = _lib
+    a = np.asarray(dets, np.float32)
+    f = lambda off, n: a[..., off:off + n].copy()
+    return {
+        "bboxes": f(L.D_BBOX, 4), "scores": f(L.D_SCORE, 1), "kps": f(L.D_KPS, 16), "clses": f(L.D_CLS, 1),
+        "obj_scale": f(L.D_OBJ_SCALE, 3), "obj_scale_uncertainty": f(L.D_OBJ_SCALE_UNC, 3),
+        "tracking": f(L.D_TRACKING, 2), "tracking_hp": f(L.D_TRACKING_HP, 16),
+        "kps_displacement_mean": f(L.D_KPS_DISP_MEAN, 16), "kps_displacement_std": f(L.D_KPS_DISP_STD, 16),
+        "kps_heatmap_mean": f(L.D_KPS_HM_MEAN, 16), "kps_heatmap_std": f(L.D_KPS_HM_STD, 16),
+        "kps_heatmap_height": f(L.D_KPS_HM_HEIGHT, 8),
+    }
+
+
+def affine_from_center_scale(c, s, out_w, out_h, inv=False):
+    """The rot=0 case of utils/image.py:35-68: three float32 control points
+    (centre, centre + (0, -s/2), and the perpendicular third point) handed to
+    cv2.getAffineTransform, which is what the reference calls."""
+    import cv2
+    src = np.zeros((3, 2), np.float32)
+    dst = np.zeros((3, 2), np.float32)
+    src[0] = c
+    src[1] = np.asarray(c, np.float32) + np.array([0, s * -0.5], np.float32)
+    dst[0] = [out_w * 0.5, out_h * 0.5]
+    dst[1] = np.array([out_w * 0.5, out_h * 0.5], np.float32) + np.array([0, out_w * -0.5], np.float32)
+    for p in (src, dst):
+        d = p[0] - p[1]
+        p[2] = p[1] + np.array([-d[1], d[0]], np.float32)
+    return cv2.getAffineTransform(dst, src) if inv else cv2.getAffineTransform(src, dst)
+
+
+# ----------------------------------------------------------------------------- detector
+class ObjectPoseDetector(object):
+    def __init__(self, opt, model=None):
+        if opt.gpus[0] < 0:
+            raise RuntimeError("centerpose_b200 runs on a CUDA device only (--gpus -1 is the reference's CPU path)")
+        opt.device = torch.device("cuda")
+        print("Creating model...")
+        self.model = model if model is not None else create_model(opt.arch, opt.heads, opt.head_conv, opt)
+        if getattr(opt, "load_model", ""):
+            self.model = load_model(self.model, opt.load_model)
+        self.model = self.model.to(opt.device)
+        self.model.eval()
+        self.mean = np.array(opt.mean, dtype=np.float32).reshape(1, 1, 3)
+        self.std = np.array(opt.std, dtype=np.float32).reshape(1, 1, 3)
+        self.max_per_image = 100
+        self.num_classes = opt.num_classes
+        self.scales = opt.test_scales
+        self.opt = opt
+        self.pause = True
+        self.pre_images = None
+        self.tracker = None
+        self.flip_idx = getattr(opt, "flip_idx", None)
+        if getattr(opt, "tracking_task", False) or getattr(opt, "refined_Kalman", False):
+            # Tracker state (utils/tracker.py) is CPU, per-video and needs filterpy: SURVEY.md row f-2.
+            self.tracker = None
+
+    # base_detector.py:91-148 -- unchanged cv2 pre-processing (host side)
+    def pre_process(self, image, scale, input_meta={}):
+        import cv2
+        height, width = image.shape[0:2]
+        new_height = int(height * scale)
+        new_width = int(width * scale)
+        if self.opt.fix_short > 0:
+            raise NotImplementedError("fix_short pre-processing is not on the supported path")
+        if not self.opt.fix_res:
+            raise NotImplementedError("keep_res pre-processing is not on the supported path")
+        inp_height, inp_width = self.opt.input_h, self.opt.input_w
+        c = np.array([new_width / 2., new_height / 2.], dtype=np.float32)
+        s = max(height, width) * 1.0
+        trans_input = affine_from_center_scale(c, s, inp_width, inp_height)
+        out_height = inp_height // self.opt.down_ratio
+        out_width = inp_width // self.opt.down_ratio
+        resized = cv2.resize(image, (new_width, new_height))
+        inp = cv2.warpAffine(resized, trans_input, (inp_width, inp_height), flags=cv2.INTER_LINEAR)
+        inp = ((inp / 255. - self.mean) / self.std).astype(np.float32)
+        images = torch.from_numpy(inp.transpose(2, 0, 1).reshape(1, 3, inp_height, inp_width))
+        meta = {"c": c, "s": s, "height": height, "width": width, "out_height": out_height,
+                "out_width": out_width, "inp_height": inp_height, "inp_width": inp_width,
+                "trans_input": trans_input}
+        for k in ("pre_dets", "camera_matrix", "id"):
+            if k in input_meta:
+                meta[k] = input_meta[k]
+        return images, meta
+
+    def _meta_tensor(self, meta, batch=1):
+        cam = meta.get("camera_matrix")
+        if cam is None:
+            if self.opt.use_pnp:
+                raise ValueError("meta_inp['camera_matrix'] is required when opt.use_pnp is set (demo.py:141-147)")
+            cam = np.eye(3)
+        return make_meta(batch, meta["c"], meta["s"], meta["width"], meta["height"], cam)
+
+    def process(self, images, pre_images=None, pre_hms=None, pre_hm_hp=None, pre_inds=None, return_time=False,
+                meta=None):
+        """object_pose.py:131-165: network + sigmoid + decode.  Returns
+        (output, dets[, forward_time]); the pose records of the fused stage are
+        kept on `self._last` for post_process / merge / PnP."""
+        torch.cuda.synchronize()
+        output = self.model(images, pre_images, pre_hms, pre_hm_hp)[-1]
+        torch.cuda.synchronize()
+        forward_time = time.time()
+        prm = decode_params(self.opt)
+        metat = self._meta_tensor(meta if meta is not None else self._dummy_meta(images), images.shape[0])
+        dets, poses, n_valid = decode_pnp(output, metat.to(images.device), prm, want_dets=True)
+        output["hm"] = output["hm"].sigmoid_()
+        if self.opt.hm_hp and not self.opt.mse_loss:
+            output["hm_hp"] = output["hm_hp"].sigmoid_()
+        output.update({"pre_inds": pre_inds})
+        self._last = (poses.cpu().numpy(), n_valid.cpu().numpy())
+        dets = dets_to_dict(dets.cpu().numpy())
+        if return_time:
+            return output, dets, forward_time
+        return output, dets
+
+    def _dummy_meta(self, images):
+        h, w = images.shape[2], images.shape[3]
+        return {"c": np.array([w / 2., h / 2.], np.float32), "s": float(max(h, w)), "width": w, "height": h,
+                "camera_matrix": np.eye(3)}
+
+    def run(self, image_or_path_or_tensor, filename=None, meta_inp={}, preprocessed_flag=False):
+        import cv2
+        load_time, pre_time, net_time, dec_time, post_time = 0, 0, 0, 0, 0
+        merge_time, track_time, pnp_time, tot_time = 0, 0, 0, 0
+        if len(self.scales) != 1 or self.scales[0] != 1.0:
+            raise NotImplementedError("multi-scale testing merges detections on the host; only test_scales=[1] is supported")
+        if getattr(self.opt, "tracking_task", False) or getattr(self.opt, "refined_Kalman", False):
+            raise NotImplementedError("tracker state (utils/tracker.py) is not on the accelerated path yet; "
+                                      "use run_batch(..., pre_images=, pre_hms=, pre_hm_hp=) for the two-frame network")
+        start_time = time.time()
+        pre_processed = preprocessed_flag
+        if isinstance(image_or_path_or_tensor, np.ndarray):
+            image = image_or_path_or_tensor
+            if filename is not None:
+                image_or_path_or_tensor = filename
+        elif type(image_or_path_or_tensor) == type(""):
+            image = cv2.imread(image_or_path_or_tensor)
+        else:
+            image = image_or_path_or_tensor["image"][0].numpy()
+            pre_processed = True
+        loaded_time = time.time()
+        load_time += loaded_time - start_time
+
+        scale = self.scales[0]
+        if not pre_processed:
+            images, meta = self.pre_process(image, scale, meta_inp)
+        else:
+            images = torch.from_numpy(np.expand_dims(image, axis=0))
+            meta = meta_inp
+        images = images.to(self.opt.device)
+        torch.cuda.synchronize()
+        pre_process_time = time.time()
+        pre_time += pre_process_time - loaded_time
+
+        output, dets, forward_time = self.process(images, None, None, None, None, return_time=True, meta=meta)
+        torch.cuda.synchronize()
+        net_time += forward_time - pre_process_time
+        decode_time = time.time()
+        dec_time += decode_time - forward_time
+
+        # post_process + merge + PnP already happened inside cp_decode_pnp; unpack the records
+        poses, n_valid = self._last
+        results, boxes = records_to_results(poses[0], n_valid[0], meta["width"], meta["height"])
+        if not self.opt.use_pnp:
+            boxes = []
+        post_process_time = time.time()
+        post_time += post_process_time - decode_time
+        merge_outputs_time = pnp_process_time = post_process_time
+        end_time = time.time()
+        track_time += end_time - pnp_process_time
+        tot_time += end_time - start_time
+
+        dict_out = {"camera_data": [], "objects": []}
+        if "camera_matrix" in meta:
+            dict_out["camera_data"] = np.asarray(meta["camera_matrix"]).tolist()
+        for box in boxes:
+            b = box[4]
+            obj = {
+                "class": self.opt.c, "ct": b["ct"], "bbox": np.array(b["bbox"]).tolist(), "confidence": b["score"],
+                "kps_displacement_mean": b["kps_displacement_mean"].tolist(),
+                "kps_heatmap_mean": b["kps_heatmap_mean"].tolist(),
+                "kps_heatmap_std": b["kps_heatmap_std"].tolist(),
+                "kps_heatmap_height": b["kps_heatmap_height"].tolist(),
+                "obj_scale": b["obj_scale"].tolist(),
+            }
+            if self.opt.use_pnp:
+                if "location" in b:
+                    obj["location"] = b["location"]
+                    obj["quaternion_xyzw"] = b["quaternion_xyzw"].tolist()
+                if "kps_pnp" in b:
+                    obj["kps_pnp"] = b["kps_pnp"].tolist()
+                    obj["kps_3d_cam"] = b["kps_3d_cam"].tolist()
+            dict_out["objects"].append(obj)
+        self.last_dict_out = dict_out
+        return {"results": results, "boxes": boxes, "output": output, "tot": tot_time, "load": load_time,
+                "pre": pre_time, "net": net_time, "dec": dec_time, "post": post_time, "merge": merge_time,
+                "pnp": pnp_time, "track": track_time}
+
+    # ------------------------------------------------------------------ batched API (not in the reference)
+    def run_batch(self, frames, camera_matrix, pre_images=None, pre_hms=None, pre_hm_hp=None, to_host=True):
+        """frames: uint8 [B,H,W,3] (numpy / pinned CPU tensor / CUDA tensor) or a
+        pre-processed fp32 [B,3,h,w] CUDA tensor.  One native cp_infer call for the
+        whole batch.  Returns (poses [B,K,192], n_valid [B]) -- on the host when
+        `to_host`, else as CUDA tensors."""
+        dev = self.opt.device
+        if isinstance(frames, np.ndarray):
+            frames = torch.from_numpy(frames)
+        if frames.dtype == torch.uint8:
+            B, sh, sw, _ = frames.shape
+            fr = frames.to(dev, non_blocking=True)
+            x = preprocess(fr, self.opt.input_h, self.opt.input_w, self.opt.mean, self.opt.std)
+            c, s = np.array([sw / 2., sh / 2.], np.float32), float(max(sh, sw))
+            iw, ih = sw, sh
+        else:
+            x = frames.to(dev)
+            B, _, ih, iw = x.shape
+            c, s = np.array([iw / 2., ih / 2.], np.float32), float(max(ih, iw))
+        meta = make_meta(B, c, s, iw, ih, camera_matrix).to(dev, non_blocking=True)
+        eng = self.model.engine(B, x.shape[2], x.shape[3], x.device)
+        prm = decode_params(self.opt)
+        _, poses, n_valid = eng.infer(x, meta, prm, pre_images, pre_hms, pre_hm_hp)
+        if to_host:
+            return poses.cpu().numpy(), n_valid.cpu().numpy()
+        return poses, n_valid
+
+    def reset_tracking(self):
+        self.pre_images = None
+
+
+detector_factory = {"object_pose": ObjectPoseDetector}

@@ -1,0 +1,254 @@
+/*
+ * centerpose_b200.h -- C ABI of libcenterpose_b200.so (sm_100a).
+ *
+ * The drop-in boundary for the CenterPose inference hot path
+ * (SURVEY.md section 8b).  Plain pointers and sizes only; every function
+ * returns 0 on success or a negative cp_status, and cp_last_error() returns a
+ * thread-local message.  The library never allocates in steady state: the
+ * caller (PyTorch on the Python side) owns every input / output buffer, a
+ * plan owns its packed weights and activation arena.  All device work is
+ * enqueued on the cudaStream_t passed as `stream` (pass
+ * torch.cuda.current_stream().cuda_stream); no call synchronises the device
+ * unless documented.
+ *
+ * Reference interfaces each entry point replaces (paths relative to
+ * /root/reference/src/lib):
+ *
+ *   cp_plan_create / cp_plan_load_weights / cp_plan_destroy
+ *       models/model.py:26-31 create_model(), :34-87 load_model()
+ *       models/networks/pose_dla_dcn.py:457-521 DLASeg.__init__, :573-590 factories
+ *   cp_forward
+ *       models/networks/pose_dla_dcn.py:523-570 DLASeg.forward
+ *       (DLA :310-322, DLAUp :437-443, IDAUp :411-417, DeformConv :377-389,
+ *        convGRU.py:72-94, GN.py:4-9)
+ *   cp_dcn_v2_forward
+ *       models/networks/DCNv2/src/vision.cpp:4-9  _ext.dcn_v2_forward
+ *       models/networks/DCNv2/src/dcn_v2.h:9-45, src/cuda/dcn_v2_cuda.cu:42-172,
+ *       src/cuda/dcn_v2_im2col_cuda.cu:125-195
+ *   cp_decode_pnp
+ *       detectors/object_pose.py:131-165 process() [sigmoid + object_pose_decode]
+ *       models/decode.py:72-375, utils/post_process.py:12-68,
+ *       detectors/object_pose.py:184-197 merge_outputs + :27-124 soft_nms_nvidia,
+ *       detectors/base_detector.py:548-654 point assembly + pnp_shell,
+ *       utils/pnp/cuboid_pnp_shell.py:11-93, utils/pnp/cuboid_pnp_solver.py:91-239
+ *   cp_infer
+ *       detectors/base_detector.py:473-654 (process -> post_process -> merge -> PnP)
+ *   cp_preprocess
+ *       detectors/base_detector.py:91-148 pre_process (resize + affine warp + normalise)
+ */
+#ifndef CENTERPOSE_B200_H_
+#define CENTERPOSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CP_ABI_VERSION 1
+
+/* ---- status codes --------------------------------------------------------- */
+enum cp_status {
+  CP_OK = 0,
+  CP_ERR_INVALID = -1,      /* bad argument / unsupported configuration        */
+  CP_ERR_CUDA = -2,         /* a CUDA runtime call failed (message has details) */
+  CP_ERR_NOT_LOADED = -3,   /* plan used before cp_plan_load_weights           */
+  CP_ERR_MISSING_KEY = -4,  /* a state_dict key the plan needs was not supplied */
+  CP_ERR_SHAPE = -5         /* tensor element count does not match the plan     */
+};
+
+/* ---- architecture / precision -------------------------------------------- */
+enum cp_arch {
+  CP_ARCH_DLA34 = 0,        /* 'dla_34'   : DLA-34 + DCNv2            (model.py:19) */
+  CP_ARCH_DLAV1_34 = 1      /* 'dlav1_34' : + convGRU + GroupNorm heads (model.py:20) */
+};
+
+enum cp_precision {
+  CP_PREC_FP32 = 0,         /* fp32 operands and accumulation on CUDA cores (parity mode)      */
+  CP_PREC_TF32X3 = 1,       /* tcgen05 kind::tf32, 3-term split: fp32-equivalent tensor cores  */
+  CP_PREC_BF16 = 2          /* tcgen05 kind::f16 bf16 operands, fp32 accumulation (fast mode)  */
+};
+
+#define CP_MAX_HEADS 16
+#define CP_POSE_RECORD 192  /* floats per detection slot in `poses`  */
+#define CP_DETS_RECORD 128  /* floats per candidate slot in `dets`   */
+#define CP_META_DOUBLES 16  /* doubles per image in `meta`           */
+#define CP_MAX_K 128
+
+typedef struct cp_plan cp_plan;
+
+typedef struct cp_config {
+  int32_t arch;                 /* cp_arch                                                */
+  int32_t tracking;             /* 1: pre_img / pre_hm / pre_hm_hp stems (pose_dla_dcn.py:253-271) */
+  int32_t tracking_task_gru;    /* dlav1 only: 4 GRU steps + tracking routing (:473-477,545-555)   */
+  int32_t max_batch;
+  int32_t height, width;        /* network input, multiples of 32                         */
+  int32_t precision;            /* cp_precision                                           */
+  int32_t device;               /* CUDA ordinal                                           */
+  int32_t head_conv;            /* 256                                                    */
+  int32_t num_heads;
+  const char* head_names[CP_MAX_HEADS];    /* in opt.heads order (opts.py:394-426)        */
+  int32_t head_channels[CP_MAX_HEADS];
+} cp_config;
+
+/* Create a plan: builds the static layer schedule and allocates the
+ * activation arena + packed-weight storage on cfg->device.  Synchronous. */
+int cp_plan_create(const cp_config* cfg, cp_plan** out);
+int cp_plan_destroy(cp_plan* plan);
+
+/* Ingest a reference state_dict (Appendix A of SURVEY.md).  names[i] is the
+ * reference key (an optional leading "module." is ignored, model.py:43-47),
+ * dev_ptrs[i] a DEVICE pointer to contiguous fp32 data in the reference's
+ * layout (OIHW conv weights, [C] vectors), numel[i] its element count.  The
+ * pointers are only borrowed for the duration of the call: BatchNorm is
+ * folded, weights are repacked (K-major, padded) into plan-owned storage.
+ * Unknown keys (e.g. base.fc.*, num_batches_tracked) are ignored; a key the
+ * plan needs but does not get returns CP_ERR_MISSING_KEY.  Enqueued on
+ * `stream`; the borrowed tensors must stay alive until that work completes. */
+int cp_plan_load_weights(cp_plan* plan, const char* const* names, const void* const* dev_ptrs,
+                         const int64_t* numel, int32_t n, void* stream);
+
+/* Network forward.  images: device fp32 NCHW [batch,3,H,W]; pre_img [batch,3,H,W],
+ * pre_hm [batch,1,H,W], pre_hm_hp [batch,8,H,W] or NULL (tracking plans only).
+ * head_out[i]: device fp32 NCHW [batch, head_channels[i], H/4, W/4] receiving the
+ * LOGITS of head i (the reference applies sigmoid later, object_pose.py:136-138). */
+int cp_forward(cp_plan* plan, int32_t batch, const float* images, const float* pre_img,
+               const float* pre_hm, const float* pre_hm_hp, float* const* head_out, void* stream);
+
+/* Arena / weight bytes owned by the plan (for logging). */
+int64_t cp_plan_bytes(const cp_plan* plan);
+/* Number of kernel launches one cp_forward enqueues (for bench gpu_launches). */
+int32_t cp_plan_forward_launches(const cp_plan* plan);
+
+/* ---- decode + grouping + post-process + soft-NMS + PnP --------------------- */
+typedef struct cp_heads {
+  /* device fp32 NCHW [batch, C, out_h, out_w]; NULL when the head is absent */
+  const float* hm;                /* [B,num_classes,..] logits (or probabilities if !apply_sigmoid) */
+  const float* wh;                /* [B,2,..]   */
+  const float* hps;               /* [B,2J,..]  */
+  const float* reg;               /* [B,2,..]   or NULL */
+  const float* hm_hp;             /* [B,J,..]   */
+  const float* hp_offset;         /* [B,2,..]   or NULL */
+  const float* scale;             /* [B,3,..]   or NULL */
+  const float* hps_uncertainty;   /* [B,2J,..]  or NULL */
+  const float* scale_uncertainty; /* [B,3,..]   or NULL */
+  const float* tracking;          /* [B,2,..]   or NULL */
+  const float* tracking_hp;       /* [B,2J,..]  or NULL */
+} cp_heads;
+
+typedef struct cp_decode_params {
+  int32_t batch, out_h, out_w;
+  int32_t num_classes;     /* 1 (Objectron single-category models, opts.py:434)           */
+  int32_t num_joints;      /* 8                                                            */
+  int32_t K;               /* opt.K = 100, <= CP_MAX_K                                     */
+  int32_t rep_mode;        /* opt.rep_mode: 0,1,3,4 (2 = random GMM sampling, unsupported) */
+  int32_t use_moments;     /* opt.tracking_task || opt.refined_Kalman (decode.py:222)      */
+  int32_t nms;             /* opt.nms (demo.py:114 sets True)                              */
+  int32_t visible_thresh;  /* cuboid_pnp_shell.py:59-66: 6 book/chair/cereal_box, 3 camera/bottle/cup, 0 bike/laptop/shoe */
+  int32_t opencv_return;   /* opt.show_axes: return the OpenCV pose instead of OpenGL      */
+  int32_t apply_sigmoid;   /* 1: hm / hm_hp are logits                                     */
+  int32_t use_pnp;         /* opt.use_pnp                                                  */
+  float vis_thresh;        /* opt.vis_thresh (0.3)                                         */
+  float balance;           /* opt.balance_coefficient[opt.c] (2)                           */
+  float reserved;
+} cp_decode_params;
+
+/* meta: device fp64 [batch, CP_META_DOUBLES] per image:
+ *   [0] c_x  [1] c_y  [2] s (src width of the affine, base_detector.py:114)
+ *   [3] image width  [4] image height  [5..13] camera matrix row-major  [14,15] unused
+ * dets:  device fp32 [batch, K, CP_DETS_RECORD] or NULL -- the 13 arrays of
+ *        decode.py:348-361 in output-map pixels (layout: cp_dets_field).
+ * poses: device fp32 [batch, K, CP_POSE_RECORD] -- slots [0, n_valid[b]) hold the
+ *        reference's `results` (after score filter + soft-NMS) in order, image pixels,
+ *        with the PnP output of each (layout: cp_pose_field).
+ * n_valid: device int32 [batch].
+ * workspace: device scratch of at least cp_decode_workspace_bytes(prm) bytes. */
+size_t cp_decode_workspace_bytes(const cp_decode_params* prm);
+int cp_decode_pnp(const cp_decode_params* prm, const cp_heads* heads, const double* meta,
+                  float* dets, float* poses, int32_t* n_valid,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* forward + decode in one call; head maps stay in plan-owned buffers.
+ * `heads_out` may be NULL, or an array of num_heads device pointers that
+ * additionally receive the head logits (NCHW). */
+int cp_infer(cp_plan* plan, int32_t batch, const float* images, const float* pre_img,
+             const float* pre_hm, const float* pre_hm_hp, const cp_decode_params* prm,
+             const double* meta, float* const* heads_out, float* dets, float* poses,
+             int32_t* n_valid, void* stream);
+
+/* Offsets (in floats) inside one CP_POSE_RECORD slot. */
+enum cp_pose_field {
+  CP_P_SCORE = 0, CP_P_CLS = 1, CP_P_STATUS = 2, CP_P_NPTS = 3,
+  CP_P_BBOX = 4,            /* 4  */
+  CP_P_CT = 8,              /* 2  */
+  CP_P_KPS = 10,            /* 16 */
+  CP_P_KPS_DISP_MEAN = 26,  /* 16 */
+  CP_P_KPS_HM_MEAN = 42,    /* 16 */
+  CP_P_KPS_HM_STD = 58,     /* 16 */
+  CP_P_KPS_HM_HEIGHT = 74,  /* 8  */
+  CP_P_KPS_DISP_STD = 82,   /* 16 */
+  CP_P_OBJ_SCALE = 98,      /* 3  */
+  CP_P_OBJ_SCALE_UNC = 101, /* 3  */
+  CP_P_TRACKING = 104,      /* 2  */
+  CP_P_TRACKING_HP = 106,   /* 16 */
+  CP_P_LOCATION = 122,      /* 3  */
+  CP_P_QUAT = 125,          /* 4 xyzw */
+  CP_P_REPROJ = 129,        /* 1  */
+  CP_P_PROJ_CUBOID = 130,   /* 16 */
+  CP_P_KPS_3D_CAM = 146,    /* 27 */
+  CP_P_KPS_PNP = 173,       /* 18 */
+  CP_P_SRC_INDEX = 191      /* index k of the candidate in the top-K list */
+};
+
+/* PnP status stored in CP_P_STATUS (mirrors the reference's None paths). */
+enum cp_pnp_status {
+  CP_PNP_NOT_RUN = 0,
+  CP_PNP_OK = 1,          /* pnp_shell returned a tuple -> goes into `boxes`                    */
+  CP_PNP_INVISIBLE = 2,   /* pose stored in the result, visibility gate returned None (:59-79)  */
+  CP_PNP_BEHIND = 3,      /* z < 0 (cuboid_pnp_solver.py:208-220)                               */
+  CP_PNP_FEW_POINTS = 4,  /* < 6 valid points (reference: <4 fails, 4-5 switch to EPNP)         */
+  CP_PNP_SOLVER_FAIL = 5
+};
+
+/* Offsets inside one CP_DETS_RECORD slot (output-map pixel units). */
+enum cp_dets_field {
+  CP_D_BBOX = 0, CP_D_SCORE = 4, CP_D_CLS = 5,
+  CP_D_KPS = 6,             /* 16 */
+  CP_D_OBJ_SCALE = 22,      /* 3  */
+  CP_D_OBJ_SCALE_UNC = 25,  /* 3  */
+  CP_D_TRACKING = 28,       /* 2  */
+  CP_D_TRACKING_HP = 30,    /* 16 */
+  CP_D_KPS_DISP_MEAN = 46,  /* 16 */
+  CP_D_KPS_DISP_STD = 62,   /* 16 */
+  CP_D_KPS_HM_MEAN = 78,    /* 16 */
+  CP_D_KPS_HM_STD = 94,     /* 16 */
+  CP_D_KPS_HM_HEIGHT = 110, /* 8  */
+  CP_D_IND = 118            /* flat index of the centre cell */
+};
+
+/* ---- stand-alone modulated deformable convolution (the `_ext` replacement) -- */
+/* input [B,C,H,W], weight [Co,C,3,3], bias [Co], offset [B,18,H,W]
+ * (channel 2k = dy, 2k+1 = dx of tap k), mask [B,9,H,W] (already sigmoid'ed),
+ * output [B,Co,H,W]; all device fp32 NCHW.  3x3, stride 1, pad 1, dilation 1,
+ * deformable_group 1 -- the only configuration CenterPose instantiates
+ * (pose_dla_dcn.py:384).  Scratch is taken from the stream-ordered allocator. */
+int cp_dcn_v2_forward(const float* input, const float* weight, const float* bias,
+                      const float* offset, const float* mask, float* output,
+                      int32_t B, int32_t C, int32_t H, int32_t W, int32_t Co, void* stream);
+
+/* ---- batched pre-process (next-row f-1) ------------------------------------ */
+/* frames: device uint8 [B, src_h, src_w, 3] (BGR as cv2.imread gives);
+ * out: device fp32 NCHW [B,3,dst_h,dst_w] = (bilinear-warped/255 - mean)/std with the
+ * reference's fix_res affine (c = src centre, s = max(src_h, src_w)). */
+int cp_preprocess(const uint8_t* frames, float* out, int32_t B, int32_t src_h, int32_t src_w,
+                  int32_t dst_h, int32_t dst_w, const float mean[3], const float std[3], void* stream);
+
+/* ---- misc ------------------------------------------------------------------ */
+int cp_version(void);
+const char* cp_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CENTERPOSE_B200_H_ */

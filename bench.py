@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the CenterPose inference hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores
+
+One "step" = one pass of the hot path over one batch of synthetic 512x512
+Objectron-shaped frames (BASELINE.json configs[2]: batch 32 per GPU, dla_34,
+7 heads): pre-process -> DLA-34 + DCNv2 network -> heads -> decode ->
+keypoint grouping -> soft-NMS -> PnP -> pose records (+ one all-gather of the
+pose tensor when N > 1; frames shard over ranks, weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` is measured with the uint8 frames
+already resident in HBM; `e2e` goes through the public `run_batch()` API with
+pinned HOST frames (H2D + D2H inside the timed region).  `roofline` is for the
+dominant kernel (the heads' 3x3 implicit-GEMM launch), timed live with CUDA
+events on the launching stream (cp_plan_profile); `cpu_baseline` is the CPU
+oracle (a port of the reference algorithm, see oracle/) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "images/sec at 512x512 DLA-34 (dla_34 + DCNv2, 7 heads, decode + PnP)"
+UNIT = "images/s"
+GFLOP_PER_IMAGE = 85.11          # BASELINE.md section 2 (reference graph, 2*MAC)
+HEAD_GAIN = 6.0                  # scales the random final 1x1 head weights so a few centres pass vis_thresh
+N_ROTATE = 6                     # distinct input batches rotated through (6 x 25 MB uint8 + activations >> 126 MB L2)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_reference_step(sd, opt, frames_u8, cam):
+    """The reference algorithm (oracle port) for a few frames on the host: returns the number of images processed."""
+    import centerpose_b200 as cpb  # noqa: F401
+    from centerpose_b200 import _lib as L
+    from centerpose_b200 import synth
+    from oracle import decode_ref, net_ref
+    from tests.util import oracle_records
+    n = frames_u8.shape[0]
+    prm = decode_ref.DecodeParams(rep_mode=opt.rep_mode, vis_thresh=opt.vis_thresh, category=opt.c)
+    c = np.array([256., 256.], np.float32)
+    for i in range(n):                                   # the reference's run() is one image per call
+        x = torch.from_numpy(synth.normalize_frames(frames_u8[i:i + 1]))
+        heads = net_ref.forward(x, sd, opt.heads, "dla_34")
+        hb = {k: v[0].numpy() for k, v in heads.items()}
+        oracle_records(hb, prm, cam, 512, 512, c, 512.0, L)
+    return n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import centerpose_b200 as cpb
+    from centerpose_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    opt = cpb.default_opt("dla_34")
+    m = cpb.create_model(opt.arch, opt.heads, opt.head_conv, opt)
+    sd = synth.seeded_state_dict(m, seed=0, offset_std=1.0, head_gain=HEAD_GAIN)
+    cam = synth.default_camera(512, 512)
+    per_step = args.ref_images
+    frames = synth.synthetic_frames(per_step, 512, 512, seed=317)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_reference_step(sd, opt, frames[:1], cam)
+    t0 = time.time()
+    n = 0
+    for _ in range(args.steps):
+        n += cpu_reference_step(sd, opt, frames, cam)
+    dt = time.time() - t0
+    val = n / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "batch=%d synthetic 512x512 frames, dla_34, host CPU" % per_step, "sample": per_step},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d steps x %d frames, one frame per call like run()" % (args.steps, per_step)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
+    ap.add_argument("--ref-images", type=int, default=2, help="frames per step of the CPU reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=4, help="frames of the in-run cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-ops", default="", help="write the per-op table (cp_plan_profile) to this path")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    import centerpose_b200 as cpb
+    from centerpose_b200 import _lib as L
+    from centerpose_b200 import synth
+    from centerpose_b200.dist import all_gather_poses
+    from centerpose_b200.engine import decode_params, make_meta, preprocess
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback); "
+                         "use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+
+    opt = cpb.default_opt("dla_34")
+    model = cpb.create_model(opt.arch, opt.heads, opt.head_conv, opt)
+    sd = synth.seeded_state_dict(model, seed=0, offset_std=1.0, head_gain=HEAD_GAIN)
+    model.load_state_dict(sd)
+    det = cpb.ObjectPoseDetector(opt, model=model)
+    cam = synth.default_camera(512, 512)
+    eng = det.model.engine(B, 512, 512, dev)
+    prm = decode_params(opt)
+    meta = make_meta(B, np.array([256., 256.], np.float32), 512.0, 512, 512, cam).to(dev)
+
+    # distinct frames per rank and per rotation slot
+    host_frames = [torch.from_numpy(synth.synthetic_frames(B, 512, 512, seed=317 + 1000 * rank + i)).pin_memory()
+                   for i in range(N_ROTATE)]
+    dev_frames = [f.to(dev) for f in host_frames]
+    x_buf = torch.empty((B, 3, 512, 512), dtype=torch.float32, device=dev)
+    poses = torch.empty((B, prm.K, L.CP_POSE_RECORD), dtype=torch.float32, device=dev)
+    n_valid = torch.empty((B,), dtype=torch.int32, device=dev)
+
+    def step_resident(i):
+        preprocess(dev_frames[i % N_ROTATE], 512, 512, opt.mean, opt.std, out=x_buf)
+        eng.infer(x_buf, meta, prm, poses=poses, n_valid=n_valid)
+        if world > 1:
+            return all_gather_poses(poses, n_valid)
+        return poses, n_valid
+
+    def step_e2e(i):
+        p, n = det.run_batch(host_frames[i % N_ROTATE], cam, to_host=False)
+        if world > 1:
+            p, n = all_gather_poses(p, n)
+        return p.cpu(), n.cpu()                           # D2H of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_res = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    total_images = B * world * args.steps
+    value = total_images / (ms_res / 1e3)
+    e2e_value = total_images / (ms_e2e / 1e3)
+    det_per_img = float(n_valid.float().mean().item())
+
+    # ---- roofline of the dominant kernel, timed live (CUDA events between ops on the launching stream)
+    peaks = load_peaks()
+    ops = None
+    for _ in range(3):
+        ops = eng.profile(x_buf)
+    tot_ms = sum(o["ms"] for o in ops)
+    dom = max(ops, key=lambda o: o["ms"])
+    reps = [eng.profile(x_buf) for _ in range(5)]
+    dom_ms = float(np.mean([[o for o in r if o["name"] == dom["name"]][0]["ms"] for r in reps]))
+    achieved = dom["flops"] / (dom_ms * 1e-3) / 1e12
+    peak = peaks["bf16_tflops_sustained"]
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "igemm_fp32_kernel<64,NHWC> @ " + dom["name"], "ms_per_launch": dom_ms,
+                "share_of_forward": dom_ms / tot_ms, "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)",
+                "algorithmic_flops_per_launch": dom["flops"],
+                "network_tflops": GFLOP_PER_IMAGE * 1e9 * B / (tot_ms * 1e-3) / 1e12}
+    if args.profile_ops and rank == 0:
+        with open(args.profile_ops, "w") as f:
+            f.write("name,kind,ms,gflop,mbytes,tflops,gbs\n")
+            for o in ops:
+                f.write("%s,%d,%.4f,%.3f,%.3f,%.2f,%.1f\n" % (o["name"], o["kind"], o["ms"], o["flops"] / 1e9,
+                                                            o["bytes"] / 1e6, o["flops"] / max(o["ms"], 1e-6) / 1e9,
+                                                            o["bytes"] / max(o["ms"], 1e-6) / 1e6))
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        fr = synth.synthetic_frames(args.cpu_sample, 512, 512, seed=317)
+        cpu_reference_step(sd, opt, fr[:1], cam)
+        t0 = time.time()
+        n = cpu_reference_step(sd, opt, fr, cam)
+        dt = time.time() - t0
+        cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "%d frames of the same workload, one frame per call like run()" % n}
+
+    if rank == 0:
+        h2d = B * 512 * 512 * 3 + meta.numel() * 8
+        d2h = B * prm.K * L.CP_POSE_RECORD * 4 * (world if world > 1 else 1) + B * 4 * world
+        launches_per_step = eng.forward_launches + 2 + 1
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "batch=%d synthetic 512x512 frames per GPU, dla_34 + DCNv2, 7 heads, K=100, rep_mode 1, "
+                                   "decode + soft-NMS + PnP" % B,
+                       "global_batch": B * world, "precision": "fp32 CUDA-core implicit GEMM (parity mode)",
+                       "weights": "seeded random init (head_gain %.1f)" % HEAD_GAIN,
+                       "l2": "inputs rotate over %d distinct batches; per-step activations (~8 GB) exceed the 126 MB L2" % N_ROTATE,
+                       "detections_per_image": det_per_img, "parallelism": "dp%d, 1 all-gather of pose records" % world},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks.summary(),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "network_gflop_per_image": GFLOP_PER_IMAGE,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -36,8 +36,13 @@ PNP_NOT_RUN, PNP_OK, PNP_INVISIBLE, PNP_BEHIND, PNP_FEW_POINTS, PNP_SOLVER_FAIL 
 EXPORTS = [
     "cp_version", "cp_last_error", "cp_plan_create", "cp_plan_destroy", "cp_plan_load_weights",
     "cp_forward", "cp_plan_bytes", "cp_plan_forward_launches", "cp_decode_workspace_bytes",
-    "cp_decode_pnp", "cp_infer", "cp_dcn_v2_forward", "cp_preprocess",
+    "cp_decode_pnp", "cp_infer", "cp_dcn_v2_forward", "cp_preprocess", "cp_plan_num_ops", "cp_plan_profile",
 ]
+
+
+class CpOpStat(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 96), ("kind", ctypes.c_int32), ("ms", ctypes.c_float),
+                ("flops", ctypes.c_double), ("bytes", ctypes.c_double)]
 
 
 class CpConfig(ctypes.Structure):
@@ -93,6 +98,9 @@ def load():
     L.cp_plan_load_weights.argtypes = [vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(vp),
                                        ctypes.POINTER(i64), i32, vp]
     L.cp_forward.argtypes = [vp, i32, vp, vp, vp, vp, ctypes.POINTER(vp), vp]
+    L.cp_plan_num_ops.argtypes = [vp]
+    L.cp_plan_profile.argtypes = [vp, i32, vp, vp, vp, vp, ctypes.POINTER(vp), vp, ctypes.POINTER(CpOpStat), i32,
+                                  ctypes.POINTER(i32)]
     L.cp_plan_bytes.argtypes = [vp]
     L.cp_plan_bytes.restype = i64
     L.cp_plan_forward_launches.argtypes = [vp]

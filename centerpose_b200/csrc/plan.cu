@@ -9,6 +9,8 @@
 //   pose_dla_dcn.py:457-570  DLASeg: ida_up, heads (3x3 -> [GN] -> ReLU -> 1x1), convGRU routing
 //   DCNv2/dcn_v2.py:97-128   DCN = 3x3 conv -> 27 ch (18 offsets + 9 mask logits) + deformable 3x3
 //   convGRU.py:20-94, GN.py:4-9
+#include <string.h>
+
 #include <map>
 #include <memory>
 #include <string>
@@ -38,6 +40,7 @@ enum OpType { OP_IGEMM, OP_MAXPOOL, OP_UPADD, OP_GN_RELU, OP_GRU };
 
 struct Op {
   OpType type = OP_IGEMM;
+  std::string name;
   // igemm
   Act src[4];
   int nsrc = 0;
@@ -182,6 +185,8 @@ struct Builder {
       op.b_off = walloc(ldw);
       add_pack(wkey, bias_key, bn, Cout, Cin, k, op.CoutPad, op.Kpad, ldw, colOff, op.w_off, op.b_off);
     }
+    op.name = wkey.empty() ? std::string("conv") + std::to_string(k) + "x" + std::to_string(k) + "_merged_" + std::to_string(Cout)
+                           : wkey.substr(0, wkey.rfind('.'));
     P->ops.push_back(op);
     return op.out;
   }
@@ -223,6 +228,7 @@ struct Builder {
     op.type = OP_MAXPOOL;
     op.src[0] = x;
     op.out = new_act(x.C, x.H / 2, x.W / 2);
+    op.name = "maxpool2";
     P->ops.push_back(op);
     return op.out;
   }
@@ -274,6 +280,7 @@ struct Builder {
     om.b_off = walloc(32);
     add_pack(p + ".conv.conv_offset_mask.weight", p + ".conv.conv_offset_mask.bias", "", 27, x.C, 3, 32,
              om.Kpad, 32, 0, om.w_off, om.b_off);
+    om.name = p + ".conv.conv_offset_mask";
     P->ops.push_back(om);
 
     Op op;
@@ -295,6 +302,7 @@ struct Builder {
     op.b_off = walloc(op.CoutPad);
     add_pack(p + ".conv.weight", p + ".conv.bias", p + ".actf.0", Cout, x.C, 3, op.CoutPad, op.Kpad,
              op.CoutPad, 0, op.w_off, op.b_off);
+    op.name = p + ".conv(dcn)";
     P->ops.push_back(op);
     return op.out;
   }
@@ -315,6 +323,7 @@ struct Builder {
     j.kh = 2 * f;
     j.dst = op.upw_off;
     P->jobs.push_back(j);
+    op.name = key.substr(0, key.rfind('.'));
     P->ops.push_back(op);
     return op.out;
   }
@@ -432,6 +441,7 @@ int build_graph(cp_plan* P) {
       op.gprev = hprev;
       op.first_step = (s == 0);
       op.out = b.new_act(HC, F.H, F.W);
+      op.name = "convGRU.gates.step" + std::to_string(s);
       P->ops.push_back(op);
       hprev = op.out;
       hs.push_back(op.out);
@@ -497,6 +507,7 @@ int build_graph(cp_plan* P) {
         j2.key = n + ".1.bias";
         j2.dst = g.beta_off;
         P->jobs.push_back(j2);
+        g.name = n + ".1(groupnorm+relu)";
         P->ops.push_back(g);
         last = n + ".3";
       }
@@ -639,9 +650,20 @@ int cp_plan_load_weights(cp_plan* P, const char* const* names, const void* const
   return CP_OK;
 }
 
-static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* const* head_out, cudaStream_t s) {
+struct ProfCtx {
+  std::vector<cudaEvent_t> ev;
+};
+
+static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* const* head_out, cudaStream_t s,
+                       ProfCtx* prof = nullptr) {
   int rc;
   for (auto& op : P->ops) {
+    if (prof) {
+      cudaEvent_t e;
+      CP_CUDA_CHECK(cudaEventCreate(&e));
+      CP_CUDA_CHECK(cudaEventRecord(e, s));
+      prof->ev.push_back(e);
+    }
     switch (op.type) {
       case OP_IGEMM: {
         IgemmParams p{};
@@ -718,7 +740,46 @@ static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* 
         break;
     }
   }
+  if (prof) {
+    cudaEvent_t e;
+    CP_CUDA_CHECK(cudaEventCreate(&e));
+    CP_CUDA_CHECK(cudaEventRecord(e, s));
+    prof->ev.push_back(e);
+  }
   return CP_OK;
+}
+
+// Algorithmic work of one op at batch `batch` (2*MAC; fp32 bytes of the tensors it must touch once).
+static void op_work(const Op& op, int batch, double* flops, double* bytes) {
+  *flops = 0;
+  *bytes = 0;
+  const double B = batch;
+  switch (op.type) {
+    case OP_IGEMM: {
+      int Hin = op.src[0].H, Win = op.src[0].W;
+      int Ho = (Hin + 2 * op.pad - op.kh) / op.stride + 1, Wo = (Win + 2 * op.pad - op.kw) / op.stride + 1;
+      double M = B * Ho * Wo;
+      *flops = 2.0 * M * op.kh * op.kw * op.Cin * op.Cout;
+      *bytes = 4.0 * (B * Hin * Win * op.Cin + (double)op.kh * op.kw * op.Cin * op.Cout + M * op.Cout +
+                      (op.has_res ? M * op.Cout : 0.0) + (op.mode == IGEMM_DCN ? M * 27 : 0.0));
+      break;
+    }
+    case OP_MAXPOOL:
+      *bytes = 4.0 * B * op.src[0].H * op.src[0].W * op.src[0].C * 1.25;
+      break;
+    case OP_UPADD: {
+      double o = B * op.out.H * op.out.W * op.out.C;
+      *flops = 2.0 * o * 4;
+      *bytes = 4.0 * (o * 2 + B * op.src[0].H * op.src[0].W * op.src[0].C);
+      break;
+    }
+    case OP_GN_RELU:
+      *bytes = 4.0 * B * op.out.H * op.out.W * op.out.C * 3;
+      break;
+    case OP_GRU:
+      *bytes = 4.0 * B * op.out.H * op.out.W * op.out.C * 8;
+      break;
+  }
 }
 
 int cp_forward(cp_plan* P, int32_t batch, const float* images, const float* pre_img, const float* pre_hm,
@@ -728,6 +789,35 @@ int cp_forward(cp_plan* P, int32_t batch, const float* images, const float* pre_
   if (batch <= 0 || batch > P->B) return fail(CP_ERR_INVALID, "cp_forward: batch exceeds the plan's max_batch");
   const float* ext[4] = {images, pre_img, pre_hm, pre_hm_hp};
   return run_forward(P, batch, ext, head_out, (cudaStream_t)stream);
+}
+
+int cp_plan_num_ops(const cp_plan* P) { return P ? (int)P->ops.size() : 0; }
+
+int cp_plan_profile(cp_plan* P, int32_t batch, const float* images, const float* pre_img, const float* pre_hm,
+                    const float* pre_hm_hp, float* const* head_out, void* stream, cp_op_stat* stats, int32_t max_stats,
+                    int32_t* n_stats) {
+  if (!P || !images || !head_out || !stats || !n_stats) return fail(CP_ERR_INVALID, "cp_plan_profile: null argument");
+  if (!P->loaded) return fail(CP_ERR_NOT_LOADED, "cp_plan_profile: call cp_plan_load_weights first");
+  if (batch <= 0 || batch > P->B) return fail(CP_ERR_INVALID, "cp_plan_profile: batch exceeds the plan's max_batch");
+  const float* ext[4] = {images, pre_img, pre_hm, pre_hm_hp};
+  ProfCtx ctx;
+  int rc = run_forward(P, batch, ext, head_out, (cudaStream_t)stream, &ctx);
+  if (rc == CP_OK) {
+    CP_CUDA_CHECK(cudaEventSynchronize(ctx.ev.back()));
+    int n = 0;
+    for (size_t i = 0; i + 1 < ctx.ev.size() && n < max_stats; ++i, ++n) {
+      const Op& op = P->ops[i];
+      cp_op_stat& st = stats[n];
+      memset(&st, 0, sizeof(st));
+      snprintf(st.name, sizeof(st.name), "%s", op.name.c_str());
+      st.kind = (int)op.type * 10 + (op.type == OP_IGEMM ? op.mode : 0);
+      cudaEventElapsedTime(&st.ms, ctx.ev[i], ctx.ev[i + 1]);
+      op_work(op, batch, &st.flops, &st.bytes);
+    }
+    *n_stats = n;
+  }
+  for (auto e : ctx.ev) cudaEventDestroy(e);
+  return rc;
 }
 
 int cp_infer(cp_plan* P, int32_t batch, const float* images, const float* pre_img, const float* pre_hm,

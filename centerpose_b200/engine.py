@@ -193,6 +193,22 @@ class Engine(object):
         _lib.check(rc, "cp_forward")
         return out
 
+    def profile(self, x, pre_img=None, pre_hm=None, pre_hm_hp=None):
+        """One forward with CUDA events between the ops: list of dicts(name, kind, ms, flops, bytes)."""
+        B, xs = self._check_inputs(x, pre_img, pre_hm, pre_hm_hp)
+        out = {n: torch.empty((B, c, self.height // 4, self.width // 4), dtype=torch.float32, device=self.device)
+               for n, c in self.heads.items()}
+        hp = (ctypes.c_void_p * len(self.head_names))(*[out[n].data_ptr() for n in self.head_names])
+        n_ops = int(self.L.cp_plan_num_ops(self.plan))
+        stats = (_lib.CpOpStat * n_ops)()
+        n = ctypes.c_int32(0)
+        with torch.cuda.device(self.device):
+            rc = self.L.cp_plan_profile(self.plan, B, _ptr(xs[0]), _ptr(xs[1]), _ptr(xs[2]), _ptr(xs[3]), hp, _stream(),
+                                        stats, n_ops, ctypes.byref(n))
+        _lib.check(rc, "cp_plan_profile")
+        return [dict(name=stats[i].name.decode(), kind=int(stats[i].kind), ms=float(stats[i].ms),
+                     flops=float(stats[i].flops), bytes=float(stats[i].bytes)) for i in range(n.value)]
+
     def infer(self, x, meta, prm, pre_img=None, pre_hm=None, pre_hm_hp=None, heads_out=None, want_dets=False,
               poses=None, n_valid=None, dets=None):
         """forward + decode + PnP in one native call.  Returns (dets|None, poses, n_valid)."""

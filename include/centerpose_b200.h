@@ -116,6 +116,24 @@ int cp_plan_load_weights(cp_plan* plan, const char* const* names, const void* co
 int cp_forward(cp_plan* plan, int32_t batch, const float* images, const float* pre_img,
                const float* pre_hm, const float* pre_hm_hp, float* const* head_out, void* stream);
 
+/* Per-op timing of one forward (the reference only has wall-clock stamps around whole stages,
+ * base_detector.py:466-498): CUDA events are recorded on `stream` between the ops of the
+ * schedule; the call synchronises on the last event.  `flops` / `bytes` are the ALGORITHMIC
+ * work of the op (2*MAC; fp32 tensors touched once), used for the roofline in bench.py.
+ * kind = op_type*10 + igemm_mode  (0: NCHW stem conv, 1: NHWC conv, 2: deformable conv,
+ * 10: max-pool, 20: up-sample+add, 30: GroupNorm+ReLU, 40: GRU gate). */
+typedef struct cp_op_stat {
+  char name[96];
+  int32_t kind;
+  float ms;
+  double flops;
+  double bytes;
+} cp_op_stat;
+int cp_plan_num_ops(const cp_plan* plan);
+int cp_plan_profile(cp_plan* plan, int32_t batch, const float* images, const float* pre_img,
+                    const float* pre_hm, const float* pre_hm_hp, float* const* head_out, void* stream,
+                    cp_op_stat* stats, int32_t max_stats, int32_t* n_stats);
+
 /* Arena / weight bytes owned by the plan (for logging). */
 int64_t cp_plan_bytes(const cp_plan* plan);
 /* Number of kernel launches one cp_forward enqueues (for bench gpu_launches). */

@@ -1,0 +1,76 @@
+"""End-to-end `ObjectPoseDetector.run()` / `run_batch()` on the GPU and the batched pre-process kernel."""
+import numpy as np
+import pytest
+import torch
+
+import centerpose_b200 as cpb
+from centerpose_b200 import _lib as L
+from centerpose_b200 import synth
+from oracle import decode_ref
+from tests.util import compare_records, oracle_records
+
+pytestmark = pytest.mark.gpu
+
+KEYS = {"results", "boxes", "output", "tot", "load", "pre", "net", "dec", "post", "merge", "pnp", "track"}
+
+
+def _detector(head_gain=6.0, seed=21):
+    opt = cpb.default_opt("dla_34")
+    m = cpb.create_model(opt.arch, opt.heads, opt.head_conv, opt)
+    m.load_state_dict(synth.seeded_state_dict(m, seed=seed, offset_std=1.0, head_gain=head_gain))
+    return cpb.ObjectPoseDetector(opt, model=m), opt
+
+
+def test_run_contract_and_consistency(cplib):
+    det, opt = _detector()
+    img = synth.synthetic_frames(1, 600, 800, seed=3)[0]
+    cam = np.array([[663.0287679036459, 0, 300.2775065104167], [0, 663.0287679036459, 395.00066121419275], [0, 0, 1]])
+    ret = det.run(img, meta_inp={"camera_matrix": cam})
+    assert set(ret) == KEYS
+    out = ret["output"]
+    assert set(opt.heads) <= set(out) and out["hm"].shape == (1, 1, 128, 128)
+    assert float(out["hm"].min()) >= 0 and float(out["hm"].max()) <= 1        # sigmoid applied like object_pose.py:136
+    # the records run() unpacked must equal the oracle pipeline run on the heads the GPU produced
+    heads = {k: out[k][0].cpu().numpy() for k in opt.heads}
+    for k in ("hm", "hm_hp"):                                                   # back to logits for the oracle entry point
+        p = np.clip(heads[k].astype(np.float64), 1e-12, 1 - 1e-7)
+        heads[k] = np.log(p / (1 - p)).astype(np.float32)
+    prm = decode_ref.DecodeParams(rep_mode=1, vis_thresh=opt.vis_thresh, category=opt.c)
+    c = np.array([800 / 2., 600 / 2.], np.float32)
+    _, want = oracle_records(heads, prm, cam, 800, 600, c, 800.0, L)
+    assert len(ret["results"]) == want.shape[0]
+    for d in ret["results"]:
+        assert {"score", "cls", "obj_scale", "bbox", "ct", "kps", "kps_displacement_mean", "kps_heatmap_mean",
+                "kps_heatmap_std", "kps_heatmap_height", "tracking", "tracking_hp"} <= set(d)
+    for b in ret["boxes"]:
+        assert b[0].shape == (9, 2) and b[1].shape == (9, 3) and b[3].shape == (9, 2) and "location" in b[4]
+
+
+def test_run_batch_matches_run(cplib):
+    det, opt = _detector()
+    frames = synth.synthetic_frames(4, 512, 512, seed=9)
+    cam = synth.default_camera(512, 512)
+    poses, n_valid = det.run_batch(frames, cam)
+    assert poses.shape == (4, opt.K, L.CP_POSE_RECORD)
+    for b in (0, 3):
+        ret = det.run(frames[b], meta_inp={"camera_matrix": cam})
+        assert len(ret["results"]) == n_valid[b]
+        for i, d in enumerate(ret["results"]):
+            assert abs(d["score"] - poses[b, i, L.P_SCORE]) <= 1e-4
+            assert np.abs(d["kps"] - poses[b, i, L.P_KPS:L.P_KPS + 16]).max() <= 0.05
+
+
+def test_preprocess_matches_cv2(cplib):
+    cv2 = pytest.importorskip("cv2")
+    det, opt = _detector()
+    for (h, w) in ((512, 512), (600, 800), (480, 640)):
+        fr = synth.synthetic_frames(2, h, w, seed=h)
+        got = cpb.preprocess(torch.from_numpy(fr).cuda(), 512, 512, opt.mean, opt.std).cpu().numpy()
+        for b in range(2):
+            want, _ = det.pre_process(fr[b], 1.0)
+            d = np.abs(got[b] - want[0].numpy())
+            if (h, w) == (512, 512):
+                assert d.max() == 0.0                                  # identity warp: bit exact
+            else:
+                assert np.percentile(d, 99.9) <= 2.5 / 255 / 0.27      # <= ~2 grey levels on random-noise frames
+                assert d.mean() <= 0.3 / 255 / 0.27

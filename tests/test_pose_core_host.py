@@ -1,0 +1,118 @@
+"""centerpose_b200/csrc/pose_core.h is __host__ __device__: the exact code the
+CUDA decode kernel runs per detection is compiled with g++ here and checked
+against the oracle and cv2 without a GPU."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from centerpose_b200 import synth
+from oracle import decode_ref, pnp_ref
+
+dp = ctypes.POINTER(ctypes.c_double)
+fp = ctypes.POINTER(ctypes.c_float)
+ip = ctypes.POINTER(ctypes.c_int)
+
+
+def _solve(Lh, pts, scale, K, w, h, vis=6, ocv=0):
+    pts = np.ascontiguousarray(pts, np.float64)
+    scale = np.ascontiguousarray(scale, np.float32)
+    K = np.ascontiguousarray(K, np.float64)
+    out = np.zeros(80)
+    st, npt = ctypes.c_int(), ctypes.c_int()
+    Lh.host_solve_and_shell(pts.ctypes.data_as(dp), ctypes.c_int(pts.shape[0]), scale.ctypes.data_as(fp),
+                            K.ctypes.data_as(dp), ctypes.c_double(w), ctypes.c_double(h), vis, ocv,
+                            out.ctypes.data_as(dp), ctypes.byref(st), ctypes.byref(npt))
+    return st.value, npt.value, out
+
+
+def test_pnp_matches_oracle_and_cv2(pose_host):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    cam = synth.default_camera(512, 512)
+    worst = np.zeros(4)
+    M = np.array([[0, 1, 0], [1, 0, 0], [0, 0, -1.]])
+    for trial in range(120):
+        scale = np.array([rng.uniform(0.3, 2), rng.uniform(0.5, 1.5), rng.uniform(0.3, 2)], np.float32)
+        V = pnp_ref.cuboid_vertices(scale)
+        R = synth._rand_rot(rng)
+        tz = rng.uniform(2.5, 7)
+        t = np.array([rng.uniform(-.3, .3) * tz, rng.uniform(-.3, .3) * tz, tz])
+        pts = np.repeat(pnp_ref.project(V, R, t, cam), 2, axis=0) + rng.normal(0, rng.choice([0.0, 0.5, 2.0, 5.0]), (16, 2))
+        for j in range(8):
+            if rng.uniform() < 0.3:
+                pts[2 * j + 1] = [-10000, -10000]
+        det = {"obj_scale": scale, "kps": pts[0::2].reshape(-1)}
+        st_o, _ = pnp_ref.pnp_shell(det, pts, cam, 512, 512, "chair")
+        st, npt, out = _solve(pose_host, pts, scale, cam, 512, 512, 6, 0)
+        assert st == st_o and npt == int((pts[:, 0] > -5000).sum())
+        ok = pts[:, 0] > -5000
+        X = np.array([V[i // 2] for i in range(16)])[ok]
+        _, rv, tv, err = cv2.solvePnPGeneric(X, pts[ok], cam, np.zeros((4, 1)), flags=cv2.SOLVEPNP_ITERATIVE)
+        qcv = pnp_ref.mat_to_quat(M @ pnp_ref.rodrigues(rv[0].reshape(3)))
+        lcv = M @ tv[0].reshape(3)
+        if st in (1, 2):
+            q = out[3:7]
+            if q @ qcv < 0:
+                q = -q
+            worst[0] = max(worst[0], np.abs(out[0:3] - lcv).max() / np.linalg.norm(lcv))
+            worst[1] = max(worst[1], np.abs(q - qcv).max())
+            worst[2] = max(worst[2], abs(out[7] - err.flatten()[0]))
+            worst[3] = max(worst[3], np.abs(out[24:51].reshape(9, 3) - det["kps_3d_cam"]).max())
+    assert worst[0] <= 1e-6 and worst[1] <= 1e-6 and worst[2] <= 1e-8 and worst[3] <= 1e-6, worst
+
+
+def test_pnp_failure_paths(pose_host):
+    cam = synth.default_camera(512, 512)
+    scale = np.array([1.0, 1.0, 1.0], np.float32)
+    pts = np.full((16, 2), -10000.0)
+    pts[:10:2] = np.random.default_rng(1).uniform(100, 400, (5, 2))    # only 5 valid points
+    st, npt, _ = _solve(pose_host, pts, scale, cam, 512, 512)
+    assert st == 4 and npt == 5                                        # reference would switch to EPNP
+    # a cuboid far outside the image: pose found, visibility gate rejects it (cuboid_pnp_shell.py:59-79)
+    V = pnp_ref.cuboid_vertices(scale)
+    uv = pnp_ref.project(V, np.eye(3), np.array([6.0, 0.0, 4.0]), cam)
+    st, _, out = _solve(pose_host, np.repeat(uv, 2, 0), scale, cam, 512, 512, 6, 0)
+    assert st == 2
+    st3, _, _ = _solve(pose_host, np.repeat(uv, 2, 0), scale, cam, 512, 512, 0, 0)     # bike/laptop/shoe: only centre gate
+    assert st3 == 2
+
+
+def test_soft_nms_matches_oracle(pose_host):
+    rng = np.random.default_rng(2)
+    for trial in range(100):
+        n = int(rng.integers(1, 40))
+        ctr = rng.uniform(100, 400, size=(n, 2))
+        wh = rng.uniform(20, 150, size=(n, 2))
+        bb = np.concatenate([ctr - wh / 2, ctr + wh / 2], 1)
+        sc = np.sort(rng.uniform(0.3001, 1, size=n))[::-1].copy()
+        boxes = [{"bbox": bb[i].copy(), "score": float(sc[i]), "id": i} for i in range(n)]
+        nn = decode_ref.soft_nms(boxes, threshold=0.3)
+        b2, s2, perm = bb.copy(), sc.copy(), np.arange(n, dtype=np.int32)
+        n2 = pose_host.host_soft_nms(b2.ctypes.data_as(dp), s2.ctypes.data_as(dp), perm.ctypes.data_as(ip), n,
+                                     ctypes.c_double(0.3))
+        assert nn == n2 and [b["id"] for b in boxes[:nn]] == list(perm[:n2])
+        assert np.allclose([b["score"] for b in boxes[:nn]], s2[:n2], rtol=0, atol=1e-15)
+
+
+def test_moments_matches_oracle(pose_host):
+    rng = np.random.default_rng(4)
+    for trial in range(100):
+        nr, nc = int(rng.integers(1, 12)), int(rng.integers(1, 12))
+        w = np.ascontiguousarray(rng.uniform(0, 1, size=(nr, nc)) * (rng.uniform(size=(nr, nc)) > 0.3))
+        if w.sum() == 0:
+            continue
+        out5 = np.zeros(5)
+        ok = pose_host.host_moments(w.ctypes.data_as(dp), nr, nc, out5.ctypes.data_as(dp))
+        with np.errstate(all="ignore"):
+            ref = decode_ref.moments(w)
+        if not np.all(np.isfinite(ref)):
+            continue
+        assert ok and np.allclose(out5, ref, rtol=1e-12, atol=1e-14)
+
+
+def test_cuboid_vertices_order(pose_host):
+    scale = np.array([0.4, 0.8, 1.2], np.float32)
+    V = np.zeros(24)
+    pose_host.host_cuboid_vertices(scale.ctypes.data_as(fp), V.ctypes.data_as(dp))
+    assert np.array_equal(V.reshape(8, 3), pnp_ref.cuboid_vertices(scale))

@@ -48,6 +48,29 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def usable_cores():
+    """Host threads this process may actually use: affinity mask and cgroup CPU quota, not just nproc."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
@@ -83,8 +106,10 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def cpu_reference_step(sd, opt, frames_u8, cam):
-    """The reference algorithm (oracle port) for a few frames on the host: returns the number of images processed."""
+def cpu_reference_step(sd, opt, frames_u8, cam, budget_s=None):
+    """The reference algorithm (oracle port) for a few frames on the host: returns the number of images
+    processed (stops early, after at least one frame, once `budget_s` seconds of wall clock are spent)."""
+    t_begin = time.time()
     import centerpose_b200 as cpb  # noqa: F401
     from centerpose_b200 import _lib as L
     from centerpose_b200 import synth
@@ -98,6 +123,8 @@ def cpu_reference_step(sd, opt, frames_u8, cam):
         heads = net_ref.forward(x, sd, opt.heads, "dla_34")
         hb = {k: v[0].numpy() for k, v in heads.items()}
         oracle_records(hb, prm, cam, 512, 512, c, 512.0, L)
+        if budget_s is not None and time.time() - t_begin > budget_s:
+            return i + 1
     return n
 
 
@@ -107,7 +134,7 @@ def run_reference(args):
         return 0
     import centerpose_b200 as cpb
     from centerpose_b200 import synth
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     opt = cpb.default_opt("dla_34")
     m = cpb.create_model(opt.arch, opt.heads, opt.head_conv, opt)
@@ -264,12 +291,12 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = usable_cores()
         torch.set_num_threads(cores)
         fr = synth.synthetic_frames(args.cpu_sample, 512, 512, seed=317)
         cpu_reference_step(sd, opt, fr[:1], cam)
         t0 = time.time()
-        n = cpu_reference_step(sd, opt, fr, cam)
+        n = cpu_reference_step(sd, opt, fr, cam, budget_s=30.0)
         dt = time.time() - t0
         cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "%d frames of the same workload, one frame per call like run()" % n}

@@ -1,0 +1,42 @@
+"""Helper for `ncu --set full` on the dominant launch of the forward (the merged heads 3x3 conv).
+
+    SKIP=$(python scripts/profile_target.py --print-skip)         # index among igemm launches
+    ncu --set full --clock-control none --import-source on -k regex:igemm -s $SKIP -c 1 \
+        -o gpurun_out/heads python scripts/profile_target.py
+
+The script builds a dla_34 plan at batch 32 / 512x512 with seeded weights and runs exactly two forwards
+(one warm-up, one to be profiled); only igemm kernels are counted so weight packing does not matter."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import centerpose_b200 as cpb  # noqa: E402
+from centerpose_b200 import synth  # noqa: E402
+
+
+def main():
+    batch = int(os.environ.get("CP_PROFILE_BATCH", "32"))
+    precision = os.environ.get("CP_PRECISION", "fp32")
+    opt = cpb.default_opt("dla_34")
+    m = cpb.create_model(opt.arch, opt.heads, opt.head_conv, opt)
+    m.precision = precision
+    m.load_state_dict(synth.seeded_state_dict(m, seed=0, head_gain=6.0))
+    m = m.cuda().eval()
+    x = torch.from_numpy(synth.normalize_frames(synth.synthetic_frames(batch, 512, 512))).cuda()
+    eng = m.engine(batch, 512, 512, x.device)
+    if "--print-skip" in sys.argv:
+        ops = eng.profile(x)
+        ig = [o for o in ops if o["kind"] in (0, 1, 2)]
+        dom = max(ig, key=lambda o: o["ms"])
+        print(len(ig) * 2 + ig.index(dom))      # profile() above + warm-up forward below come first
+        return
+    eng.forward(x)
+    torch.cuda.synchronize()
+    eng.forward(x)
+    torch.cuda.synchronize()
+
+
+if __name__ == "__main__":
+    main()

@@ -35,7 +35,8 @@ import torch  # noqa: E402
 METRIC = "images/sec at 512x512 DLA-34 (dla_34 + DCNv2, 7 heads, decode + PnP)"
 UNIT = "images/s"
 GFLOP_PER_IMAGE = 85.11          # BASELINE.md section 2 (reference graph, 2*MAC)
-HEAD_GAIN = 6.0                  # scales the random final 1x1 head weights so a few centres pass vis_thresh
+HEAD_GAIN = 1.0
+TARGET_OBJECTS = 4               # centre peaks per frame that pass vis_thresh after bias calibration (Objectron-like density)
 N_ROTATE = 6                     # distinct input batches rotated through (6 x 25 MB uint8 + activations >> 126 MB L2)
 
 
@@ -106,6 +107,25 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def calibrate_head_bias(model, eng, x, target=TARGET_OBJECTS):
+    """Random-init weights put every (or no) heat-map peak above the thresholds, which would make the decode /
+    PnP stage do 100 (or 0) solves per frame.  Shift the two heat-map biases -- setup only, outside any timed
+    region -- so that about `target` centre peaks per frame pass vis_thresh = 0.3 and about `target` peaks per
+    keypoint channel pass the 0.1 gate, i.e. a realistic scene density for the post-network stage."""
+    import math
+    import torch.nn.functional as F
+    out = eng.forward(x)
+    with torch.no_grad():
+        for head, thr in (("hm", math.log(0.3 / 0.7)), ("hm_hp", math.log(0.1 / 0.9))):
+            hm = out[head]
+            pk = F.max_pool2d(hm, 3, 1, 1)
+            peaks = torch.where(pk == hm, hm, torch.full_like(hm, -1e9)).flatten(2)      # [B, C, HW]
+            kth = peaks.topk(target + 1, dim=2).values
+            mid = (0.5 * (kth[..., target - 1] + kth[..., target])).median()
+            getattr(model, head)[2].bias += (thr - mid)
+    return model
+
+
 def cpu_reference_step(sd, opt, frames_u8, cam, budget_s=None):
     """The reference algorithm (oracle port) for a few frames on the host: returns the number of images
     processed (stops early, after at least one frame, once `budget_s` seconds of wall clock are spent)."""
@@ -138,7 +158,7 @@ def run_reference(args):
     torch.set_num_threads(cores)
     opt = cpb.default_opt("dla_34")
     m = cpb.create_model(opt.arch, opt.heads, opt.head_conv, opt)
-    sd = synth.seeded_state_dict(m, seed=0, offset_std=1.0, head_gain=HEAD_GAIN)
+    sd = synth.seeded_state_dict(m, seed=0, offset_std=0.3, head_gain=HEAD_GAIN)
     cam = synth.default_camera(512, 512)
     per_step = args.ref_images
     frames = synth.synthetic_frames(per_step, 512, 512, seed=317)
@@ -175,6 +195,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4, help="frames of the in-run cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", default="", help="write the per-op table (cp_plan_profile) to this path")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "bf16"],
+                    help="fp32: CUDA-core parity mode; tf32x3: tcgen05 fp32-equivalent; bf16: tcgen05 fast mode")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -203,11 +225,17 @@ def main():
 
     opt = cpb.default_opt("dla_34")
     model = cpb.create_model(opt.arch, opt.heads, opt.head_conv, opt)
-    sd = synth.seeded_state_dict(model, seed=0, offset_std=1.0, head_gain=HEAD_GAIN)
+    model.precision = args.precision
+    sd = synth.seeded_state_dict(model, seed=0, offset_std=0.3, head_gain=HEAD_GAIN)
     model.load_state_dict(sd)
     det = cpb.ObjectPoseDetector(opt, model=model)
     cam = synth.default_camera(512, 512)
     eng = det.model.engine(B, 512, 512, dev)
+    calib = torch.from_numpy(synth.normalize_frames(synth.synthetic_frames(B, 512, 512, seed=317 + 1000 * rank))).to(dev)
+    calibrate_head_bias(det.model, eng, calib)
+    eng = det.model.engine(B, 512, 512, dev)            # re-ingests the calibrated weights
+    sd = {k: v.detach().cpu() for k, v in det.model.state_dict().items()}
+    del calib
     prm = decode_params(opt)
     meta = make_meta(B, np.array([256., 256.], np.float32), 512.0, 512, 512, cam).to(dev)
 
@@ -277,7 +305,9 @@ def main():
     achieved = dom["flops"] / (dom_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "igemm_fp32_kernel<64,NHWC> @ " + dom["name"], "ms_per_launch": dom_ms,
+                "traffic": None,
+                "kernel": ("igemm_fp32_kernel<64,NHWC> @ " if args.precision == "fp32" else "igemm_umma_kernel @ ") + dom["name"],
+                "ms_per_launch": dom_ms,
                 "share_of_forward": dom_ms / tot_ms, "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)",
                 "algorithmic_flops_per_launch": dom["flops"],
                 "network_tflops": GFLOP_PER_IMAGE * 1e9 * B / (tot_ms * 1e-3) / 1e12}
@@ -308,11 +338,15 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "bf16": "bf16"}[args.precision], "data": "synthetic",
             "config": {"workload": "batch=%d synthetic 512x512 frames per GPU, dla_34 + DCNv2, 7 heads, K=100, rep_mode 1, "
                                    "decode + soft-NMS + PnP" % B,
-                       "global_batch": B * world, "precision": "fp32 CUDA-core implicit GEMM (parity mode)",
-                       "weights": "seeded random init (head_gain %.1f)" % HEAD_GAIN,
+                       "global_batch": B * world,
+                       "precision": {"fp32": "fp32 CUDA-core implicit GEMM (parity mode)",
+                                     "tf32x3": "tcgen05 kind::tf32 3-term split (fp32-equivalent parity mode)",
+                                     "bf16": "tcgen05 kind::f16 bf16 operands, fp32 accumulate (fast mode)"}[args.precision],
+                       "weights": "seeded random init; hm / hm_hp biases calibrated so ~%d peaks per frame pass the "
+                                  "thresholds" % TARGET_OBJECTS,
                        "l2": "inputs rotate over %d distinct batches; per-step activations (~8 GB) exceed the 126 MB L2" % N_ROTATE,
                        "detections_per_image": det_per_img, "parallelism": "dp%d, 1 all-gather of pose records" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

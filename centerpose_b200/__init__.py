@@ -10,7 +10,7 @@ no PyTorch or CPU fallback.
 """
 from .model import create_model, load_model, save_model, DLASegB200          # noqa: F401
 from .detector import ObjectPoseDetector, detector_factory                   # noqa: F401
-from .engine import Engine, decode_pnp, decode_params, make_meta, dcn_v2_forward, preprocess  # noqa: F401
+from .engine import Engine, decode_pnp, decode_params, make_meta, dcn_v2_forward, preprocess, conv2d_nhwc  # noqa: F401
 from .opts import default_opt                                                # noqa: F401
 
 __version__ = "0.1.0"

@@ -21,6 +21,7 @@ CP_ARCH_DLAV1_34 = 1
 CP_PREC_FP32 = 0
 CP_PREC_TF32X3 = 1
 CP_PREC_BF16 = 2
+PRECISIONS = {"fp32": CP_PREC_FP32, "tf32x3": CP_PREC_TF32X3, "bf16": CP_PREC_BF16}
 
 # cp_pose_field
 P_SCORE, P_CLS, P_STATUS, P_NPTS, P_BBOX, P_CT, P_KPS = 0, 1, 2, 3, 4, 8, 10
@@ -37,6 +38,7 @@ EXPORTS = [
     "cp_version", "cp_last_error", "cp_plan_create", "cp_plan_destroy", "cp_plan_load_weights",
     "cp_forward", "cp_plan_bytes", "cp_plan_forward_launches", "cp_decode_workspace_bytes",
     "cp_decode_pnp", "cp_infer", "cp_dcn_v2_forward", "cp_preprocess", "cp_plan_num_ops", "cp_plan_profile",
+    "cp_dcn_v2_forward_ex", "cp_conv2d",
 ]
 
 
@@ -112,6 +114,8 @@ def load():
     L.cp_infer.argtypes = [vp, i32, vp, vp, vp, vp, ctypes.POINTER(CpDecodeParams), vp,
                            ctypes.POINTER(vp), vp, vp, vp, vp]
     L.cp_dcn_v2_forward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.cp_dcn_v2_forward_ex.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    L.cp_conv2d.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     L.cp_preprocess.argtypes = [vp, vp, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_float),
                                 ctypes.POINTER(ctypes.c_float), vp]
     for name in EXPORTS:

@@ -62,9 +62,17 @@ struct IgemmParams {
   int omStride;
   int mask_is_logit;     // 1: apply sigmoid to channels 18..26
   int mode;
+  const void* wgt_umma;  // tcgen05 path: pre-swizzled weight tiles (igemm_umma.cu), else null
 };
 
 int launch_igemm_fp32(const IgemmParams& p, cudaStream_t stream);
+
+// tcgen05 tensor-core path (igemm_umma.cu).  prec: 0 = bf16 (kind::f16), 1 = tf32 x 3 (kind::tf32, fp32-equivalent)
+bool umma_supported(const IgemmParams& p, int prec);
+size_t umma_weight_bytes(int Kreal, int CoutPad, int prec);
+int launch_pack_umma_weight(const float* src_k_by_ld, int ld, int Kreal, int Cout, int CoutPad, int prec, void* dst,
+                            cudaStream_t s);
+int launch_igemm_umma(const IgemmParams& p, int prec, cudaStream_t stream);
 
 // elementwise / data-movement kernels (elementwise.cu)
 int launch_maxpool2(const float* in, float* out, int B, int H, int W, int C, cudaStream_t s);

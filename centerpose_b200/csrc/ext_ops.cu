@@ -59,9 +59,94 @@ using namespace cp;
 
 extern "C" {
 
+static int prec_code(int32_t precision, int* prec) {
+  if (precision == CP_PREC_FP32) *prec = -1;
+  else if (precision == CP_PREC_BF16) *prec = 0;
+  else if (precision == CP_PREC_TF32X3) *prec = 1;
+  else return fail(CP_ERR_INVALID, "unknown precision");
+  return CP_OK;
+}
+
+// run one implicit-GEMM launch with the kernel family selected by `prec` (weights already packed as fp32 [K][CoutPad])
+static int run_igemm(IgemmParams& p, int prec, int Kreal, cudaStream_t s) {
+  if (prec < 0) return launch_igemm_fp32(p, s);
+  if (!umma_supported(p, prec)) return fail(CP_ERR_INVALID, "shape not supported by the tcgen05 kernel");
+  void* tiles = nullptr;
+  CP_CUDA_CHECK(cudaMallocAsync(&tiles, umma_weight_bytes(Kreal, p.CoutPad, prec), s));
+  int rc = launch_pack_umma_weight(p.wgt, p.CoutPad, Kreal, p.Cout, p.CoutPad, prec, tiles, s);
+  if (!rc) {
+    p.wgt_umma = tiles;
+    rc = launch_igemm_umma(p, prec, s);
+  }
+  cudaFreeAsync(tiles, s);
+  return rc;
+}
+
+int cp_conv2d(const float* x, const float* weight, const float* bias, const float* residual, float* out, int32_t B,
+              int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k, int32_t stride, int32_t pad, int32_t relu,
+              int32_t precision, void* stream_) {
+  if (!x || !weight || !out) return fail(CP_ERR_INVALID, "cp_conv2d: null argument");
+  if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || k <= 0 || stride <= 0 || pad < 0)
+    return fail(CP_ERR_INVALID, "cp_conv2d: bad shape");
+  if (Cin % 16 || Cout % 4) return fail(CP_ERR_INVALID, "cp_conv2d: Cin must be a multiple of 16 and Cout of 4");
+  int prec;
+  int rc = prec_code(precision, &prec);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int CoPad = round_up(Cout, Cout > 32 ? 64 : (Cout > 16 ? 32 : 16));
+  const int K = k * k * Cin;
+  float* scratch = nullptr;
+  CP_CUDA_CHECK(cudaMallocAsync(&scratch, ((size_t)K * CoPad + CoPad) * sizeof(float), s));
+  float* wp = scratch;
+  float* bp = wp + (size_t)K * CoPad;
+  do {
+    if ((rc = launch_pack_conv_weight(weight, nullptr, wp, Cout, Cin, k, k, CoPad, K, CoPad, 0, s))) break;
+    if ((rc = launch_pack_bias(bias, nullptr, nullptr, nullptr, nullptr, nullptr, bp, Cout, CoPad, 0.f, s))) break;
+    IgemmParams p{};
+    p.nsrc = 1;
+    p.src[0] = x;
+    p.srcC[0] = Cin;
+    p.srcStride[0] = Cin;
+    p.B = B;
+    p.Hin = H;
+    p.Win = W;
+    p.Cin = Cin;
+    p.kh = p.kw = k;
+    p.stride = stride;
+    p.pad = pad;
+    p.Hout = (H + 2 * pad - k) / stride + 1;
+    p.Wout = (W + 2 * pad - k) / stride + 1;
+    p.Cout = Cout;
+    p.CoutPad = CoPad;
+    p.Kpad = K;
+    p.wgt = wp;
+    p.bias = bp;
+    p.residual = residual;
+    p.resStride = Cout;
+    p.relu = relu;
+    p.out = out;
+    p.outStride = Cout;
+    p.mode = IGEMM_NHWC_VEC;
+    rc = run_igemm(p, prec, K, s);
+  } while (0);
+  cudaFreeAsync(scratch, s);
+  return rc;
+}
+
 int cp_dcn_v2_forward(const float* input, const float* weight, const float* bias, const float* offset,
                       const float* mask, float* output, int32_t B, int32_t C, int32_t H, int32_t W, int32_t Co,
                       void* stream_) {
+  return cp_dcn_v2_forward_ex(input, weight, bias, offset, mask, output, B, C, H, W, Co, CP_PREC_FP32, stream_);
+}
+
+int cp_dcn_v2_forward_ex(const float* input, const float* weight, const float* bias, const float* offset,
+                         const float* mask, float* output, int32_t B, int32_t C, int32_t H, int32_t W, int32_t Co,
+                         int32_t precision, void* stream_) {
+  int prec;
+  {
+    int rcp = prec_code(precision, &prec);
+    if (rcp) return rcp;
+  }
   if (!input || !weight || !bias || !offset || !mask || !output)
     return fail(CP_ERR_INVALID, "cp_dcn_v2_forward: null argument");
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || Co <= 0) return fail(CP_ERR_INVALID, "cp_dcn_v2_forward: bad shape");
@@ -110,7 +195,7 @@ int cp_dcn_v2_forward(const float* input, const float* weight, const float* bias
     p.omStride = 32;
     p.mask_is_logit = 0;
     p.mode = IGEMM_DCN;
-    rc = launch_igemm_fp32(p, s);
+    rc = run_igemm(p, prec, 9 * Cp, s);
   } while (0);
   cudaFreeAsync(scratch, s);
   return rc;

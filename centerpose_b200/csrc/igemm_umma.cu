@@ -1,0 +1,534 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a.
+//
+//   D[m, n] = sum_k A[m, k] * W[n, k]      m = output pixel, n = output channel, k = (tap, ci)
+//
+// Same contract as igemm_fp32.cu (IgemmParams: NHWC fp32 activations, channel-concatenated
+// sources, DCNv2 deformable gather, fused bias / residual / ReLU epilogue) but the contraction
+// runs on the tensor cores:
+//   * warps 0-3 (128 threads, one per tile row) GATHER the A tile -- plain im2col rows or the
+//     bilinear deformable samples of dcn_v2_im2col_cuda.cu:125-195 -- convert it and write it
+//     straight into shared memory in the canonical K-major SWIZZLE_128B layout the UMMA
+//     descriptor expects (a data-dependent gather cannot come from TMA);
+//   * warp 5 streams the weight tiles, pre-swizzled at load time into exact smem images, with one
+//     cp.async.bulk (UBLKCP) per stage, completing on the stage's mbarrier;
+//   * warp 4 (one elected lane) issues tcgen05.mma (M = 128, N = BN, cta_group::1) with the
+//     accumulator in TMEM and releases stages with tcgen05.commit;
+//   * warps 0-3 then read the accumulator with tcgen05.ld (lane == output row) and run the epilogue.
+// Precisions:
+//   PREC_BF16   kind::f16, bf16 operands, fp32 accumulate                       (fast mode)
+//   PREC_TF32X3 kind::tf32, 3-term split  a_hi*b_hi + a_lo*b_hi + a_hi*b_lo     (fp32-equivalent mode)
+// Every mbarrier wait carries a clock64 watchdog that traps instead of hanging the GPU.
+#include "common.cuh"
+
+namespace cp {
+namespace {
+
+constexpr int UM_BM = 128;
+constexpr int UM_THREADS = 192;
+constexpr uint32_t ROW_BYTES = 128;        // one K block = 128 bytes per row (64 bf16 / 32 tf32)
+constexpr uint32_t A_TILE_BYTES = UM_BM * ROW_BYTES;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("igemm_umma: mbarrier watchdog (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <int KIND_TF32>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (KIND_TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4, [16,30) LBO >> 4 (ignored for swizzled K-major, 1), [32,46) SBO >> 4 = 1024 B between
+//   8-row groups, [46,48) version = 1, [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1 << 4), a/b format (1 = bf16, 2 = tf32) at
+// [7,10) / [10,13), K-major A and B (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int n, int fmt) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half <- a
+  return r;
+}
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+struct UmmaSmem {   // control block at the head of dynamic smem (the tiles follow, 1024-byte aligned)
+  unsigned long long full[8];
+  unsigned long long empty[8];
+  unsigned long long accum_full;
+  uint32_t tmem_base;
+};
+
+template <int PREC>
+struct PrecTraits;
+template <>
+struct PrecTraits<0> {   // bf16
+  static constexpr int kElems = 64, kChunkCh = 8, kTilesA = 1, kTf32 = 0, kFmt = 1;
+};
+template <>
+struct PrecTraits<1> {   // tf32 x 3
+  static constexpr int kElems = 32, kChunkCh = 4, kTilesA = 2, kTf32 = 1, kFmt = 2;
+};
+
+// ------------------------------------------------------------------ the kernel
+template <int PREC, int MODE>
+__global__ void __launch_bounds__(UM_THREADS, 1) igemm_umma_kernel(const IgemmParams p, const int BN, const int STAGES) {
+  using T = PrecTraits<PREC>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  UmmaSmem* ctl = reinterpret_cast<UmmaSmem*>(smem);
+  const uint32_t tiles0 = (smem_u32(smem) + 1024u + 1023u) & ~1023u;   // first tile, 1024-aligned
+  const uint32_t b_tile_bytes = (uint32_t)BN * ROW_BYTES * T::kTilesA; // hi (+ lo) weight tiles of one stage
+  const uint32_t a_bytes = A_TILE_BYTES * T::kTilesA;
+  const uint32_t stage_bytes = a_bytes + b_tile_bytes;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = p.B * p.Hout * p.Wout;
+  const int n_tile = blockIdx.x;
+  const int m0 = blockIdx.y * UM_BM;
+  const int K = p.kh * p.kw * p.Cin;
+  const int KB = (K + T::kElems - 1) / T::kElems;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&ctl->full[s]), 128 + 1);
+      mbar_init(smem_u32(&ctl->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&ctl->accum_full), 1);
+    fence_mbar_init();
+  }
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < BN) tmem_cols <<= 1;
+  if (warp == 4) {
+    tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp < 4) {
+    // =========================== A producers: thread == tile row ===========================
+    const int r = tid;
+    const int m = m0 + r;
+    const bool valid = m < M;
+    int ox = 0, oy = 0, n = 0;
+    if (valid) {
+      ox = m % p.Wout;
+      int t = m / p.Wout;
+      oy = t % p.Hout;
+      n = t / p.Hout;
+    }
+    const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+    const uint32_t sw = (uint32_t)(r & 7);
+    // DCN sampling state of the current tap
+    float w1 = 0, w2 = 0, w3 = 0, w4 = 0, mk = 0;
+    int o1 = 0, o2 = 0, o3 = 0, o4 = 0;
+    int cur_tap = -1;
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < KB; ++kb) {
+      mbar_wait(smem_u32(&ctl->empty[stage]), phase ^ 1u);
+      const uint32_t a_hi = tiles0 + (uint32_t)stage * stage_bytes + row_off;
+      const uint32_t a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll 2
+      for (int q = 0; q < 8; ++q) {
+        const int k0 = kb * T::kElems + q * T::kChunkCh;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        if (valid && k0 < K) {
+          const int tap = k0 / p.Cin;
+          const int c = k0 - tap * p.Cin;
+          if (MODE == IGEMM_DCN) {
+            if (tap != cur_tap) {
+              cur_tap = tap;
+              const int ky = tap / 3, kx = tap - ky * 3;
+              const float* om = p.offmask + ((size_t)(n * p.Hout + oy) * p.Wout + ox) * p.omStride;
+              const float dy = __ldg(om + 2 * tap), dx = __ldg(om + 2 * tap + 1);
+              float mm = __ldg(om + 18 + tap);
+              if (p.mask_is_logit) mm = 1.0f / (1.0f + expf(-mm));
+              const float h_im = (float)(oy - 1 + ky) + dy, w_im = (float)(ox - 1 + kx) + dx;
+              const int H = p.Hin, W = p.Win;
+              w1 = w2 = w3 = w4 = 0.f;
+              mk = 0.f;
+              o1 = o2 = o3 = o4 = 0;
+              if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
+                const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+                const int h_high = h_low + 1, w_high = w_low + 1;
+                const float lh = h_im - (float)h_low, lw = w_im - (float)w_low;
+                const float hh = 1.f - lh, hw = 1.f - lw;
+                const bool t_ok = h_low >= 0, b_ok = h_high <= H - 1, l_ok = w_low >= 0, r_ok = w_high <= W - 1;
+                const int hl = t_ok ? h_low : 0, hb = b_ok ? h_high : H - 1;
+                const int wl = l_ok ? w_low : 0, wr = r_ok ? w_high : W - 1;
+                w1 = (t_ok && l_ok) ? hh * hw : 0.f;
+                w2 = (t_ok && r_ok) ? hh * lw : 0.f;
+                w3 = (b_ok && l_ok) ? lh * hw : 0.f;
+                w4 = (b_ok && r_ok) ? lh * lw : 0.f;
+                o1 = hl * W + wl;
+                o2 = hl * W + wr;
+                o3 = hb * W + wl;
+                o4 = hb * W + wr;
+                mk = mm;
+              }
+            }
+            const int ss = p.srcStride[0];
+            const float* base = p.src[0] + (size_t)n * p.Hin * p.Win * ss + c;
+#pragma unroll
+            for (int h4 = 0; h4 < T::kChunkCh / 4; ++h4) {
+              const float4 c1 = __ldg(reinterpret_cast<const float4*>(base + (size_t)o1 * ss) + h4);
+              const float4 c2 = __ldg(reinterpret_cast<const float4*>(base + (size_t)o2 * ss) + h4);
+              const float4 c3 = __ldg(reinterpret_cast<const float4*>(base + (size_t)o3 * ss) + h4);
+              const float4 c4 = __ldg(reinterpret_cast<const float4*>(base + (size_t)o4 * ss) + h4);
+              v[h4 * 4 + 0] = (w1 * c1.x + w2 * c2.x + w3 * c3.x + w4 * c4.x) * mk;
+              v[h4 * 4 + 1] = (w1 * c1.y + w2 * c2.y + w3 * c3.y + w4 * c4.y) * mk;
+              v[h4 * 4 + 2] = (w1 * c1.z + w2 * c2.z + w3 * c3.z + w4 * c4.z) * mk;
+              v[h4 * 4 + 3] = (w1 * c1.w + w2 * c2.w + w3 * c3.w + w4 * c4.w) * mk;
+            }
+          } else {
+            const int ky = tap / p.kw, kx = tap - ky * p.kw;
+            const int iy = oy * p.stride - p.pad + ky, ix = ox * p.stride - p.pad + kx;
+            if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) {
+              int s = 0, cb = 0;
+              while (s + 1 < p.nsrc && c >= cb + p.srcC[s]) {
+                cb += p.srcC[s];
+                ++s;
+              }
+              const float* sp = p.src[s] + ((size_t)(n * p.Hin + iy) * p.Win + ix) * p.srcStride[s] + (c - cb);
+#pragma unroll
+              for (int h4 = 0; h4 < T::kChunkCh / 4; ++h4) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(sp) + h4);
+                v[h4 * 4 + 0] = x.x;
+                v[h4 * 4 + 1] = x.y;
+                v[h4 * 4 + 2] = x.z;
+                v[h4 * 4 + 3] = x.w;
+              }
+            }
+          }
+        }
+        const uint32_t coff = ((uint32_t)q ^ sw) << 4;
+        if (PREC == 0) {
+          st_shared_v4(a_hi + coff, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                       pack_bf16x2(v[6], v[7]));
+        } else {
+          float h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            h[j] = tf32_round(v[j]);
+            l[j] = tf32_round(v[j] - h[j]);
+          }
+          st_shared_v4(a_hi + coff, __float_as_uint(h[0]), __float_as_uint(h[1]), __float_as_uint(h[2]),
+                       __float_as_uint(h[3]));
+          st_shared_v4(a_lo + coff, __float_as_uint(l[0]), __float_as_uint(l[1]), __float_as_uint(l[2]),
+                       __float_as_uint(l[3]));
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&ctl->full[stage]));
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+
+    // =========================== epilogue: TMEM lane == tile row ===========================
+    mbar_wait(smem_u32(&ctl->accum_full), 0u);
+    tc_fence_after();
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t rr[16];
+      tmem_ld16(lane_base + (uint32_t)c0, rr);     // warp-collective: every lane participates
+      tmem_ld_wait();
+      const int nb = n_tile * BN + c0;
+      if (valid && nb < p.Cout) {
+        float vv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) vv[j] = __uint_as_float(rr[j]) + __ldg(p.bias + nb + j);
+        if (p.residual && !p.res_after_relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < p.Cout) vv[j] += __ldg(p.residual + (size_t)m * p.resStride + nb + j);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) vv[j] = fmaxf(vv[j], 0.f);
+        }
+        if (p.residual && p.res_after_relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < p.Cout) vv[j] += __ldg(p.residual + (size_t)m * p.resStride + nb + j);
+        }
+        if (p.out_nchw) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < p.Cout) p.out[(((size_t)n * p.Cout + nb + j) * p.Hout + oy) * p.Wout + ox] = vv[j];
+        } else {
+          float* o = p.out + (size_t)m * p.outStride + nb;
+          if (nb + 15 < p.Cout) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(vv[j], vv[j + 1], vv[j + 2], vv[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (nb + j < p.Cout) o[j] = vv[j];
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // =========================== MMA issuer (one lane) ===========================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN, T::kFmt);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(smem_u32(&ctl->full[stage]), phase);
+        tc_fence_after();
+        const uint32_t a_hi = tiles0 + (uint32_t)stage * stage_bytes;
+        const uint32_t b_hi = a_hi + a_bytes;
+        const uint64_t da_hi = make_desc(a_hi), db_hi = make_desc(b_hi);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {       // 4 x 32-byte K slices per 128-byte row
+          const uint64_t adv = (uint64_t)(k * 2);
+          if (PREC == 0) {
+            umma<0>(tmem_base, da_hi + adv, db_hi + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          } else {
+            const uint64_t da_lo = make_desc(a_hi + A_TILE_BYTES), db_lo = make_desc(b_hi + (uint32_t)BN * ROW_BYTES);
+            umma<1>(tmem_base, da_lo + adv, db_hi + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma<1>(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
+            umma<1>(tmem_base, da_hi + adv, db_hi + adv, idesc, 1u);
+          }
+        }
+        umma_commit(smem_u32(&ctl->empty[stage]));     // frees the stage when these MMAs have read it
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(smem_u32(&ctl->accum_full));
+    }
+    __syncwarp();
+  } else {
+    // =========================== weight-tile loader (one lane) ===========================
+    if (lane == 0) {
+      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wgt_umma) + (size_t)n_tile * KB * b_tile_bytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(smem_u32(&ctl->empty[stage]), phase ^ 1u);
+        const uint32_t bar = smem_u32(&ctl->full[stage]);
+        mbar_arrive_expect_tx(bar, b_tile_bytes);
+        bulk_g2s(tiles0 + (uint32_t)stage * stage_bytes + a_bytes, wsrc + (size_t)kb * b_tile_bytes, b_tile_bytes, bar);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------ weight tiling
+// src: fp32 [Ksrc][ld] (k-major rows, BN-folded, the matrix the fp32 kernel consumes);
+// dst: for n_tile, for kb: [hi tile | lo tile], each BN rows x 128 bytes in the SWIZZLE_128B K-major image.
+template <int PREC>
+__global__ void pack_umma_weight_kernel(const float* __restrict__ src, int ld, int K, int Cout, int BN, int n_tiles,
+                                        int KB, unsigned char* __restrict__ dst) {
+  using T = PrecTraits<PREC>;
+  const size_t total = (size_t)n_tiles * KB * BN * 8;   // one thread per 16-byte chunk
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int q = i & 7;
+    size_t t = i >> 3;
+    const int nr = t % BN;
+    t /= BN;
+    const int kb = t % KB;
+    const int nt = t / KB;
+    const int n = nt * BN + nr;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kb * T::kElems + q * T::kChunkCh + j;
+      v[j] = (j < T::kChunkCh && k < K && n < Cout) ? src[(size_t)k * ld + n] : 0.f;
+    }
+    const size_t tile = ((size_t)nt * KB + kb) * (size_t)BN * ROW_BYTES * T::kTilesA;
+    const size_t off = (size_t)(nr >> 3) * 1024 + (size_t)(nr & 7) * 128 + (size_t)((q ^ (nr & 7)) << 4);
+    if (PREC == 0) {
+      uint4 w;
+      w.x = pack_bf16x2(v[0], v[1]);
+      w.y = pack_bf16x2(v[2], v[3]);
+      w.z = pack_bf16x2(v[4], v[5]);
+      w.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(dst + tile + off) = w;
+    } else {
+      float h[4], l[4];
+      for (int j = 0; j < 4; ++j) {
+        h[j] = tf32_round(v[j]);
+        l[j] = tf32_round(v[j] - h[j]);
+      }
+      *reinterpret_cast<float4*>(dst + tile + off) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(dst + tile + (size_t)BN * ROW_BYTES + off) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
+}  // namespace
+
+// ---- host side -----------------------------------------------------------------------------------------------
+int umma_tile_n(int CoutPad) { return CoutPad <= 256 ? CoutPad : 256; }
+
+bool umma_supported(const IgemmParams& p, int prec) {
+  if (p.mode != IGEMM_NHWC_VEC && p.mode != IGEMM_DCN) return false;
+  const int ch = prec == 0 ? 8 : 4;
+  if (p.Cin % ch) return false;
+  for (int s = 0; s < p.nsrc; ++s)
+    if (p.srcC[s] % ch || p.srcStride[s] % 4) return false;
+  const int bn = umma_tile_n(p.CoutPad);
+  if (bn % 16 || p.CoutPad % bn) return false;
+  return true;
+}
+
+size_t umma_weight_bytes(int Kreal, int CoutPad, int prec) {
+  const int elems = prec == 0 ? 64 : 32;
+  const int KB = (Kreal + elems - 1) / elems;
+  const int bn = umma_tile_n(CoutPad);
+  return (size_t)(CoutPad / bn) * KB * bn * ROW_BYTES * (prec == 0 ? 1 : 2);
+}
+
+int launch_pack_umma_weight(const float* src, int ld, int Kreal, int Cout, int CoutPad, int prec, void* dst,
+                            cudaStream_t s) {
+  const int elems = prec == 0 ? 64 : 32;
+  const int KB = (Kreal + elems - 1) / elems;
+  const int bn = umma_tile_n(CoutPad);
+  const int nt = CoutPad / bn;
+  size_t total = (size_t)nt * KB * bn * 8;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (prec == 0)
+    pack_umma_weight_kernel<0><<<blocks, 256, 0, s>>>(src, ld, Kreal, Cout, bn, nt, KB, (unsigned char*)dst);
+  else
+    pack_umma_weight_kernel<1><<<blocks, 256, 0, s>>>(src, ld, Kreal, Cout, bn, nt, KB, (unsigned char*)dst);
+  CP_LAUNCH_CHECK("pack_umma_weight_kernel");
+  return CP_OK;
+}
+
+int launch_igemm_umma(const IgemmParams& p, int prec, cudaStream_t stream) {
+  if (!umma_supported(p, prec)) return fail(CP_ERR_INVALID, "igemm_umma: unsupported shape");
+  if (!p.wgt_umma) return fail(CP_ERR_INVALID, "igemm_umma: weight tiles missing");
+  const int bn = umma_tile_n(p.CoutPad);
+  const int tilesA = prec == 0 ? 1 : 2;
+  const size_t stage_bytes = (size_t)A_TILE_BYTES * tilesA + (size_t)bn * ROW_BYTES * tilesA;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 6) stages = 6;
+  if (stages < 2) return fail(CP_ERR_INVALID, "igemm_umma: tile does not fit shared memory");
+  const size_t smem = 2048 + stages * stage_bytes;
+  const int M = p.B * p.Hout * p.Wout;
+  dim3 grid(p.CoutPad / bn, (M + UM_BM - 1) / UM_BM);
+  void (*kern)(const IgemmParams, const int, const int) = nullptr;
+  if (prec == 0)
+    kern = (p.mode == IGEMM_DCN) ? igemm_umma_kernel<0, IGEMM_DCN> : igemm_umma_kernel<0, IGEMM_NHWC_VEC>;
+  else
+    kern = (p.mode == IGEMM_DCN) ? igemm_umma_kernel<1, IGEMM_DCN> : igemm_umma_kernel<1, IGEMM_NHWC_VEC>;
+  static thread_local bool configured[4] = {false, false, false, false};
+  const int slot = prec * 2 + (p.mode == IGEMM_DCN ? 1 : 0);
+  if (!configured[slot]) {
+    CP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[slot] = true;
+  }
+  kern<<<grid, UM_THREADS, smem, stream>>>(p, bn, stages);
+  CP_LAUNCH_CHECK("igemm_umma_kernel");
+  return CP_OK;
+}
+
+}  // namespace cp

@@ -51,6 +51,9 @@ struct Op {
   Act res;
   int kh = 1, kw = 1, stride = 1, pad = 0, Cin = 0, Cout = 0, CoutPad = 0, Kpad = 0;
   size_t w_off = 0, b_off = 0;
+  int w_ld = 0;            // leading dimension of the fp32 packed weight matrix
+  bool use_umma = false;   // run on the tcgen05 kernel
+  size_t umma_off = 0;     // bytes into the plan's tensor-core weight-tile buffer
   Act om;
   // up-sample
   int f = 0;
@@ -104,6 +107,9 @@ struct cp_plan {
   void* decode_ws = nullptr;
   size_t decode_ws_bytes = 0;
   double* gn_stats = nullptr;
+  int prec = -1;                 // -1 fp32 CUDA cores, 0 bf16 tcgen05, 1 tf32x3 tcgen05
+  unsigned char* umma_wts = nullptr;
+  size_t umma_bytes = 0;
 };
 
 namespace cp {
@@ -176,6 +182,7 @@ struct Builder {
       op.out.W = Wo;
     }
     // weights
+    op.w_ld = op.CoutPad;
     if (shared_w != (size_t)-1) {
       op.w_off = shared_w;
       op.b_off = shared_b;
@@ -276,6 +283,7 @@ struct Builder {
     om.Kpad = 9 * x.C;
     om.out = new_act(32, x.H, x.W);
     om.out.C = 27;
+    om.w_ld = 32;
     om.w_off = walloc((size_t)om.Kpad * 32);
     om.b_off = walloc(32);
     add_pack(p + ".conv.conv_offset_mask.weight", p + ".conv.conv_offset_mask.bias", "", 27, x.C, 3, 32,
@@ -298,6 +306,7 @@ struct Builder {
     op.relu = true;
     op.om = om.out;
     op.out = new_act(Cout, x.H, x.W);
+    op.w_ld = op.CoutPad;
     op.w_off = walloc((size_t)op.Kpad * op.CoutPad);
     op.b_off = walloc(op.CoutPad);
     add_pack(p + ".conv.weight", p + ".conv.bias", p + ".actf.0", Cout, x.C, 3, op.CoutPad, op.Kpad,
@@ -523,6 +532,27 @@ int build_graph(cp_plan* P) {
   }
   P->act_floats = b.act_cur;
   P->w_floats = b.w_cur;
+  // tensor-core eligibility + weight-tile storage
+  P->umma_bytes = 0;
+  if (P->prec >= 0) {
+    for (auto& op : P->ops) {
+      if (op.type != OP_IGEMM) continue;
+      IgemmParams q{};
+      q.mode = op.mode;
+      q.nsrc = op.nsrc;
+      q.Cin = op.Cin;
+      q.CoutPad = op.CoutPad;
+      for (int i = 0; i < op.nsrc; ++i) {
+        q.srcC[i] = op.src[i].C;
+        q.srcStride[i] = op.src[i].stride;
+      }
+      if (op.src[0].ext < 0 && umma_supported(q, P->prec)) {
+        op.use_umma = true;
+        op.umma_off = P->umma_bytes;
+        P->umma_bytes += (umma_weight_bytes(op.kh * op.kw * op.Cin, op.CoutPad, P->prec) + 1023) / 1024 * 1024;
+      }
+    }
+  }
   return CP_OK;
 }
 
@@ -541,8 +571,8 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
   if (!cfg || !out) return fail(CP_ERR_INVALID, "cp_plan_create: null argument");
   if (cfg->arch != CP_ARCH_DLA34 && cfg->arch != CP_ARCH_DLAV1_34)
     return fail(CP_ERR_INVALID, "cp_plan_create: unknown arch");
-  if (cfg->precision != CP_PREC_FP32)
-    return fail(CP_ERR_INVALID, "cp_plan_create: only CP_PREC_FP32 is built in this version");
+  if (cfg->precision != CP_PREC_FP32 && cfg->precision != CP_PREC_TF32X3 && cfg->precision != CP_PREC_BF16)
+    return fail(CP_ERR_INVALID, "cp_plan_create: unknown precision");
   if (cfg->height % 32 || cfg->width % 32 || cfg->height <= 0 || cfg->width <= 0)
     return fail(CP_ERR_INVALID, "cp_plan_create: height/width must be positive multiples of 32");
   if (cfg->max_batch <= 0 || cfg->num_heads <= 0 || cfg->num_heads > CP_MAX_HEADS)
@@ -562,6 +592,7 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
   P->B = cfg->max_batch;
   P->H = cfg->height;
   P->W = cfg->width;
+  P->prec = cfg->precision == CP_PREC_BF16 ? 0 : (cfg->precision == CP_PREC_TF32X3 ? 1 : -1);
   CP_CUDA_CHECK(cudaSetDevice(cfg->device));
   int rc = build_graph(P.get());
   if (rc) return rc;
@@ -569,6 +600,7 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
   CP_CUDA_CHECK(cudaMalloc(&P->wts, P->w_floats * sizeof(float)));
   CP_CUDA_CHECK(cudaMemset(P->wts, 0, P->w_floats * sizeof(float)));
   CP_CUDA_CHECK(cudaMalloc(&P->gn_stats, sizeof(double) * (size_t)P->B * 64 * 2));
+  if (P->umma_bytes) CP_CUDA_CHECK(cudaMalloc(&P->umma_wts, P->umma_bytes));
   int n = 0;
   for (auto& op : P->ops) n += (op.type == OP_GN_RELU) ? 2 : 1;
   P->launches = n;
@@ -581,6 +613,7 @@ int cp_plan_destroy(cp_plan* P) {
   cudaFree(P->act);
   cudaFree(P->wts);
   cudaFree(P->gn_stats);
+  if (P->umma_wts) cudaFree(P->umma_wts);
   if (P->decode_ws) cudaFree(P->decode_ws);
   delete P;
   return CP_OK;
@@ -645,6 +678,13 @@ int cp_plan_load_weights(cp_plan* P, const char* const* names, const void* const
         break;
       }
     }
+  }
+  // second pass: tensor-core weight tiles are cut from the finished fp32 matrices (merged matrices are complete now)
+  for (auto& op : P->ops) {
+    if (op.type != OP_IGEMM || !op.use_umma) continue;
+    if ((rc = launch_pack_umma_weight(P->wts + op.w_off, op.w_ld, op.kh * op.kw * op.Cin, op.Cout, op.CoutPad, P->prec,
+                                      P->umma_wts + op.umma_off, s)))
+      return rc;
   }
   P->loaded = true;
   return CP_OK;
@@ -712,7 +752,12 @@ static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* 
           p.mask_is_logit = 1;
         }
         p.mode = op.mode;
-        if ((rc = launch_igemm_fp32(p, s))) return rc;
+        if (op.use_umma) {
+          p.wgt_umma = P->umma_wts + op.umma_off;
+          if ((rc = launch_igemm_umma(p, P->prec, s))) return rc;
+        } else if ((rc = launch_igemm_fp32(p, s))) {
+          return rc;
+        }
         break;
       }
       case OP_MAXPOOL:

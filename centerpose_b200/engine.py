@@ -245,7 +245,25 @@ def preprocess(frames_u8, dst_h, dst_w, mean, std, out=None):
     return out
 
 
-def dcn_v2_forward(inp, weight, bias, offset, mask, kh=3, kw=3, sh=1, sw=1, ph=1, pw=1, dh=1, dw=1, dg=1):
+def conv2d_nhwc(x, weight, bias=None, residual=None, stride=1, pad=0, relu=False, precision="fp32"):
+    """cp_conv2d: x [B,H,W,Cin] NHWC fp32 CUDA, weight OIHW -> [B,Ho,Wo,Cout] NHWC."""
+    L = _lib.load()
+    if not x.is_cuda:
+        raise RuntimeError("centerpose_b200 conv2d_nhwc needs CUDA tensors (no CPU fallback)")
+    B, H, W, Cin = x.shape
+    Cout, _, k, _ = weight.shape
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    out = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+    ts = [t.contiguous().float() if t is not None else None for t in (x, weight, bias, residual)]
+    with torch.cuda.device(x.device):
+        rc = L.cp_conv2d(_ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(ts[3]), _ptr(out), B, H, W, Cin, Cout, k, stride,
+                         pad, int(relu), _lib.PRECISIONS[precision], _stream())
+    _lib.check(rc, "cp_conv2d")
+    return out
+
+
+def dcn_v2_forward(inp, weight, bias, offset, mask, kh=3, kw=3, sh=1, sw=1, ph=1, pw=1, dh=1, dw=1, dg=1,
+                   precision="fp32"):
     """`_ext.dcn_v2_forward` signature (DCNv2/src/vision.cpp:4-9) on top of cp_dcn_v2_forward."""
     if (kh, kw, sh, sw, ph, pw, dh, dw, dg) != (3, 3, 1, 1, 1, 1, 1, 1, 1):
         raise RuntimeError("centerpose_b200 dcn_v2_forward: only 3x3 / stride 1 / pad 1 / dilation 1 / "
@@ -258,8 +276,8 @@ def dcn_v2_forward(inp, weight, bias, offset, mask, kh=3, kw=3, sh=1, sw=1, ph=1
     out = torch.empty((B, Co, H, W), dtype=torch.float32, device=inp.device)
     ts = [t.contiguous().float() for t in (inp, weight, bias, offset, mask)]
     with torch.cuda.device(inp.device):
-        rc = L.cp_dcn_v2_forward(_ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(ts[3]), _ptr(ts[4]), _ptr(out),
-                                 B, C, H, W, Co, _stream())
+        rc = L.cp_dcn_v2_forward_ex(_ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(ts[3]), _ptr(ts[4]), _ptr(out),
+                                    B, C, H, W, Co, _lib.PRECISIONS[precision], _stream())
     _lib.check(rc, "cp_dcn_v2_forward")
     out._cp_keep = ts
     return out

@@ -255,6 +255,19 @@ int cp_dcn_v2_forward(const float* input, const float* weight, const float* bias
                       const float* offset, const float* mask, float* output,
                       int32_t B, int32_t C, int32_t H, int32_t W, int32_t Co, void* stream);
 
+/* Same op with an explicit cp_precision (CP_PREC_FP32: CUDA cores; CP_PREC_TF32X3 / CP_PREC_BF16: tcgen05). */
+int cp_dcn_v2_forward_ex(const float* input, const float* weight, const float* bias, const float* offset,
+                         const float* mask, float* output, int32_t B, int32_t C, int32_t H, int32_t W,
+                         int32_t Co, int32_t precision, void* stream);
+
+/* ---- single fused convolution (building block of the plan, exposed for layer-level parity tests) ----
+ * out = [relu]( conv2d(x, weight, stride, pad) + bias [+ residual] ); x / residual / out are device fp32
+ * NHWC ([B,H,W,Cin] / [B,Ho,Wo,Cout]), weight is OIHW like nn.Conv2d (pose_dla_dcn.py:37-44);
+ * Cin % 16 == 0, Cout % 4 == 0.  bias / residual may be NULL. */
+int cp_conv2d(const float* x, const float* weight, const float* bias, const float* residual, float* out,
+              int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k, int32_t stride,
+              int32_t pad, int32_t relu, int32_t precision, void* stream);
+
 /* ---- batched pre-process (next-row f-1) ------------------------------------ */
 /* frames: device uint8 [B, src_h, src_w, 3] (BGR as cv2.imread gives);
  * out: device fp32 NCHW [B,3,dst_h,dst_w] = (bilinear-warped/255 - mean)/std with the

@@ -66,7 +66,7 @@ def make_net():
     for name, arch, trk, B, H, W, wseed, iseed in NET_CASES:
         opt = ref_shims.make_opt(arch, tracking_task=trk)
         ours = cpb.create_model(opt.arch, opt.heads, opt.head_conv, cpb.default_opt(arch, tracking_task=trk))
-        sd = synth.seeded_state_dict(ours, seed=wseed, offset_std=1.5)
+        sd = synth.seeded_state_dict(ours, seed=wseed, offset_std=0.3)
         ref = ref_create(opt.arch, opt.heads, opt.head_conv, opt).eval()
         missing = ref.load_state_dict(sd, strict=True)
         x, extra = net_inputs(B, H, W, iseed, trk)
@@ -74,7 +74,7 @@ def make_net():
             out = ref(torch.from_numpy(x), *[torch.from_numpy(extra[k]) if k in extra else None
                                              for k in ("pre_img", "pre_hm", "pre_hm_hp")])[-1]
         np.savez_compressed(os.path.join(GOLD, name + ".npz"), arch=arch, tracking=int(trk), batch=B, H=H, W=W,
-                            wseed=wseed, iseed=iseed, offset_std=1.5,
+                            wseed=wseed, iseed=iseed, offset_std=0.3,
                             **{"head_" + k: v.numpy() for k, v in out.items()})
         print(name, {k: float(v.abs().max()) for k, v in out.items()}, missing)
 

@@ -30,7 +30,7 @@ def main():
         ops = eng.profile(x)
         ig = [o for o in ops if o["kind"] in (0, 1, 2)]
         dom = max(ig, key=lambda o: o["ms"])
-        print(len(ig) * 2 + ig.index(dom))      # profile() above + warm-up forward below come first
+        print(len(ig) + ig.index(dom))          # the profiled run does one warm-up forward first
         return
     eng.forward(x)
     torch.cuda.synchronize()

@@ -10,12 +10,13 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 TOL_KP_PX = 1e-3        # keypoint pixel coordinates
 TOL_QUAT = 1e-4         # sign-normalised quaternion
 TOL_LOC_REL = 1e-4      # location, relative to |t|
-# Network heads (stage B): max-abs <= 1e-3 * max|head| against the reference's fp32 CPU heads.  SURVEY.md 8d
-# proposed 1e-4, but the reference's OWN fp32 CPU path is 1.3e-4 .. 3.9e-4 away from an fp64 evaluation of the
-# same graph on the seeded-weight fixtures (fp32 rounding amplified through ~50 layers and the deformable
-# sampling), so two correct fp32 implementations cannot agree to 1e-4.  tests/test_gpu_net.py additionally
-# requires the CUDA heads to be no further from the fp64 truth than 2x the reference's fp32 path.
-TOL_HEAD_REL = 1e-3
+# Network heads (stage B): max-abs <= 3e-4 * max|head| against the reference's fp32 CPU heads, on fixtures whose
+# DCN offset convs have std 0.3.  (The graph amplifies fp32 rounding through ~50 layers and 16 deformable
+# samplings: on these fixtures the reference's OWN fp32 CPU path is up to 6e-5 away from an fp64 evaluation of
+# the same graph, and with offset std 1.5 on noise frames it is 16-23 % away, so SURVEY.md 8d's 1e-4 between two
+# fp32 implementations is only meaningful relative to that floor.)  tests/test_gpu_net.py additionally requires
+# the CUDA heads to be no further from the fp64 truth than 4x the reference's fp32 path + 3e-5.
+TOL_HEAD_REL = 3e-4
 
 
 def golden(name):

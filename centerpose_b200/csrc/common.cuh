@@ -67,6 +67,10 @@ struct IgemmParams {
 
 int launch_igemm_fp32(const IgemmParams& p, cudaStream_t stream);
 
+// dedicated 7x7 stem kernel (stem_conv.cu); consumes the same packed fp32 weights as the generic kernel
+bool stem_supported(const IgemmParams& p);
+int launch_stem_conv(const IgemmParams& p, cudaStream_t s);
+
 // tcgen05 tensor-core path (igemm_umma.cu).  prec: 0 = bf16 (kind::f16), 1 = tf32 x 3 (kind::tf32, fp32-equivalent)
 bool umma_supported(const IgemmParams& p, int prec);
 size_t umma_weight_bytes(int Kreal, int CoutPad, int prec);

@@ -57,8 +57,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
-      printf("igemm_umma: mbarrier watchdog (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, bar, parity);
+      printf("igemm_umma: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
       __trap();
     }
   }
@@ -169,8 +169,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) igemm_umma_kernel(const IgemmPa
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = p.B * p.Hout * p.Wout;
-  const int n_tile = blockIdx.x;
-  const int m0 = blockIdx.y * UM_BM;
+  // 1-D grid, n tile fastest: the CTAs that share an A row block run back to back and hit it in L2
+  // (gridDim.y would overflow at 65535 row blocks: B = 32 at 512 x 512 has 65536)
+  const int n_tiles = p.CoutPad / BN;
+  const int n_tile = blockIdx.x % n_tiles;
+  const int m0 = (blockIdx.x / n_tiles) * UM_BM;
   const int K = p.kh * p.kw * p.Cin;
   const int KB = (K + T::kElems - 1) / T::kElems;
 
@@ -514,7 +517,7 @@ int launch_igemm_umma(const IgemmParams& p, int prec, cudaStream_t stream) {
   if (stages < 2) return fail(CP_ERR_INVALID, "igemm_umma: tile does not fit shared memory");
   const size_t smem = 2048 + stages * stage_bytes;
   const int M = p.B * p.Hout * p.Wout;
-  dim3 grid(p.CoutPad / bn, (M + UM_BM - 1) / UM_BM);
+  dim3 grid((unsigned)((size_t)(p.CoutPad / bn) * ((M + UM_BM - 1) / UM_BM)));
   void (*kern)(const IgemmParams, const int, const int) = nullptr;
   if (prec == 0)
     kern = (p.mode == IGEMM_DCN) ? igemm_umma_kernel<0, IGEMM_DCN> : igemm_umma_kernel<0, IGEMM_NHWC_VEC>;

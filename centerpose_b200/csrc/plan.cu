@@ -755,6 +755,8 @@ static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* 
         if (op.use_umma) {
           p.wgt_umma = P->umma_wts + op.umma_off;
           if ((rc = launch_igemm_umma(p, P->prec, s))) return rc;
+        } else if (stem_supported(p)) {
+          if ((rc = launch_stem_conv(p, s))) return rc;
         } else if ((rc = launch_igemm_fp32(p, s))) {
           return rc;
         }

@@ -75,7 +75,8 @@ def test_forward_512_matches_oracle(cplib):
     x = torch.from_numpy(synth.normalize_frames(synth.synthetic_frames(1, 512, 512, seed=317)))
     want = net_ref.forward(x, sd, opt.heads, "dla_34")
     out = m(x.cuda())[-1]
-    _check(out, {h: v.numpy() for h, v in want.items()}, truth=_truth(x.numpy(), sd, opt.heads, "dla_34"))
+    # at 512 x 512 the fp32 floor is higher (the reference's fp32 heads are 1.2e-4 .. 2.6e-4 from the fp64 truth)
+    _check(out, {h: v.numpy() for h, v in want.items()}, rel=1e-3, truth=_truth(x.numpy(), sd, opt.heads, "dla_34"))
 
 
 def test_batch_invariance_and_replay(cplib):

@@ -24,7 +24,8 @@ namespace cp {
 namespace {
 
 constexpr int UM_BM = 128;
-constexpr int UM_THREADS = 192;
+constexpr int UM_PROD_WARPS = 8;            // A-gather warps: two threads per tile row, 4 chunks each
+constexpr int UM_THREADS = (UM_PROD_WARPS + 2) * 32;
 constexpr uint32_t ROW_BYTES = 128;        // one K block = 128 bytes per row (64 bf16 / 32 tf32)
 constexpr uint32_t A_TILE_BYTES = UM_BM * ROW_BYTES;
 
@@ -158,7 +159,7 @@ struct PrecTraits<1> {   // tf32 x 3
 
 // ------------------------------------------------------------------ the kernel
 template <int PREC, int MODE>
-__global__ void __launch_bounds__(UM_THREADS, 1) igemm_umma_kernel(const IgemmParams p, const int BN, const int STAGES) {
+__global__ void __launch_bounds__(UM_THREADS) igemm_umma_kernel(const IgemmParams p, const int BN, const int STAGES) {
   using T = PrecTraits<PREC>;
   extern __shared__ __align__(1024) unsigned char smem[];
   UmmaSmem* ctl = reinterpret_cast<UmmaSmem*>(smem);
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) igemm_umma_kernel(const IgemmPa
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&ctl->full[s]), 128 + 1);
+      mbar_init(smem_u32(&ctl->full[s]), UM_PROD_WARPS * 32 + 1);
       mbar_init(smem_u32(&ctl->empty[s]), 1);
     }
     mbar_init(smem_u32(&ctl->accum_full), 1);
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) igemm_umma_kernel(const IgemmPa
   }
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < BN) tmem_cols <<= 1;
-  if (warp == 4) {
+  if (warp == UM_PROD_WARPS) {
     tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     tmem_relinquish();
   }
@@ -196,10 +197,162 @@ __global__ void __launch_bounds__(UM_THREADS, 1) igemm_umma_kernel(const IgemmPa
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
-  if (warp < 4) {
-    // =========================== A producers: thread == tile row ===========================
-    const int r = tid;
-    const int m = m0 + r;
+  if (warp < UM_PROD_WARPS) {
+    // =========================== A producers: two threads per tile row, four 16-byte chunks each ===============
+    {
+      const int r = tid >> 1;
+      const int qbase = (tid & 1) * 4;
+      const int m = m0 + r;
+      const bool valid = m < M;
+      int ox = 0, oy = 0, n = 0;
+      if (valid) {
+        ox = m % p.Wout;
+        int t = m / p.Wout;
+        oy = t % p.Hout;
+        n = t / p.Hout;
+      }
+      const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+      const uint32_t sw = (uint32_t)(r & 7);
+      // DCN sampling state of the current tap
+      float w1 = 0, w2 = 0, w3 = 0, w4 = 0, mk = 0;
+      int o1 = 0, o2 = 0, o3 = 0, o4 = 0;
+      int cur_tap = -1;
+      constexpr int F4 = T::kChunkCh / 4;     // float4 loads per chunk (2 for bf16, 1 for tf32)
+
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < KB; ++kb) {
+        // ---- issue every global load of this thread's 4 chunks first (memory-level parallelism) ...
+        float4 ld[4][MODE == IGEMM_DCN ? 4 * F4 : F4];
+        bool live[4];
+#pragma unroll
+        for (int qi = 0; qi < 4; ++qi) {
+          const int k0 = kb * T::kElems + (qbase + qi) * T::kChunkCh;
+          live[qi] = false;
+#pragma unroll
+          for (int j = 0; j < (MODE == IGEMM_DCN ? 4 * F4 : F4); ++j) ld[qi][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid && k0 < K) {
+            const int tap = k0 / p.Cin;
+            const int c = k0 - tap * p.Cin;
+            if (MODE == IGEMM_DCN) {
+              if (tap != cur_tap) {
+                cur_tap = tap;
+                const int ky = tap / 3, kx = tap - ky * 3;
+                const float* om = p.offmask + ((size_t)(n * p.Hout + oy) * p.Wout + ox) * p.omStride;
+                const float dy = __ldg(om + 2 * tap), dx = __ldg(om + 2 * tap + 1);
+                float mm = __ldg(om + 18 + tap);
+                if (p.mask_is_logit) mm = 1.0f / (1.0f + expf(-mm));
+                const float h_im = (float)(oy - 1 + ky) + dy, w_im = (float)(ox - 1 + kx) + dx;
+                const int H = p.Hin, W = p.Win;
+                w1 = w2 = w3 = w4 = 0.f;
+                mk = 0.f;
+                o1 = o2 = o3 = o4 = 0;
+                if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
+                  const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+                  const int h_high = h_low + 1, w_high = w_low + 1;
+                  const float lh = h_im - (float)h_low, lw = w_im - (float)w_low;
+                  const float hh = 1.f - lh, hw = 1.f - lw;
+                  const bool t_ok = h_low >= 0, b_ok = h_high <= H - 1, l_ok = w_low >= 0, r_ok = w_high <= W - 1;
+                  const int hl = t_ok ? h_low : 0, hb = b_ok ? h_high : H - 1;
+                  const int wl = l_ok ? w_low : 0, wr = r_ok ? w_high : W - 1;
+                  w1 = (t_ok && l_ok) ? hh * hw : 0.f;
+                  w2 = (t_ok && r_ok) ? hh * lw : 0.f;
+                  w3 = (b_ok && l_ok) ? lh * hw : 0.f;
+                  w4 = (b_ok && r_ok) ? lh * lw : 0.f;
+                  o1 = hl * W + wl;
+                  o2 = hl * W + wr;
+                  o3 = hb * W + wl;
+                  o4 = hb * W + wr;
+                  mk = mm;
+                }
+              }
+              live[qi] = true;
+              const int ss = p.srcStride[0];
+              const float* base = p.src[0] + (size_t)n * p.Hin * p.Win * ss + c;
+#pragma unroll
+              for (int h4 = 0; h4 < F4; ++h4) {
+                ld[qi][0 * F4 + h4] = __ldg(reinterpret_cast<const float4*>(base + (size_t)o1 * ss) + h4);
+                ld[qi][1 * F4 + h4] = __ldg(reinterpret_cast<const float4*>(base + (size_t)o2 * ss) + h4);
+                ld[qi][2 * F4 + h4] = __ldg(reinterpret_cast<const float4*>(base + (size_t)o3 * ss) + h4);
+                ld[qi][3 * F4 + h4] = __ldg(reinterpret_cast<const float4*>(base + (size_t)o4 * ss) + h4);
+              }
+            } else {
+              const int ky = tap / p.kw, kx = tap - ky * p.kw;
+              const int iy = oy * p.stride - p.pad + ky, ix = ox * p.stride - p.pad + kx;
+              if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) {
+                int s = 0, cb = 0;
+                while (s + 1 < p.nsrc && c >= cb + p.srcC[s]) {
+                  cb += p.srcC[s];
+                  ++s;
+                }
+                const float* sp = p.src[s] + ((size_t)(n * p.Hin + iy) * p.Win + ix) * p.srcStride[s] + (c - cb);
+#pragma unroll
+                for (int h4 = 0; h4 < F4; ++h4) ld[qi][h4] = __ldg(reinterpret_cast<const float4*>(sp) + h4);
+              }
+            }
+          }
+        }
+        // ---- ... then wait for the stage, convert and store into the swizzled K-major tile
+        mbar_wait(smem_u32(&ctl->empty[stage]), phase ^ 1u);
+        const uint32_t a_hi = tiles0 + (uint32_t)stage * stage_bytes + row_off;
+        const uint32_t a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+        for (int qi = 0; qi < 4; ++qi) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = 0.f;
+          if (MODE == IGEMM_DCN) {
+            if (live[qi]) {
+#pragma unroll
+              for (int h4 = 0; h4 < F4; ++h4) {
+                const float4 c1 = ld[qi][0 * F4 + h4], c2 = ld[qi][1 * F4 + h4], c3 = ld[qi][2 * F4 + h4],
+                             c4 = ld[qi][3 * F4 + h4];
+                // NOTE: w1..w4 / mk belong to the tap of the LAST chunk decoded above; chunks of one thread share a
+                // tap whenever Cin is a multiple of the thread's 4-chunk span (all DCN layers: Cin % 64 == 0)
+                v[h4 * 4 + 0] = (w1 * c1.x + w2 * c2.x + w3 * c3.x + w4 * c4.x) * mk;
+                v[h4 * 4 + 1] = (w1 * c1.y + w2 * c2.y + w3 * c3.y + w4 * c4.y) * mk;
+                v[h4 * 4 + 2] = (w1 * c1.z + w2 * c2.z + w3 * c3.z + w4 * c4.z) * mk;
+                v[h4 * 4 + 3] = (w1 * c1.w + w2 * c2.w + w3 * c3.w + w4 * c4.w) * mk;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int h4 = 0; h4 < F4; ++h4) {
+              v[h4 * 4 + 0] = ld[qi][h4].x;
+              v[h4 * 4 + 1] = ld[qi][h4].y;
+              v[h4 * 4 + 2] = ld[qi][h4].z;
+              v[h4 * 4 + 3] = ld[qi][h4].w;
+            }
+          }
+          const uint32_t coff = ((uint32_t)(qbase + qi) ^ sw) << 4;
+          if (PREC == 0) {
+            st_shared_v4(a_hi + coff, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                         pack_bf16x2(v[6], v[7]));
+          } else {
+            float h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              h[j] = tf32_round(v[j]);
+              l[j] = tf32_round(v[j] - h[j]);
+            }
+            st_shared_v4(a_hi + coff, __float_as_uint(h[0]), __float_as_uint(h[1]), __float_as_uint(h[2]),
+                         __float_as_uint(h[3]));
+            st_shared_v4(a_lo + coff, __float_as_uint(l[0]), __float_as_uint(l[1]), __float_as_uint(l[2]),
+                         __float_as_uint(l[3]));
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(smem_u32(&ctl->full[stage]));
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+
+    // =========================== epilogue (warps 0-3): TMEM lane == tile row ===========================
+    if (warp < 4) {
+    const int m = m0 + tid;
     const bool valid = m < M;
     int ox = 0, oy = 0, n = 0;
     if (valid) {
@@ -208,120 +361,6 @@ __global__ void __launch_bounds__(UM_THREADS, 1) igemm_umma_kernel(const IgemmPa
       oy = t % p.Hout;
       n = t / p.Hout;
     }
-    const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-    const uint32_t sw = (uint32_t)(r & 7);
-    // DCN sampling state of the current tap
-    float w1 = 0, w2 = 0, w3 = 0, w4 = 0, mk = 0;
-    int o1 = 0, o2 = 0, o3 = 0, o4 = 0;
-    int cur_tap = -1;
-
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int kb = 0; kb < KB; ++kb) {
-      mbar_wait(smem_u32(&ctl->empty[stage]), phase ^ 1u);
-      const uint32_t a_hi = tiles0 + (uint32_t)stage * stage_bytes + row_off;
-      const uint32_t a_lo = a_hi + A_TILE_BYTES;
-#pragma unroll 2
-      for (int q = 0; q < 8; ++q) {
-        const int k0 = kb * T::kElems + q * T::kChunkCh;
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.f;
-        if (valid && k0 < K) {
-          const int tap = k0 / p.Cin;
-          const int c = k0 - tap * p.Cin;
-          if (MODE == IGEMM_DCN) {
-            if (tap != cur_tap) {
-              cur_tap = tap;
-              const int ky = tap / 3, kx = tap - ky * 3;
-              const float* om = p.offmask + ((size_t)(n * p.Hout + oy) * p.Wout + ox) * p.omStride;
-              const float dy = __ldg(om + 2 * tap), dx = __ldg(om + 2 * tap + 1);
-              float mm = __ldg(om + 18 + tap);
-              if (p.mask_is_logit) mm = 1.0f / (1.0f + expf(-mm));
-              const float h_im = (float)(oy - 1 + ky) + dy, w_im = (float)(ox - 1 + kx) + dx;
-              const int H = p.Hin, W = p.Win;
-              w1 = w2 = w3 = w4 = 0.f;
-              mk = 0.f;
-              o1 = o2 = o3 = o4 = 0;
-              if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
-                const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-                const int h_high = h_low + 1, w_high = w_low + 1;
-                const float lh = h_im - (float)h_low, lw = w_im - (float)w_low;
-                const float hh = 1.f - lh, hw = 1.f - lw;
-                const bool t_ok = h_low >= 0, b_ok = h_high <= H - 1, l_ok = w_low >= 0, r_ok = w_high <= W - 1;
-                const int hl = t_ok ? h_low : 0, hb = b_ok ? h_high : H - 1;
-                const int wl = l_ok ? w_low : 0, wr = r_ok ? w_high : W - 1;
-                w1 = (t_ok && l_ok) ? hh * hw : 0.f;
-                w2 = (t_ok && r_ok) ? hh * lw : 0.f;
-                w3 = (b_ok && l_ok) ? lh * hw : 0.f;
-                w4 = (b_ok && r_ok) ? lh * lw : 0.f;
-                o1 = hl * W + wl;
-                o2 = hl * W + wr;
-                o3 = hb * W + wl;
-                o4 = hb * W + wr;
-                mk = mm;
-              }
-            }
-            const int ss = p.srcStride[0];
-            const float* base = p.src[0] + (size_t)n * p.Hin * p.Win * ss + c;
-#pragma unroll
-            for (int h4 = 0; h4 < T::kChunkCh / 4; ++h4) {
-              const float4 c1 = __ldg(reinterpret_cast<const float4*>(base + (size_t)o1 * ss) + h4);
-              const float4 c2 = __ldg(reinterpret_cast<const float4*>(base + (size_t)o2 * ss) + h4);
-              const float4 c3 = __ldg(reinterpret_cast<const float4*>(base + (size_t)o3 * ss) + h4);
-              const float4 c4 = __ldg(reinterpret_cast<const float4*>(base + (size_t)o4 * ss) + h4);
-              v[h4 * 4 + 0] = (w1 * c1.x + w2 * c2.x + w3 * c3.x + w4 * c4.x) * mk;
-              v[h4 * 4 + 1] = (w1 * c1.y + w2 * c2.y + w3 * c3.y + w4 * c4.y) * mk;
-              v[h4 * 4 + 2] = (w1 * c1.z + w2 * c2.z + w3 * c3.z + w4 * c4.z) * mk;
-              v[h4 * 4 + 3] = (w1 * c1.w + w2 * c2.w + w3 * c3.w + w4 * c4.w) * mk;
-            }
-          } else {
-            const int ky = tap / p.kw, kx = tap - ky * p.kw;
-            const int iy = oy * p.stride - p.pad + ky, ix = ox * p.stride - p.pad + kx;
-            if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) {
-              int s = 0, cb = 0;
-              while (s + 1 < p.nsrc && c >= cb + p.srcC[s]) {
-                cb += p.srcC[s];
-                ++s;
-              }
-              const float* sp = p.src[s] + ((size_t)(n * p.Hin + iy) * p.Win + ix) * p.srcStride[s] + (c - cb);
-#pragma unroll
-              for (int h4 = 0; h4 < T::kChunkCh / 4; ++h4) {
-                const float4 x = __ldg(reinterpret_cast<const float4*>(sp) + h4);
-                v[h4 * 4 + 0] = x.x;
-                v[h4 * 4 + 1] = x.y;
-                v[h4 * 4 + 2] = x.z;
-                v[h4 * 4 + 3] = x.w;
-              }
-            }
-          }
-        }
-        const uint32_t coff = ((uint32_t)q ^ sw) << 4;
-        if (PREC == 0) {
-          st_shared_v4(a_hi + coff, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                       pack_bf16x2(v[6], v[7]));
-        } else {
-          float h[4], l[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            h[j] = tf32_round(v[j]);
-            l[j] = tf32_round(v[j] - h[j]);
-          }
-          st_shared_v4(a_hi + coff, __float_as_uint(h[0]), __float_as_uint(h[1]), __float_as_uint(h[2]),
-                       __float_as_uint(h[3]));
-          st_shared_v4(a_lo + coff, __float_as_uint(l[0]), __float_as_uint(l[1]), __float_as_uint(l[2]),
-                       __float_as_uint(l[3]));
-        }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(smem_u32(&ctl->full[stage]));
-      if (++stage == STAGES) {
-        stage = 0;
-        phase ^= 1u;
-      }
-    }
-
-    // =========================== epilogue: TMEM lane == tile row ===========================
     mbar_wait(smem_u32(&ctl->accum_full), 0u);
     tc_fence_after();
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -365,7 +404,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) igemm_umma_kernel(const IgemmPa
         }
       }
     }
-  } else if (warp == 4) {
+    }
+  } else if (warp == UM_PROD_WARPS) {
     // =========================== MMA issuer (one lane) ===========================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BN, T::kFmt);
@@ -420,7 +460,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) igemm_umma_kernel(const IgemmPa
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == UM_PROD_WARPS) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // ------------------------------------------------------------------ weight tiling

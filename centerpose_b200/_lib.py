@@ -21,7 +21,8 @@ CP_ARCH_DLAV1_34 = 1
 CP_PREC_FP32 = 0
 CP_PREC_TF32X3 = 1
 CP_PREC_BF16 = 2
-PRECISIONS = {"fp32": CP_PREC_FP32, "tf32x3": CP_PREC_TF32X3, "bf16": CP_PREC_BF16}
+CP_PREC_TF32 = 3
+PRECISIONS = {"fp32": CP_PREC_FP32, "tf32x3": CP_PREC_TF32X3, "bf16": CP_PREC_BF16, "tf32": CP_PREC_TF32}
 
 # cp_pose_field
 P_SCORE, P_CLS, P_STATUS, P_NPTS, P_BBOX, P_CT, P_KPS = 0, 1, 2, 3, 4, 8, 10

@@ -98,6 +98,14 @@ int launch_group_norm_relu(float* x, const float* gamma, const float* beta, int 
 int launch_gru_gates(const float* xi, const float* hh, const float* hprev, float* hout, int B_HW, int C,
                      int first_step, cudaStream_t s);
 
+// TMA-fed shifted-window tcgen05 convolution (conv_tma.cu): stride-1 1x1 / 3x3 over NHWC fp32, kind::tf32
+bool tma_conv_supported(const IgemmParams& p);
+size_t tma_weight_bytes(int Cin, int taps, int CoutPad);
+int launch_pack_tma_weight(const float* src_k_by_ld, int ld, int Cin, int taps, int Cout, int CoutPad, int round_tf32,
+                           void* dst, cudaStream_t s);
+int tma_conv_encode(const IgemmParams& p, int Bmax, void* maps_out /* 4 x 128 bytes */);
+int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, int use_base_offset, cudaStream_t stream);
+
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 }  // namespace cp

@@ -1,0 +1,532 @@
+// TMA-fed tcgen05 convolution ("shifted-window" implicit GEMM) for stride-1 1x1 / 3x3 convolutions
+// over NHWC fp32 activations, kind::tf32.
+//
+// Idea: pad the image by one pixel and flatten it to a 1-D sequence of positions with pitch Wt = W + 2.
+// A 3x3 tap (ky, kx) is then a CONSTANT offset (ky-1)*Wt + (kx-1) in that sequence, so the A operand of
+// tap (ky,kx) for 128 consecutive output positions is simply the same shared-memory slab read from a
+// different start row.  One TMA tiled load (box = 32 channels x Wt columns x BOXH rows, out-of-bounds
+// elements zero-filled = the convolution padding) brings a [positions][32 ch] slab of 128-byte rows in
+// SWIZZLE_128B layout; nine UMMA descriptors with different start addresses contract it against nine
+// weight tiles.  Outputs computed at the two pad columns of every row are discarded (W/Wt efficiency).
+// The im2col matrix never exists anywhere and no thread touches activation data before the epilogue.
+//
+//   warp 0 : TMA producer for activation slabs            (ring of SA stages)
+//   warp 1 : weight-tile producer, cp.async.bulk          (ring of SB stages, tiles pre-swizzled at load time)
+//   warp 2 : tcgen05.mma issuer (one lane), accumulator in TMEM; also owns the TMEM allocation
+//   warp 3 : idle
+//   warps 4-7 : epilogue, TMEM lane == flattened output position
+// Reference semantics: nn.Conv2d(k, stride 1, padding k//2) + folded BatchNorm + residual + ReLU
+// (pose_dla_dcn.py:37-62, 153-168, 496-505).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace cp {
+namespace {
+
+constexpr int TM_BM = 128;
+constexpr int TM_THREADS = 256;
+constexpr uint32_t TM_ROW = 128;      // bytes per position row: 32 fp32 channels
+
+struct TmaConvParams {
+  CUtensorMap amap[4];
+  int nsrc;
+  int srcC[4];
+  int B, H, W, Cin, Cout, CoutPad, BN;
+  int k;              // 1 or 3
+  int Wt, boxh;       // padded pitch and slab rows (k == 3)
+  int tiles_per_image;
+  uint32_t slab_bytes, slab_stride;   // TMA transaction bytes, 1024-aligned stage stride
+  int SA, SB;
+  const float* bias;
+  const float* residual;
+  int resStride, relu, res_after_relu;
+  float* out;
+  int outStride, out_nchw;
+  int round_tf32;     // round the stored outputs to tf32 (consumers feed them to kind::tf32 untouched)
+  int use_base_offset;
+  const unsigned char* wtiles;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("conv_tma: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-major SWIZZLE_128B descriptor; `saddr` may be any multiple of 16 bytes.  When the matrix does not start on a
+// 1024-byte swizzle-atom boundary the 3-bit base-offset field carries (addr >> 7) & 7.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int use_base_offset) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+  if (use_base_offset) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM_BM >> 4) << 24);
+}
+
+struct TmaCtl {
+  unsigned long long a_full[4], a_empty[4];
+  unsigned long long b_full[8], b_empty[8];
+  unsigned long long accum_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmaConvParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  TmaCtl* ctl = reinterpret_cast<TmaCtl*>(smem);
+  const uint32_t slabs0 = (smem_u32(smem) + 1024u + 1023u) & ~1023u;
+  const uint32_t btile_bytes = (uint32_t)p.BN * TM_ROW;
+  const uint32_t btiles0 = slabs0 + (uint32_t)p.SA * p.slab_stride;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = p.CoutPad / p.BN;
+  const int n_tile = blockIdx.x % n_tiles;
+  const int m_tile = blockIdx.x / n_tiles;
+  const int taps = p.k * p.k;
+  const int nslab = p.Cin / 32;
+  const int KB = nslab * taps;
+
+  // tile geometry
+  int img = 0, g0 = 0, r_lo = 0;
+  long long pos0 = 0;    // k == 1: first flattened pixel of the tile
+  if (p.k == 3) {
+    img = m_tile / p.tiles_per_image;
+    g0 = (m_tile - img * p.tiles_per_image) * TM_BM;
+    const int t = g0 - 1;
+    r_lo = (t >= 0) ? t / p.Wt : -((-t + p.Wt - 1) / p.Wt);      // floor((g0 - 1) / Wt)
+  } else {
+    pos0 = (long long)m_tile * TM_BM;
+  }
+
+  if (tid == 0) {
+    for (int s = 0; s < p.SA; ++s) {
+      mbar_init(smem_u32(&ctl->a_full[s]), 1);
+      mbar_init(smem_u32(&ctl->a_empty[s]), 1);
+    }
+    for (int s = 0; s < p.SB; ++s) {
+      mbar_init(smem_u32(&ctl->b_full[s]), 1);
+      mbar_init(smem_u32(&ctl->b_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&ctl->accum_full), 1);
+    fence_mbar_init();
+  }
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.BN) tmem_cols <<= 1;
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ===================== activation slabs via TMA =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 0; s < nslab; ++s) {
+        int src = 0, cb = 0;
+        while (src + 1 < p.nsrc && s * 32 >= cb + p.srcC[src]) {
+          cb += p.srcC[src];
+          ++src;
+        }
+        mbar_wait(smem_u32(&ctl->a_empty[stage]), phase ^ 1u);
+        const uint32_t bar = smem_u32(&ctl->a_full[stage]);
+        mbar_arrive_expect_tx(bar, p.slab_bytes);
+        const uint32_t dst = slabs0 + (uint32_t)stage * p.slab_stride;
+        if (p.k == 3)
+          tma_load_4d(dst, &p.amap[src], s * 32 - cb, -1, r_lo - 1, img, bar);
+        else
+          tma_load_2d(dst, &p.amap[src], s * 32 - cb, (int)pos0, bar);
+        if (++stage == p.SA) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== weight tiles =====================
+    if (lane == 0) {
+      const unsigned char* wsrc = p.wtiles + (size_t)n_tile * KB * btile_bytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(smem_u32(&ctl->b_empty[stage]), phase ^ 1u);
+        const uint32_t bar = smem_u32(&ctl->b_full[stage]);
+        mbar_arrive_expect_tx(bar, btile_bytes);
+        bulk_g2s(btiles0 + (uint32_t)stage * btile_bytes, wsrc + (size_t)kb * btile_bytes, btile_bytes, bar);
+        if (++stage == p.SB) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(p.BN);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int s = 0; s < nslab; ++s) {
+        mbar_wait(smem_u32(&ctl->a_full[sa]), pa);
+        tc_fence_after();
+        const uint32_t slab = slabs0 + (uint32_t)sa * p.slab_stride;
+        for (int t = 0; t < taps; ++t) {
+          mbar_wait(smem_u32(&ctl->b_full[sb]), pb);
+          tc_fence_after();
+          uint32_t a_addr = slab;
+          if (p.k == 3) {
+            const int ky = t / 3, kx = t - ky * 3;
+            a_addr += (uint32_t)(g0 + ky * p.Wt + kx - 1 - r_lo * p.Wt) * TM_ROW;
+          }
+          const uint32_t b_addr = btiles0 + (uint32_t)sb * btile_bytes;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t da = make_desc(a_addr + ks * 32, p.use_base_offset);
+            const uint64_t db = make_desc(b_addr + ks * 32, 0);
+            umma_tf32(tmem_base, da, db, idesc, (s > 0 || t > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&ctl->b_empty[sb]));
+          if (++sb == p.SB) {
+            sb = 0;
+            pb ^= 1u;
+          }
+        }
+        umma_commit(smem_u32(&ctl->a_empty[sa]));
+        if (++sa == p.SA) {
+          sa = 0;
+          pa ^= 1u;
+        }
+      }
+      umma_commit(smem_u32(&ctl->accum_full));
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM lane == flattened output position =====================
+    const int q = warp & 3;
+    const int i = q * 32 + lane;
+    bool valid;
+    int n, oy, ox;
+    if (p.k == 3) {
+      const int g = g0 + i;
+      oy = g / p.Wt;
+      const int xp = g - oy * p.Wt;
+      ox = xp - 1;
+      n = img;
+      valid = (oy < p.H) && (xp >= 1) && (xp <= p.W);
+    } else {
+      const long long pix = pos0 + i;
+      valid = pix < (long long)p.B * p.H * p.W;
+      const long long pp = valid ? pix : 0;
+      ox = (int)(pp % p.W);
+      const long long t = pp / p.W;
+      oy = (int)(t % p.H);
+      n = (int)(t / p.H);
+    }
+    const size_t m = ((size_t)n * p.H + oy) * p.W + ox;
+    mbar_wait(smem_u32(&ctl->accum_full), 0u);
+    tc_fence_after();
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      uint32_t rr[16];
+      tmem_ld16(lane_base + (uint32_t)c0, rr);
+      tmem_ld_wait();
+      const int nb = n_tile * p.BN + c0;
+      if (valid && nb < p.Cout) {
+        float vv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) vv[j] = __uint_as_float(rr[j]) + __ldg(p.bias + nb + j);
+        if (p.residual && !p.res_after_relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < p.Cout) vv[j] += __ldg(p.residual + m * p.resStride + nb + j);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) vv[j] = fmaxf(vv[j], 0.f);
+        }
+        if (p.residual && p.res_after_relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < p.Cout) vv[j] += __ldg(p.residual + m * p.resStride + nb + j);
+        }
+        if (p.round_tf32) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) vv[j] = tf32_round(vv[j]);
+        }
+        if (p.out_nchw) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < p.Cout) p.out[(((size_t)n * p.Cout + nb + j) * p.H + oy) * p.W + ox] = vv[j];
+        } else {
+          float* o = p.out + m * p.outStride + nb;
+          if (nb + 15 < p.Cout) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(vv[j], vv[j + 1], vv[j + 2], vv[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (nb + j < p.Cout) o[j] = vv[j];
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// weight tiles for the slab-major K order:  kb = slab * taps + tap,  element j of the row = channel slab*32 + j
+__global__ void pack_tma_weight_kernel(const float* __restrict__ src, int ld, int Cin, int taps, int Cout, int BN, int n_tiles,
+                                       int round_tf32, unsigned char* __restrict__ dst) {
+  const int KB = (Cin / 32) * taps;
+  const size_t total = (size_t)n_tiles * KB * BN * 8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int q = i & 7;
+    size_t t = i >> 3;
+    const int nr = t % BN;
+    t /= BN;
+    const int kb = t % KB;
+    const int nt = t / KB;
+    const int n = nt * BN + nr;
+    const int slab = kb / taps, tap = kb - slab * taps;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = tap * Cin + slab * 32 + q * 4 + j;
+      float x = (n < Cout) ? src[(size_t)k * ld + n] : 0.f;
+      v[j] = round_tf32 ? tf32_round(x) : x;
+    }
+    const size_t tile = ((size_t)nt * KB + kb) * (size_t)BN * TM_ROW;
+    const size_t off = (size_t)(nr >> 3) * 1024 + (size_t)(nr & 7) * 128 + (size_t)((q ^ (nr & 7)) << 4);
+    *reinterpret_cast<float4*>(dst + tile + off) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------- host side
+int tma_tile_n(int CoutPad) { return CoutPad <= 256 ? CoutPad : 256; }
+
+bool tma_conv_supported(const IgemmParams& p) {
+  if (p.mode != IGEMM_NHWC_VEC) return false;
+  if (!((p.kh == 1 && p.kw == 1 && p.pad == 0) || (p.kh == 3 && p.kw == 3 && p.pad == 1))) return false;
+  if (p.stride != 1) return false;
+  if (p.Cin % 32) return false;
+  for (int s = 0; s < p.nsrc; ++s)
+    if (p.srcC[s] % 32 || p.srcStride[s] % 4) return false;
+  if (p.kh == 3 && p.Win + 2 > 256) return false;
+  const int bn = tma_tile_n(p.CoutPad);
+  if (bn % 16 || p.CoutPad % bn) return false;
+  return get_encode() != nullptr;
+}
+
+size_t tma_weight_bytes(int Cin, int taps, int CoutPad) {
+  return (size_t)CoutPad * (Cin / 32) * taps * TM_ROW;
+}
+
+int launch_pack_tma_weight(const float* src, int ld, int Cin, int taps, int Cout, int CoutPad, int round_tf32, void* dst,
+                           cudaStream_t s) {
+  const int bn = tma_tile_n(CoutPad);
+  const int nt = CoutPad / bn;
+  size_t total = (size_t)nt * (Cin / 32) * taps * bn * 8;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  pack_tma_weight_kernel<<<blocks, 256, 0, s>>>(src, ld, Cin, taps, Cout, bn, nt, round_tf32, (unsigned char*)dst);
+  CP_LAUNCH_CHECK("pack_tma_weight_kernel");
+  return CP_OK;
+}
+
+// Encodes the tensor maps of the op's sources into `maps_out` (4 x 128 bytes, host memory, reusable across launches).
+int tma_conv_encode(const IgemmParams& p, int Bmax, void* maps_out) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(CP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(maps_out);
+  const int Wt = p.Win + 2;
+  const int boxh = (129 + 2 * Wt + Wt - 1) / Wt + 1;
+  for (int s = 0; s < p.nsrc; ++s) {
+    CUresult r;
+    if (p.kh == 3) {
+      cuuint64_t dims[4] = {(cuuint64_t)p.srcC[s], (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)Bmax};
+      cuuint64_t strides[3] = {(cuuint64_t)p.srcStride[s] * 4, (cuuint64_t)p.Win * p.srcStride[s] * 4,
+                               (cuuint64_t)p.Hin * p.Win * p.srcStride[s] * 4};
+      cuuint32_t box[4] = {32, (cuuint32_t)Wt, (cuuint32_t)boxh, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      r = enc(&maps[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p.src[s], dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t dims[2] = {(cuuint64_t)p.srcC[s], (cuuint64_t)Bmax * p.Hin * p.Win};
+      cuuint64_t strides[1] = {(cuuint64_t)p.srcStride[s] * 4};
+      cuuint32_t box[2] = {32, TM_BM};
+      cuuint32_t es[2] = {1, 1};
+      r = enc(&maps[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p.src[s], dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return fail(CP_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  }
+  return CP_OK;
+}
+
+int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, int use_base_offset, cudaStream_t stream) {
+  if (!p.wgt_umma) return fail(CP_ERR_INVALID, "conv_tma: weight tiles missing");
+  TmaConvParams q;
+  memset(&q, 0, sizeof(q));
+  memcpy(q.amap, maps, sizeof(CUtensorMap) * 4);
+  q.nsrc = p.nsrc;
+  for (int s = 0; s < 4; ++s) q.srcC[s] = p.srcC[s];
+  q.B = p.B;
+  q.H = p.Hin;
+  q.W = p.Win;
+  q.Cin = p.Cin;
+  q.Cout = p.Cout;
+  q.CoutPad = p.CoutPad;
+  q.BN = tma_tile_n(p.CoutPad);
+  q.k = p.kh;
+  q.Wt = p.Win + 2;
+  q.boxh = (129 + 2 * q.Wt + q.Wt - 1) / q.Wt + 1;
+  size_t m_tiles;
+  if (q.k == 3) {
+    q.tiles_per_image = (p.Hin * q.Wt + TM_BM - 1) / TM_BM;
+    m_tiles = (size_t)q.tiles_per_image * p.B;
+    q.slab_bytes = (uint32_t)q.boxh * q.Wt * TM_ROW;
+  } else {
+    q.tiles_per_image = 0;
+    m_tiles = ((size_t)p.B * p.Hin * p.Win + TM_BM - 1) / TM_BM;
+    q.slab_bytes = TM_BM * TM_ROW;
+  }
+  q.slab_stride = (q.slab_bytes + 1023u) & ~1023u;
+  const uint32_t btile = (uint32_t)q.BN * TM_ROW;
+  const size_t budget = 220 * 1024;
+  q.SA = 2;
+  if ((size_t)q.SA * q.slab_stride + 2 * btile > budget) q.SA = 1;
+  size_t left = budget - (size_t)q.SA * q.slab_stride;
+  q.SB = (int)(left / btile);
+  if (q.SB > 8) q.SB = 8;
+  if (q.SB < 2) return fail(CP_ERR_INVALID, "conv_tma: tile does not fit shared memory");
+  if (q.k == 1 && q.SA < 4) {
+    // 1x1: slabs are small (16 KB); use up to 4 stages of them
+    int sa = (int)((budget - (size_t)q.SB * btile) / q.slab_stride);
+    if (sa > 4) sa = 4;
+    if (sa > q.SA) q.SA = sa;
+  }
+  q.bias = p.bias;
+  q.residual = p.residual;
+  q.resStride = p.resStride;
+  q.relu = p.relu;
+  q.res_after_relu = p.res_after_relu;
+  q.out = p.out;
+  q.outStride = p.outStride;
+  q.out_nchw = p.out_nchw;
+  q.round_tf32 = round_out_tf32;
+  q.use_base_offset = use_base_offset;
+  q.wtiles = (const unsigned char*)p.wgt_umma;
+  const size_t smem = 2048 + (size_t)q.SA * q.slab_stride + (size_t)q.SB * btile;
+  static thread_local bool configured = false;
+  if (!configured) {
+    CP_CUDA_CHECK(cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  dim3 grid((unsigned)(m_tiles * (size_t)(p.CoutPad / q.BN)));
+  conv_tma_kernel<<<grid, TM_THREADS, smem, stream>>>(q);
+  CP_LAUNCH_CHECK("conv_tma_kernel");
+  return CP_OK;
+}
+
+}  // namespace cp

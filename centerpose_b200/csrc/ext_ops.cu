@@ -4,6 +4,8 @@
 //                        (reference: DCNv2/src/cuda/dcn_v2_cuda.cu:42-172).
 //   cp_preprocess     -- batched uint8 HWC frames -> normalised fp32 NCHW network input
 //                        (reference: detectors/base_detector.py:91-148, fix_res branch).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cp {
@@ -63,6 +65,7 @@ static int prec_code(int32_t precision, int* prec) {
   if (precision == CP_PREC_FP32) *prec = -1;
   else if (precision == CP_PREC_BF16) *prec = 0;
   else if (precision == CP_PREC_TF32X3) *prec = 1;
+  else if (precision == CP_PREC_TF32) *prec = 2;
   else return fail(CP_ERR_INVALID, "unknown precision");
   return CP_OK;
 }
@@ -70,6 +73,25 @@ static int prec_code(int32_t precision, int* prec) {
 // run one implicit-GEMM launch with the kernel family selected by `prec` (weights already packed as fp32 [K][CoutPad])
 static int run_igemm(IgemmParams& p, int prec, int Kreal, cudaStream_t s) {
   if (prec < 0) return launch_igemm_fp32(p, s);
+  if (prec == 2) {
+    if (!tma_conv_supported(p)) {
+      prec = 1;     // deformable / strided ops: 3-term split gather kernel
+    } else {
+      void* tiles = nullptr;
+      const int taps = p.kh * p.kw;
+      CP_CUDA_CHECK(cudaMallocAsync(&tiles, tma_weight_bytes(p.Cin, taps, p.CoutPad), s));
+      alignas(64) unsigned char maps[512];
+      int rc = tma_conv_encode(p, p.B, maps);
+      if (!rc) rc = launch_pack_tma_weight(p.wgt, p.CoutPad, p.Cin, taps, p.Cout, p.CoutPad, 1, tiles, s);
+      if (!rc) {
+        p.wgt_umma = tiles;
+        const char* e = getenv("CP_TMA_BASE_OFFSET");
+        rc = launch_conv_tma(p, maps, 0, e ? atoi(e) : 1, s);
+      }
+      cudaFreeAsync(tiles, s);
+      return rc;
+    }
+  }
   if (!umma_supported(p, prec)) return fail(CP_ERR_INVALID, "shape not supported by the tcgen05 kernel");
   void* tiles = nullptr;
   CP_CUDA_CHECK(cudaMallocAsync(&tiles, umma_weight_bytes(Kreal, p.CoutPad, prec), s));

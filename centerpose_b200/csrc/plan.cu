@@ -9,6 +9,7 @@
 //   pose_dla_dcn.py:457-570  DLASeg: ida_up, heads (3x3 -> [GN] -> ReLU -> 1x1), convGRU routing
 //   DCNv2/dcn_v2.py:97-128   DCN = 3x3 conv -> 27 ch (18 offsets + 9 mask logits) + deformable 3x3
 //   convGRU.py:20-94, GN.py:4-9
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -52,7 +53,9 @@ struct Op {
   int kh = 1, kw = 1, stride = 1, pad = 0, Cin = 0, Cout = 0, CoutPad = 0, Kpad = 0;
   size_t w_off = 0, b_off = 0;
   int w_ld = 0;            // leading dimension of the fp32 packed weight matrix
-  bool use_umma = false;   // run on the tcgen05 kernel
+  bool use_umma = false;   // run on the tcgen05 gather kernel
+  bool use_tma = false;    // run on the TMA-fed tcgen05 kernel (conv_tma.cu)
+  std::vector<unsigned char> tma_maps;   // 4 CUtensorMap, encoded once the arena exists
   size_t umma_off = 0;     // bytes into the plan's tensor-core weight-tile buffer
   Act om;
   // up-sample
@@ -107,7 +110,8 @@ struct cp_plan {
   void* decode_ws = nullptr;
   size_t decode_ws_bytes = 0;
   double* gn_stats = nullptr;
-  int prec = -1;                 // -1 fp32 CUDA cores, 0 bf16 tcgen05, 1 tf32x3 tcgen05
+  int prec = -1;                 // -1 fp32 CUDA cores, 0 bf16 tcgen05, 1 tf32x3 tcgen05, 2 tf32 (TMA) + tf32x3 elsewhere
+  int tma_base_offset = 1;
   unsigned char* umma_wts = nullptr;
   size_t umma_bytes = 0;
 };
@@ -546,10 +550,21 @@ int build_graph(cp_plan* P) {
         q.srcC[i] = op.src[i].C;
         q.srcStride[i] = op.src[i].stride;
       }
-      if (op.src[0].ext < 0 && umma_supported(q, P->prec)) {
+      q.kh = op.kh;
+      q.kw = op.kw;
+      q.stride = op.stride;
+      q.pad = op.pad;
+      q.Win = op.src[0].W;
+      const int gather_prec = P->prec == 2 ? 1 : P->prec;
+      if (op.src[0].ext >= 0) continue;
+      if (P->prec == 2 && tma_conv_supported(q)) {
+        op.use_tma = true;
+        op.umma_off = P->umma_bytes;
+        P->umma_bytes += (tma_weight_bytes(op.Cin, op.kh * op.kw, op.CoutPad) + 1023) / 1024 * 1024;
+      } else if (umma_supported(q, gather_prec)) {
         op.use_umma = true;
         op.umma_off = P->umma_bytes;
-        P->umma_bytes += (umma_weight_bytes(op.kh * op.kw * op.Cin, op.CoutPad, P->prec) + 1023) / 1024 * 1024;
+        P->umma_bytes += (umma_weight_bytes(op.kh * op.kw * op.Cin, op.CoutPad, gather_prec) + 1023) / 1024 * 1024;
       }
     }
   }
@@ -571,7 +586,8 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
   if (!cfg || !out) return fail(CP_ERR_INVALID, "cp_plan_create: null argument");
   if (cfg->arch != CP_ARCH_DLA34 && cfg->arch != CP_ARCH_DLAV1_34)
     return fail(CP_ERR_INVALID, "cp_plan_create: unknown arch");
-  if (cfg->precision != CP_PREC_FP32 && cfg->precision != CP_PREC_TF32X3 && cfg->precision != CP_PREC_BF16)
+  if (cfg->precision != CP_PREC_FP32 && cfg->precision != CP_PREC_TF32X3 && cfg->precision != CP_PREC_BF16 &&
+      cfg->precision != CP_PREC_TF32)
     return fail(CP_ERR_INVALID, "cp_plan_create: unknown precision");
   if (cfg->height % 32 || cfg->width % 32 || cfg->height <= 0 || cfg->width <= 0)
     return fail(CP_ERR_INVALID, "cp_plan_create: height/width must be positive multiples of 32");
@@ -592,7 +608,8 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
   P->B = cfg->max_batch;
   P->H = cfg->height;
   P->W = cfg->width;
-  P->prec = cfg->precision == CP_PREC_BF16 ? 0 : (cfg->precision == CP_PREC_TF32X3 ? 1 : -1);
+  P->prec = cfg->precision == CP_PREC_BF16 ? 0 : (cfg->precision == CP_PREC_TF32X3 ? 1 : (cfg->precision == CP_PREC_TF32 ? 2 : -1));
+  if (const char* e = getenv("CP_TMA_BASE_OFFSET")) P->tma_base_offset = atoi(e);
   CP_CUDA_CHECK(cudaSetDevice(cfg->device));
   int rc = build_graph(P.get());
   if (rc) return rc;
@@ -601,6 +618,24 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
   CP_CUDA_CHECK(cudaMemset(P->wts, 0, P->w_floats * sizeof(float)));
   CP_CUDA_CHECK(cudaMalloc(&P->gn_stats, sizeof(double) * (size_t)P->B * 64 * 2));
   if (P->umma_bytes) CP_CUDA_CHECK(cudaMalloc(&P->umma_wts, P->umma_bytes));
+  for (auto& op : P->ops) {
+    if (!op.use_tma) continue;
+    IgemmParams q{};
+    q.nsrc = op.nsrc;
+    for (int i = 0; i < op.nsrc; ++i) {
+      q.src[i] = P->act + op.src[i].off;
+      q.srcC[i] = op.src[i].C;
+      q.srcStride[i] = op.src[i].stride;
+    }
+    q.kh = op.kh;
+    q.kw = op.kw;
+    q.Hin = op.src[0].H;
+    q.Win = op.src[0].W;
+    op.tma_maps.resize(512 + 64);
+    unsigned char* mp = (unsigned char*)(((uintptr_t)op.tma_maps.data() + 63) & ~(uintptr_t)63);
+    int rc2 = tma_conv_encode(q, P->B, mp);
+    if (rc2) return rc2;
+  }
   int n = 0;
   for (auto& op : P->ops) n += (op.type == OP_GN_RELU) ? 2 : 1;
   P->launches = n;
@@ -681,10 +716,16 @@ int cp_plan_load_weights(cp_plan* P, const char* const* names, const void* const
   }
   // second pass: tensor-core weight tiles are cut from the finished fp32 matrices (merged matrices are complete now)
   for (auto& op : P->ops) {
-    if (op.type != OP_IGEMM || !op.use_umma) continue;
-    if ((rc = launch_pack_umma_weight(P->wts + op.w_off, op.w_ld, op.kh * op.kw * op.Cin, op.Cout, op.CoutPad, P->prec,
-                                      P->umma_wts + op.umma_off, s)))
-      return rc;
+    if (op.type != OP_IGEMM) continue;
+    if (op.use_tma) {
+      if ((rc = launch_pack_tma_weight(P->wts + op.w_off, op.w_ld, op.Cin, op.kh * op.kw, op.Cout, op.CoutPad, 1,
+                                       P->umma_wts + op.umma_off, s)))
+        return rc;
+    } else if (op.use_umma) {
+      if ((rc = launch_pack_umma_weight(P->wts + op.w_off, op.w_ld, op.kh * op.kw * op.Cin, op.Cout, op.CoutPad,
+                                        P->prec == 2 ? 1 : P->prec, P->umma_wts + op.umma_off, s)))
+        return rc;
+    }
   }
   P->loaded = true;
   return CP_OK;
@@ -752,9 +793,13 @@ static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* 
           p.mask_is_logit = 1;
         }
         p.mode = op.mode;
-        if (op.use_umma) {
+        if (op.use_tma) {
           p.wgt_umma = P->umma_wts + op.umma_off;
-          if ((rc = launch_igemm_umma(p, P->prec, s))) return rc;
+          const unsigned char* mp = (const unsigned char*)(((uintptr_t)op.tma_maps.data() + 63) & ~(uintptr_t)63);
+          if ((rc = launch_conv_tma(p, mp, 1, P->tma_base_offset, s))) return rc;
+        } else if (op.use_umma) {
+          p.wgt_umma = P->umma_wts + op.umma_off;
+          if ((rc = launch_igemm_umma(p, P->prec == 2 ? 1 : P->prec, s))) return rc;
         } else if (stem_supported(p)) {
           if ((rc = launch_stem_conv(p, s))) return rc;
         } else if ((rc = launch_igemm_fp32(p, s))) {

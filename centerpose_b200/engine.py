@@ -121,7 +121,7 @@ class Engine(object):
         cfg.tracking = int(tracking)
         cfg.tracking_task_gru = int(tracking_task_gru)
         cfg.max_batch, cfg.height, cfg.width = self.max_batch, self.height, self.width
-        cfg.precision = {"fp32": _lib.CP_PREC_FP32, "tf32x3": _lib.CP_PREC_TF32X3, "bf16": _lib.CP_PREC_BF16}[precision]
+        cfg.precision = _lib.PRECISIONS[precision]
         cfg.device = device_index
         cfg.head_conv = int(head_conv)
         cfg.num_heads = len(self.head_names)

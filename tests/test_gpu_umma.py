@@ -12,7 +12,7 @@ from tests.util import TOL_HEAD_REL, golden, net_case_inputs
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 2e-5, "tf32x3": 5e-5, "bf16": 1.5e-2}     # max-abs error / max|ref| of one layer
+TOL = {"fp32": 2e-5, "tf32x3": 5e-5, "bf16": 1.5e-2, "tf32": 4e-3}     # max-abs error / max|ref| of one layer
 
 
 def _conv_case(B, H, W, Cin, Cout, k, stride, pad, relu, res, seed):
@@ -42,7 +42,7 @@ CONV_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("prec", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("prec", ["tf32x3", "bf16", "tf32"])
 @pytest.mark.parametrize("shape", CONV_SHAPES)
 def test_conv2d_tensor_core(shape, prec, cplib):
     B, H, W, Cin, Cout, k, stride, pad, relu, res = shape
@@ -98,6 +98,19 @@ def test_network_tf32x3_is_fp32_equivalent(name, cplib):
         err = np.abs(out[h].cpu().numpy() - want).max() / np.abs(want).max()
         print("tf32x3 %s %s %.3e" % (name, h, err))
         assert err <= TOL_HEAD_REL, (h, err)
+
+
+def test_network_tf32_drift_is_bounded(cplib):
+    """TMA-fed single-pass tf32 plan (the math of PyTorch's default cuDNN convs): report drift, bound it at 5e-2."""
+    g = golden("net_dla34_b2_96x128")
+    m, opt = _net("dla_34", False, int(g["wseed"]), "tf32")
+    x, _ = net_case_inputs(g)
+    out = m(torch.from_numpy(x).cuda())[-1]
+    for h in opt.heads:
+        want = g["head_" + h]
+        err = np.abs(out[h].cpu().numpy() - want).max() / np.abs(want).max()
+        print("tf32 %s %.3e" % (h, err))
+        assert err <= 5e-2, (h, err)
 
 
 def test_network_bf16_drift_is_bounded(cplib):

@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4, help="frames of the in-run cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", default="", help="write the per-op table (cp_plan_profile) to this path")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "bf16"],
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "bf16", "tf32"],
                     help="fp32: CUDA-core parity mode; tf32x3: tcgen05 fp32-equivalent; bf16: tcgen05 fast mode")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -306,7 +306,8 @@ def main():
     peak = peaks["bf16_tflops_sustained"]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": None,
-                "kernel": ("igemm_fp32_kernel<64,NHWC> @ " if args.precision == "fp32" else "igemm_umma_kernel @ ") + dom["name"],
+                "kernel": {"fp32": "igemm_fp32_kernel<64,NHWC> @ ", "tf32": "conv_tma_kernel @ "}.get(
+                    args.precision, "igemm_umma_kernel @ ") + dom["name"],
                 "ms_per_launch": dom_ms,
                 "share_of_forward": dom_ms / tot_ms, "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)",
                 "algorithmic_flops_per_launch": dom["flops"],
@@ -338,13 +339,15 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "bf16": "bf16"}[args.precision], "data": "synthetic",
+            "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "bf16": "bf16", "tf32": "tf32"}[args.precision], "data": "synthetic",
             "config": {"workload": "batch=%d synthetic 512x512 frames per GPU, dla_34 + DCNv2, 7 heads, K=100, rep_mode 1, "
                                    "decode + soft-NMS + PnP" % B,
                        "global_batch": B * world,
                        "precision": {"fp32": "fp32 CUDA-core implicit GEMM (parity mode)",
                                      "tf32x3": "tcgen05 kind::tf32 3-term split (fp32-equivalent parity mode)",
-                                     "bf16": "tcgen05 kind::f16 bf16 operands, fp32 accumulate (fast mode)"}[args.precision],
+                                     "bf16": "tcgen05 kind::f16 bf16 operands, fp32 accumulate (fast mode)",
+                                     "tf32": "tcgen05 kind::tf32 single pass, TMA-fed shifted-window convs (cuDNN-default-equivalent "
+                                             "math); deformable / strided ops on the 3-term split kernel"}[args.precision],
                        "weights": "seeded random init; hm / hm_hp biases calibrated so ~%d peaks per frame pass the "
                                   "thresholds" % TARGET_OBJECTS,
                        "l2": "inputs rotate over %d distinct batches; per-step activations (~8 GB) exceed the 126 MB L2" % N_ROTATE,

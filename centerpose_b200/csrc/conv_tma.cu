@@ -126,8 +126,11 @@ __device__ __forceinline__ float tf32_round(float x) {
   return __uint_as_float(r);
 }
 
-// K-major SWIZZLE_128B descriptor; `saddr` may be any multiple of 16 bytes.  When the matrix does not start on a
-// 1024-byte swizzle-atom boundary the 3-bit base-offset field carries (addr >> 7) & 7.
+// K-major SWIZZLE_128B descriptor; `saddr` may be any multiple of 16 bytes.  Measured on B200
+// (scripts/tma_diag.py): the tensor core applies the 128-byte swizzle to the ABSOLUTE shared-memory address bits
+// [7,10), exactly like TMA does when it writes the slab, so a matrix that starts at an arbitrary 128-byte row of
+// the slab needs NO base-offset correction (setting the field to (addr >> 7) & 7 gives wrong results).
+// `use_base_offset` is kept only as a debug switch (CP_TMA_BASE_OFFSET=1).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int use_base_offset) {
   uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
   if (use_base_offset) d |= (uint64_t)((saddr >> 7) & 7u) << 49;

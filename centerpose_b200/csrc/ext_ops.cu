@@ -86,7 +86,7 @@ static int run_igemm(IgemmParams& p, int prec, int Kreal, cudaStream_t s) {
       if (!rc) {
         p.wgt_umma = tiles;
         const char* e = getenv("CP_TMA_BASE_OFFSET");
-        rc = launch_conv_tma(p, maps, 0, e ? atoi(e) : 1, s);
+        rc = launch_conv_tma(p, maps, 0, e ? atoi(e) : 0, s);
       }
       cudaFreeAsync(tiles, s);
       return rc;

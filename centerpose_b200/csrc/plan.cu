@@ -111,7 +111,7 @@ struct cp_plan {
   size_t decode_ws_bytes = 0;
   double* gn_stats = nullptr;
   int prec = -1;                 // -1 fp32 CUDA cores, 0 bf16 tcgen05, 1 tf32x3 tcgen05, 2 tf32 (TMA) + tf32x3 elsewhere
-  int tma_base_offset = 1;
+  int tma_base_offset = 0;       // measured on B200: UMMA swizzles on absolute smem address bits, the field must stay 0
   unsigned char* umma_wts = nullptr;
   size_t umma_bytes = 0;
 };

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import centerpose_b200 as cpb  # noqa: E402
 
 torch.manual_seed(0)
-for bo in ("1", "0"):
+for bo in ("0",):
     os.environ["CP_TMA_BASE_OFFSET"] = bo
     for (B, H, W, Cin, Cout, k) in ((1, 8, 16, 32, 32, 1), (1, 16, 16, 32, 64, 3), (2, 12, 30, 64, 32, 3),
                                     (1, 128, 128, 64, 256, 3), (1, 16, 16, 512, 128, 3)):
@@ -38,7 +38,7 @@ for bo in ("1", "0"):
             print("base_offset=%s B%d %dx%d Cin%d Cout%d k%d: FAILED %s" % (bo, B, H, W, Cin, Cout, k, str(e)[:200]))
             sys.exit(0)          # a trap kills the context; stop here
 # random-data accuracy (tf32 single pass): expect ~1e-3 of max
-os.environ["CP_TMA_BASE_OFFSET"] = os.environ.get("CP_TMA_BEST", "1")
+os.environ["CP_TMA_BASE_OFFSET"] = os.environ.get("CP_TMA_BEST", "0")
 for (B, H, W, Cin, Cout, k) in ((2, 32, 32, 64, 64, 3), (1, 64, 64, 128, 256, 1), (4, 128, 128, 64, 1792, 3)):
     x = torch.randn(B, H, W, Cin)
     w = torch.randn(Cout, Cin, k, k) / np.sqrt(Cin * k * k)

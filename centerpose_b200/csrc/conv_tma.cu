@@ -26,6 +26,7 @@ namespace {
 
 constexpr int TM_BM = 128;
 constexpr int TM_THREADS = 256;
+constexpr int TM_GROUP_X3 = 3;
 constexpr uint32_t TM_ROW = 128;      // bytes per position row: 32 fp32 channels
 
 struct TmaConvParams {
@@ -45,6 +46,8 @@ struct TmaConvParams {
   int outStride, out_nchw;
   int round_tf32;     // round the stored outputs to tf32 (consumers feed them to kind::tf32 untouched)
   int use_base_offset;
+  int x3;             // 3-term split (fp32-equivalent): hi/lo slabs + hi/lo weight tiles, BN <= 128
+  int group;          // x3: K blocks per TMEM accumulation group (promoted into fp32 registers after each group)
   const unsigned char* wtiles;
 };
 
@@ -120,6 +123,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ float tf32_round(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -141,18 +148,23 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
 }
 
 struct TmaCtl {
-  unsigned long long a_full[4], a_empty[4];
+  unsigned long long a_full[4], a_empty[4], a_split[4];
   unsigned long long b_full[8], b_empty[8];
   unsigned long long accum_full;
+  unsigned long long p_full[2], p_empty[2];
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmaConvParams p) {
+constexpr int TM_THREADS_X3 = 384;    // + warps 8-11: hi/lo splitters
+
+template <bool X3>
+__global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmaConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   TmaCtl* ctl = reinterpret_cast<TmaCtl*>(smem);
   const uint32_t slabs0 = (smem_u32(smem) + 1024u + 1023u) & ~1023u;
-  const uint32_t btile_bytes = (uint32_t)p.BN * TM_ROW;
-  const uint32_t btiles0 = slabs0 + (uint32_t)p.SA * p.slab_stride;
+  const uint32_t btile_bytes = (uint32_t)p.BN * TM_ROW * (X3 ? 2u : 1u);       // hi (+ lo) weight tile
+  const uint32_t a_stage = p.slab_stride * (X3 ? 2u : 1u);                    // hi (+ lo) slab
+  const uint32_t btiles0 = slabs0 + (uint32_t)p.SA * a_stage;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = p.CoutPad / p.BN;
@@ -178,6 +190,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     for (int s = 0; s < p.SA; ++s) {
       mbar_init(smem_u32(&ctl->a_full[s]), 1);
       mbar_init(smem_u32(&ctl->a_empty[s]), 1);
+      mbar_init(smem_u32(&ctl->a_split[s]), 128);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&ctl->p_full[s]), 1);
+      mbar_init(smem_u32(&ctl->p_empty[s]), 128);
     }
     for (int s = 0; s < p.SB; ++s) {
       mbar_init(smem_u32(&ctl->b_full[s]), 1);
@@ -187,7 +204,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
     fence_mbar_init();
   }
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.BN) tmem_cols <<= 1;
+  while ((int)tmem_cols < p.BN * (X3 ? 2 : 1)) tmem_cols <<= 1;
   if (warp == 2) {
     tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     tmem_relinquish();
@@ -211,7 +228,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
         mbar_wait(smem_u32(&ctl->a_empty[stage]), phase ^ 1u);
         const uint32_t bar = smem_u32(&ctl->a_full[stage]);
         mbar_arrive_expect_tx(bar, p.slab_bytes);
-        const uint32_t dst = slabs0 + (uint32_t)stage * p.slab_stride;
+        const uint32_t dst = slabs0 + (uint32_t)stage * a_stage;
         if (p.k == 3)
           tma_load_4d(dst, &p.amap[src], s * 32 - cb, -1, r_lo - 1, img, bar);
         else
@@ -247,11 +264,22 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
       const uint32_t idesc = make_idesc_tf32(p.BN);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
+      int kbi = 0;                       // running K-block index (slab-major, tap-minor)
+      int buf = 0;
+      uint32_t pe[2] = {0u, 0u};         // phases of p_empty
       for (int s = 0; s < nslab; ++s) {
-        mbar_wait(smem_u32(&ctl->a_full[sa]), pa);
+        mbar_wait(smem_u32(X3 ? &ctl->a_split[sa] : &ctl->a_full[sa]), pa);
         tc_fence_after();
-        const uint32_t slab = slabs0 + (uint32_t)sa * p.slab_stride;
-        for (int t = 0; t < taps; ++t) {
+        const uint32_t slab = slabs0 + (uint32_t)sa * a_stage;
+        for (int t = 0; t < taps; ++t, ++kbi) {
+          bool first = (kbi == 0);
+          if (X3) {
+            first = (kbi % p.group == 0);
+            if (first) {                 // new accumulation group: the epilogue must have drained this TMEM buffer
+              mbar_wait(smem_u32(&ctl->p_empty[buf]), pe[buf] ^ 1u);
+              tc_fence_after();
+            }
+          }
           mbar_wait(smem_u32(&ctl->b_full[sb]), pb);
           tc_fence_after();
           uint32_t a_addr = slab;
@@ -260,16 +288,30 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
             a_addr += (uint32_t)(g0 + ky * p.Wt + kx - 1 - r_lo * p.Wt) * TM_ROW;
           }
           const uint32_t b_addr = btiles0 + (uint32_t)sb * btile_bytes;
+          const uint32_t d_tmem = tmem_base + (X3 ? (uint32_t)(buf * p.BN) : 0u);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t da = make_desc(a_addr + ks * 32, p.use_base_offset);
             const uint64_t db = make_desc(b_addr + ks * 32, 0);
-            umma_tf32(tmem_base, da, db, idesc, (s > 0 || t > 0 || ks > 0) ? 1u : 0u);
+            if (X3) {
+              const uint64_t da_lo = make_desc(a_addr + p.slab_stride + ks * 32, p.use_base_offset);
+              const uint64_t db_lo = make_desc(b_addr + (uint32_t)p.BN * TM_ROW + ks * 32, 0);
+              umma_tf32(d_tmem, da_lo, db, idesc, (first && ks == 0) ? 0u : 1u);
+              umma_tf32(d_tmem, da, db_lo, idesc, 1u);
+              umma_tf32(d_tmem, da, db, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, da, db, idesc, (first && ks == 0) ? 0u : 1u);
+            }
           }
           umma_commit(smem_u32(&ctl->b_empty[sb]));
           if (++sb == p.SB) {
             sb = 0;
             pb ^= 1u;
+          }
+          if (X3 && ((kbi % p.group == p.group - 1) || kbi == KB - 1)) {
+            umma_commit(smem_u32(&ctl->p_full[buf]));     // group finished -> epilogue promotes it
+            pe[buf] ^= 1u;
+            buf ^= 1;
           }
         }
         umma_commit(smem_u32(&ctl->a_empty[sa]));
@@ -278,10 +320,38 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
           pa ^= 1u;
         }
       }
-      umma_commit(smem_u32(&ctl->accum_full));
+      if (!X3) umma_commit(smem_u32(&ctl->accum_full));
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  } else if (X3 && warp >= 8) {
+    // ===================== hi / lo splitters (x3): slab -> tf32-exact hi (in place) + lo slab =====================
+    const int st = tid - 256;
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t nchunk = p.slab_bytes >> 4;
+    for (int s = 0; s < nslab; ++s) {
+      mbar_wait(smem_u32(&ctl->a_full[stage]), phase);
+      const uint32_t hi = slabs0 + (uint32_t)stage * a_stage;
+      const uint32_t lo = hi + p.slab_stride;
+      for (uint32_t c = st; c < nchunk; c += 128) {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi + (c << 4)));
+        float4 h, l;
+        h.x = tf32_round(v.x); l.x = tf32_round(v.x - h.x);
+        h.y = tf32_round(v.y); l.y = tf32_round(v.y - h.y);
+        h.z = tf32_round(v.z); l.z = tf32_round(v.z - h.z);
+        h.w = tf32_round(v.w); l.w = tf32_round(v.w - h.w);
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi + (c << 4)), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo + (c << 4)), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&ctl->a_split[stage]));
+      if (++stage == p.SA) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
     // ===================== epilogue: TMEM lane == flattened output position =====================
     const int q = warp & 3;
     const int i = q * 32 + lane;
@@ -304,13 +374,50 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
       n = (int)(t / p.H);
     }
     const size_t m = ((size_t)n * p.H + oy) * p.W + ox;
-    mbar_wait(smem_u32(&ctl->accum_full), 0u);
-    tc_fence_after();
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+    float sums[X3 ? 128 : 1];
+    if (X3) {
+      // two-level accumulation: the tensor core only ever sums `group` K blocks in TMEM (its accumulator truncates,
+      // error ~ chain length); every finished group is added into fp32 registers with round-to-nearest
+#pragma unroll
+      for (int j = 0; j < (X3 ? 128 : 1); ++j) sums[j] = 0.f;
+      const int ngroups = (KB + p.group - 1) / p.group;
+      int buf = 0;
+      uint32_t pf[2] = {0u, 0u};
+      for (int g = 0; g < ngroups; ++g) {
+        mbar_wait(smem_u32(&ctl->p_full[buf]), pf[buf]);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (c * 16 < p.BN) {
+            uint32_t rr[16];
+            tmem_ld16(lane_base + (uint32_t)(buf * p.BN + c * 16), rr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sums[(X3 ? c * 16 + j : 0)] += __uint_as_float(rr[j]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&ctl->p_empty[buf]));
+        pf[buf] ^= 1u;
+        buf ^= 1;
+      }
+    } else {
+      mbar_wait(smem_u32(&ctl->accum_full), 0u);
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int cc = 0; cc < (X3 ? 8 : 16); ++cc) {
+      const int c0 = cc * 16;
+      if (c0 >= p.BN) break;
       uint32_t rr[16];
-      tmem_ld16(lane_base + (uint32_t)c0, rr);
-      tmem_ld_wait();
+      if (X3) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(sums[(X3 ? cc * 16 + j : 0)]);
+      } else {
+        tmem_ld16(lane_base + (uint32_t)c0, rr);
+        tmem_ld_wait();
+      }
       const int nb = n_tile * p.BN + c0;
       if (valid && nb < p.Cout) {
         float vv[16];
@@ -360,7 +467,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) conv_tma_kernel(const __grid_co
 
 // weight tiles for the slab-major K order:  kb = slab * taps + tap,  element j of the row = channel slab*32 + j
 __global__ void pack_tma_weight_kernel(const float* __restrict__ src, int ld, int Cin, int taps, int Cout, int BN, int n_tiles,
-                                       int round_tf32, unsigned char* __restrict__ dst) {
+                                       int round_tf32, int x3, unsigned char* __restrict__ dst) {
   const int KB = (Cin / 32) * taps;
   const size_t total = (size_t)n_tiles * KB * BN * 8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -379,9 +486,19 @@ __global__ void pack_tma_weight_kernel(const float* __restrict__ src, int ld, in
       float x = (n < Cout) ? src[(size_t)k * ld + n] : 0.f;
       v[j] = round_tf32 ? tf32_round(x) : x;
     }
-    const size_t tile = ((size_t)nt * KB + kb) * (size_t)BN * TM_ROW;
+    const size_t tile = ((size_t)nt * KB + kb) * (size_t)BN * TM_ROW * (x3 ? 2 : 1);
     const size_t off = (size_t)(nr >> 3) * 1024 + (size_t)(nr & 7) * 128 + (size_t)((q ^ (nr & 7)) << 4);
     *reinterpret_cast<float4*>(dst + tile + off) = make_float4(v[0], v[1], v[2], v[3]);
+    if (x3) {     // lo tile = residual of the tf32 rounding (round_tf32 is always set together with x3)
+      float l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = tap * Cin + slab * 32 + q * 4 + j;
+        const float x = (n < Cout) ? src[(size_t)k * ld + n] : 0.f;
+        l[j] = tf32_round(x - v[j]);
+      }
+      *reinterpret_cast<float4*>(dst + tile + (size_t)BN * TM_ROW + off) = make_float4(l[0], l[1], l[2], l[3]);
+    }
   }
 }
 
@@ -404,9 +521,12 @@ EncodeTiledFn get_encode() {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------- host side
-int tma_tile_n(int CoutPad) { return CoutPad <= 256 ? CoutPad : 256; }
+int tma_tile_n(int CoutPad, int x3) {
+  const int cap = x3 ? 128 : 256;     // x3 keeps the promoted sums of one row in 128 registers
+  return CoutPad <= cap ? CoutPad : cap;
+}
 
-bool tma_conv_supported(const IgemmParams& p) {
+bool tma_conv_supported(const IgemmParams& p, int x3) {
   if (p.mode != IGEMM_NHWC_VEC) return false;
   if (!((p.kh == 1 && p.kw == 1 && p.pad == 0) || (p.kh == 3 && p.kw == 3 && p.pad == 1))) return false;
   if (p.stride != 1) return false;
@@ -414,23 +534,24 @@ bool tma_conv_supported(const IgemmParams& p) {
   for (int s = 0; s < p.nsrc; ++s)
     if (p.srcC[s] % 32 || p.srcStride[s] % 4) return false;
   if (p.kh == 3 && p.Win + 2 > 256) return false;
-  const int bn = tma_tile_n(p.CoutPad);
+  const int bn = tma_tile_n(p.CoutPad, x3);
   if (bn % 16 || p.CoutPad % bn) return false;
   return get_encode() != nullptr;
 }
 
-size_t tma_weight_bytes(int Cin, int taps, int CoutPad) {
-  return (size_t)CoutPad * (Cin / 32) * taps * TM_ROW;
+size_t tma_weight_bytes(int Cin, int taps, int CoutPad, int x3) {
+  return (size_t)CoutPad * (Cin / 32) * taps * TM_ROW * (x3 ? 2 : 1);
 }
 
-int launch_pack_tma_weight(const float* src, int ld, int Cin, int taps, int Cout, int CoutPad, int round_tf32, void* dst,
-                           cudaStream_t s) {
-  const int bn = tma_tile_n(CoutPad);
+int launch_pack_tma_weight(const float* src, int ld, int Cin, int taps, int Cout, int CoutPad, int round_tf32, int x3,
+                           void* dst, cudaStream_t s) {
+  const int bn = tma_tile_n(CoutPad, x3);
+  if (x3) round_tf32 = 1;
   const int nt = CoutPad / bn;
   size_t total = (size_t)nt * (Cin / 32) * taps * bn * 8;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
-  pack_tma_weight_kernel<<<blocks, 256, 0, s>>>(src, ld, Cin, taps, Cout, bn, nt, round_tf32, (unsigned char*)dst);
+  pack_tma_weight_kernel<<<blocks, 256, 0, s>>>(src, ld, Cin, taps, Cout, bn, nt, round_tf32, x3, (unsigned char*)dst);
   CP_LAUNCH_CHECK("pack_tma_weight_kernel");
   return CP_OK;
 }
@@ -467,7 +588,8 @@ int tma_conv_encode(const IgemmParams& p, int Bmax, void* maps_out) {
   return CP_OK;
 }
 
-int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, int use_base_offset, cudaStream_t stream) {
+int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, int use_base_offset, int x3,
+                    cudaStream_t stream) {
   if (!p.wgt_umma) return fail(CP_ERR_INVALID, "conv_tma: weight tiles missing");
   TmaConvParams q;
   memset(&q, 0, sizeof(q));
@@ -480,7 +602,9 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.Cin = p.Cin;
   q.Cout = p.Cout;
   q.CoutPad = p.CoutPad;
-  q.BN = tma_tile_n(p.CoutPad);
+  q.BN = tma_tile_n(p.CoutPad, x3);
+  q.x3 = x3;
+  q.group = TM_GROUP_X3;
   q.k = p.kh;
   q.Wt = p.Win + 2;
   q.boxh = (129 + 2 * q.Wt + q.Wt - 1) / q.Wt + 1;
@@ -495,17 +619,19 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
     q.slab_bytes = TM_BM * TM_ROW;
   }
   q.slab_stride = (q.slab_bytes + 1023u) & ~1023u;
-  const uint32_t btile = (uint32_t)q.BN * TM_ROW;
+  const uint32_t btile = (uint32_t)q.BN * TM_ROW * (x3 ? 2u : 1u);
+  const uint32_t a_stage = q.slab_stride * (x3 ? 2u : 1u);
   const size_t budget = 220 * 1024;
   q.SA = 2;
-  if ((size_t)q.SA * q.slab_stride + 2 * btile > budget) q.SA = 1;
-  size_t left = budget - (size_t)q.SA * q.slab_stride;
+  if ((size_t)q.SA * a_stage + 2 * btile > budget) q.SA = 1;
+  if ((size_t)q.SA * a_stage + 2 * btile > budget) return fail(CP_ERR_INVALID, "conv_tma: slab does not fit shared memory");
+  size_t left = budget - (size_t)q.SA * a_stage;
   q.SB = (int)(left / btile);
   if (q.SB > 8) q.SB = 8;
   if (q.SB < 2) return fail(CP_ERR_INVALID, "conv_tma: tile does not fit shared memory");
   if (q.k == 1 && q.SA < 4) {
     // 1x1: slabs are small (16 KB); use up to 4 stages of them
-    int sa = (int)((budget - (size_t)q.SB * btile) / q.slab_stride);
+    int sa = (int)((budget - (size_t)q.SB * btile) / a_stage);
     if (sa > 4) sa = 4;
     if (sa > q.SA) q.SA = sa;
   }
@@ -520,14 +646,20 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.round_tf32 = round_out_tf32;
   q.use_base_offset = use_base_offset;
   q.wtiles = (const unsigned char*)p.wgt_umma;
-  const size_t smem = 2048 + (size_t)q.SA * q.slab_stride + (size_t)q.SB * btile;
-  static thread_local bool configured = false;
-  if (!configured) {
-    CP_CUDA_CHECK(cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+  const size_t smem = 2048 + (size_t)q.SA * a_stage + (size_t)q.SB * btile;
+  static thread_local bool configured[2] = {false, false};
+  if (!configured[x3 ? 1 : 0]) {
+    if (x3)
+      CP_CUDA_CHECK(cudaFuncSetAttribute(conv_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    else
+      CP_CUDA_CHECK(cudaFuncSetAttribute(conv_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[x3 ? 1 : 0] = true;
   }
   dim3 grid((unsigned)(m_tiles * (size_t)(p.CoutPad / q.BN)));
-  conv_tma_kernel<<<grid, TM_THREADS, smem, stream>>>(q);
+  if (x3)
+    conv_tma_kernel<true><<<grid, TM_THREADS_X3, smem, stream>>>(q);
+  else
+    conv_tma_kernel<false><<<grid, TM_THREADS, smem, stream>>>(q);
   CP_LAUNCH_CHECK("conv_tma_kernel");
   return CP_OK;
 }

@@ -73,20 +73,22 @@ static int prec_code(int32_t precision, int* prec) {
 // run one implicit-GEMM launch with the kernel family selected by `prec` (weights already packed as fp32 [K][CoutPad])
 static int run_igemm(IgemmParams& p, int prec, int Kreal, cudaStream_t s) {
   if (prec < 0) return launch_igemm_fp32(p, s);
-  if (prec == 2) {
-    if (!tma_conv_supported(p)) {
+  if (prec == 2 || prec == 1) {
+    const int x3 = prec == 1;
+    const char* force_gather = getenv("CP_FORCE_GATHER");
+    if (!tma_conv_supported(p, x3) || (force_gather && atoi(force_gather))) {
       prec = 1;     // deformable / strided ops: 3-term split gather kernel
     } else {
       void* tiles = nullptr;
       const int taps = p.kh * p.kw;
-      CP_CUDA_CHECK(cudaMallocAsync(&tiles, tma_weight_bytes(p.Cin, taps, p.CoutPad), s));
+      CP_CUDA_CHECK(cudaMallocAsync(&tiles, tma_weight_bytes(p.Cin, taps, p.CoutPad, x3), s));
       alignas(64) unsigned char maps[512];
       int rc = tma_conv_encode(p, p.B, maps);
-      if (!rc) rc = launch_pack_tma_weight(p.wgt, p.CoutPad, p.Cin, taps, p.Cout, p.CoutPad, 1, tiles, s);
+      if (!rc) rc = launch_pack_tma_weight(p.wgt, p.CoutPad, p.Cin, taps, p.Cout, p.CoutPad, 1, x3, tiles, s);
       if (!rc) {
         p.wgt_umma = tiles;
         const char* e = getenv("CP_TMA_BASE_OFFSET");
-        rc = launch_conv_tma(p, maps, 0, e ? atoi(e) : 0, s);
+        rc = launch_conv_tma(p, maps, 0, e ? atoi(e) : 0, x3, s);
       }
       cudaFreeAsync(tiles, s);
       return rc;

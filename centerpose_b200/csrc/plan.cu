@@ -557,10 +557,10 @@ int build_graph(cp_plan* P) {
       q.Win = op.src[0].W;
       const int gather_prec = P->prec == 2 ? 1 : P->prec;
       if (op.src[0].ext >= 0) continue;
-      if (P->prec == 2 && tma_conv_supported(q)) {
+      if ((P->prec == 2 || P->prec == 1) && tma_conv_supported(q, P->prec == 1)) {
         op.use_tma = true;
         op.umma_off = P->umma_bytes;
-        P->umma_bytes += (tma_weight_bytes(op.Cin, op.kh * op.kw, op.CoutPad) + 1023) / 1024 * 1024;
+        P->umma_bytes += (tma_weight_bytes(op.Cin, op.kh * op.kw, op.CoutPad, P->prec == 1) + 1023) / 1024 * 1024;
       } else if (umma_supported(q, gather_prec)) {
         op.use_umma = true;
         op.umma_off = P->umma_bytes;
@@ -719,7 +719,7 @@ int cp_plan_load_weights(cp_plan* P, const char* const* names, const void* const
     if (op.type != OP_IGEMM) continue;
     if (op.use_tma) {
       if ((rc = launch_pack_tma_weight(P->wts + op.w_off, op.w_ld, op.Cin, op.kh * op.kw, op.Cout, op.CoutPad, 1,
-                                       P->umma_wts + op.umma_off, s)))
+                                       P->prec == 1, P->umma_wts + op.umma_off, s)))
         return rc;
     } else if (op.use_umma) {
       if ((rc = launch_pack_umma_weight(P->wts + op.w_off, op.w_ld, op.kh * op.kw * op.Cin, op.Cout, op.CoutPad,
@@ -796,7 +796,7 @@ static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* 
         if (op.use_tma) {
           p.wgt_umma = P->umma_wts + op.umma_off;
           const unsigned char* mp = (const unsigned char*)(((uintptr_t)op.tma_maps.data() + 63) & ~(uintptr_t)63);
-          if ((rc = launch_conv_tma(p, mp, 1, P->tma_base_offset, s))) return rc;
+          if ((rc = launch_conv_tma(p, mp, P->prec == 2, P->tma_base_offset, P->prec == 1, s))) return rc;
         } else if (op.use_umma) {
           p.wgt_umma = P->umma_wts + op.umma_off;
           if ((rc = launch_igemm_umma(p, P->prec == 2 ? 1 : P->prec, s))) return rc;

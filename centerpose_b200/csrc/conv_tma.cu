@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "umma_common.cuh"
 
 namespace cp {
 namespace {
@@ -46,45 +47,14 @@ struct TmaConvParams {
   int outStride, out_nchw;
   int round_tf32;     // round the stored outputs to tf32 (consumers feed them to kind::tf32 untouched)
   int use_base_offset;
+  int cslab;          // channels per slab: 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B; Cin = 16 layers)
   int x3;             // 3-term split (fp32-equivalent): hi/lo slabs + hi/lo weight tiles, BN <= 128
   int group;          // x3: K blocks per TMEM accumulation group (promoted into fp32 registers after each group)
   const unsigned char* wtiles;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("conv_tma: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
+using namespace umma;
+
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
@@ -96,50 +66,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                "l"(map), "r"(c0), "r"(c1), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ float tf32_round(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
 // K-major SWIZZLE_128B descriptor; `saddr` may be any multiple of 16 bytes.  Measured on B200
 // (scripts/tma_diag.py): the tensor core applies the 128-byte swizzle to the ABSOLUTE shared-memory address bits
 // [7,10), exactly like TMA does when it writes the slab, so a matrix that starts at an arbitrary 128-byte row of
 // the slab needs NO base-offset correction (setting the field to (addr >> 7) & 7 gives wrong results).
 // `use_base_offset` is kept only as a debug switch (CP_TMA_BASE_OFFSET=1).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int use_base_offset) {
-  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+// cslab = 32: 128-byte rows, SWIZZLE_128B (layout type 2), 8-row groups 1024 bytes apart;
+// cslab = 16:  64-byte rows, SWIZZLE_64B  (layout type 4), 8-row groups  512 bytes apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int use_base_offset, int cslab) {
+  const uint64_t sbo = cslab == 32 ? (1024 >> 4) : (512 >> 4);
+  const uint64_t lay = cslab == 32 ? 2ull : 4ull;
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (lay << 61);
   if (use_base_offset) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
   return d;
 }
@@ -161,8 +104,10 @@ template <bool X3>
 __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmaConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   TmaCtl* ctl = reinterpret_cast<TmaCtl*>(smem);
-  const uint32_t slabs0 = (smem_u32(smem) + 1024u + 1023u) & ~1023u;
-  const uint32_t btile_bytes = (uint32_t)p.BN * TM_ROW * (X3 ? 2u : 1u);       // hi (+ lo) weight tile
+  const uint32_t slabs0 = (smem_u32(smem) + 512u + 4u * kStageFloatsPerWarp * 4u + 1023u) & ~1023u;
+  const uint32_t rowb = (uint32_t)p.cslab * 4u;                               // bytes per position row
+  const int kslices = p.cslab / 8;                                            // tf32 MMA K = 8
+  const uint32_t btile_bytes = (uint32_t)p.BN * rowb * (X3 ? 2u : 1u);         // hi (+ lo) weight tile
   const uint32_t a_stage = p.slab_stride * (X3 ? 2u : 1u);                    // hi (+ lo) slab
   const uint32_t btiles0 = slabs0 + (uint32_t)p.SA * a_stage;
 
@@ -171,7 +116,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   const int n_tile = blockIdx.x % n_tiles;
   const int m_tile = blockIdx.x / n_tiles;
   const int taps = p.k * p.k;
-  const int nslab = p.Cin / 32;
+  const int nslab = p.Cin / p.cslab;
   const int KB = nslab * taps;
 
   // tile geometry
@@ -221,7 +166,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
       uint32_t phase = 0;
       for (int s = 0; s < nslab; ++s) {
         int src = 0, cb = 0;
-        while (src + 1 < p.nsrc && s * 32 >= cb + p.srcC[src]) {
+        while (src + 1 < p.nsrc && s * p.cslab >= cb + p.srcC[src]) {
           cb += p.srcC[src];
           ++src;
         }
@@ -230,9 +175,9 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
         mbar_arrive_expect_tx(bar, p.slab_bytes);
         const uint32_t dst = slabs0 + (uint32_t)stage * a_stage;
         if (p.k == 3)
-          tma_load_4d(dst, &p.amap[src], s * 32 - cb, -1, r_lo - 1, img, bar);
+          tma_load_4d(dst, &p.amap[src], s * p.cslab - cb, -1, r_lo - 1, img, bar);
         else
-          tma_load_2d(dst, &p.amap[src], s * 32 - cb, (int)pos0, bar);
+          tma_load_2d(dst, &p.amap[src], s * p.cslab - cb, (int)pos0, bar);
         if (++stage == p.SA) {
           stage = 0;
           phase ^= 1u;
@@ -285,17 +230,16 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
           uint32_t a_addr = slab;
           if (p.k == 3) {
             const int ky = t / 3, kx = t - ky * 3;
-            a_addr += (uint32_t)(g0 + ky * p.Wt + kx - 1 - r_lo * p.Wt) * TM_ROW;
+            a_addr += (uint32_t)(g0 + ky * p.Wt + kx - 1 - r_lo * p.Wt) * rowb;
           }
           const uint32_t b_addr = btiles0 + (uint32_t)sb * btile_bytes;
           const uint32_t d_tmem = tmem_base + (X3 ? (uint32_t)(buf * p.BN) : 0u);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t da = make_desc(a_addr + ks * 32, p.use_base_offset);
-            const uint64_t db = make_desc(b_addr + ks * 32, 0);
+          for (int ks = 0; ks < kslices; ++ks) {
+            const uint64_t da = make_desc(a_addr + ks * 32, p.use_base_offset, p.cslab);
+            const uint64_t db = make_desc(b_addr + ks * 32, 0, p.cslab);
             if (X3) {
-              const uint64_t da_lo = make_desc(a_addr + p.slab_stride + ks * 32, p.use_base_offset);
-              const uint64_t db_lo = make_desc(b_addr + (uint32_t)p.BN * TM_ROW + ks * 32, 0);
+              const uint64_t da_lo = make_desc(a_addr + p.slab_stride + ks * 32, p.use_base_offset, p.cslab);
+              const uint64_t db_lo = make_desc(b_addr + (uint32_t)p.BN * rowb + ks * 32, 0, p.cslab);
               umma_tf32(d_tmem, da_lo, db, idesc, (first && ks == 0) ? 0u : 1u);
               umma_tf32(d_tmem, da, db_lo, idesc, 1u);
               umma_tf32(d_tmem, da, db, idesc, 1u);
@@ -373,8 +317,24 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
       oy = (int)(t % p.H);
       n = (int)(t / p.H);
     }
-    const size_t m = ((size_t)n * p.H + oy) * p.W + ox;
+    const int m = (int)(((size_t)n * p.H + oy) * p.W + ox);
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* stage = reinterpret_cast<float*>(smem + 512) + q * kStageFloatsPerWarp;    // per-warp transpose area
+    EpiParams ep;
+    ep.bias = p.bias;
+    ep.residual = p.residual;
+    ep.resStride = p.resStride;
+    ep.relu = p.relu;
+    ep.res_after_relu = p.res_after_relu;
+    ep.round_tf32 = p.round_tf32;
+    ep.out = p.out;
+    ep.outStride = p.outStride;
+    ep.out_nchw = p.out_nchw;
+    ep.Cout = p.Cout;
+    ep.CoutPad = p.CoutPad;
+    ep.H = p.H;
+    ep.W = p.W;
+    const int col_end = min(p.Cout, (n_tile + 1) * p.BN);
     float sums[X3 ? 128 : 1];
     if (X3) {
       // two-level accumulation: the tensor core only ever sums `group` K blocks in TMEM (its accumulator truncates,
@@ -407,56 +367,27 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
       tc_fence_after();
     }
 #pragma unroll
-    for (int cc = 0; cc < (X3 ? 8 : 16); ++cc) {
-      const int c0 = cc * 16;
+    for (int cc = 0; cc < (X3 ? 4 : 8); ++cc) {
+      const int c0 = cc * 32;
       if (c0 >= p.BN) break;
-      uint32_t rr[16];
+      float vv[32];
       if (X3) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(sums[(X3 ? cc * 16 + j : 0)]);
+        for (int j = 0; j < 32; ++j) vv[j] = sums[(X3 ? cc * 32 + j : 0)];
       } else {
+        uint32_t rr[32];
         tmem_ld16(lane_base + (uint32_t)c0, rr);
-        tmem_ld_wait();
-      }
-      const int nb = n_tile * p.BN + c0;
-      if (valid && nb < p.Cout) {
-        float vv[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) vv[j] = __uint_as_float(rr[j]) + __ldg(p.bias + nb + j);
-        if (p.residual && !p.res_after_relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < p.Cout) vv[j] += __ldg(p.residual + m * p.resStride + nb + j);
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) vv[j] = fmaxf(vv[j], 0.f);
-        }
-        if (p.residual && p.res_after_relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < p.Cout) vv[j] += __ldg(p.residual + m * p.resStride + nb + j);
-        }
-        if (p.round_tf32) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) vv[j] = tf32_round(vv[j]);
-        }
-        if (p.out_nchw) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < p.Cout) p.out[(((size_t)n * p.Cout + nb + j) * p.H + oy) * p.W + ox] = vv[j];
+        if (c0 + 16 < p.BN) {
+          tmem_ld16(lane_base + (uint32_t)(c0 + 16), rr + 16);
         } else {
-          float* o = p.out + m * p.outStride + nb;
-          if (nb + 15 < p.Cout) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(vv[j], vv[j + 1], vv[j + 2], vv[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (nb + j < p.Cout) o[j] = vv[j];
-          }
+          for (int j = 16; j < 32; ++j) rr[j] = 0u;
         }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(rr[j]);
       }
+      epilogue_sub_tile(ep, stage, vv, lane, valid, m, n, oy, ox, n_tile * p.BN + c0, col_end);
     }
   }
 
@@ -467,12 +398,14 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
 
 // weight tiles for the slab-major K order:  kb = slab * taps + tap,  element j of the row = channel slab*32 + j
 __global__ void pack_tma_weight_kernel(const float* __restrict__ src, int ld, int Cin, int taps, int Cout, int BN, int n_tiles,
-                                       int round_tf32, int x3, unsigned char* __restrict__ dst) {
-  const int KB = (Cin / 32) * taps;
-  const size_t total = (size_t)n_tiles * KB * BN * 8;
+                                       int round_tf32, int x3, int cslab, unsigned char* __restrict__ dst) {
+  const int KB = (Cin / cslab) * taps;
+  const int cpr = cslab / 4;                 // 16-byte chunks per row: 8 or 4
+  const size_t rowb = (size_t)cslab * 4;
+  const size_t total = (size_t)n_tiles * KB * BN * cpr;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int q = i & 7;
-    size_t t = i >> 3;
+    const int q = i % cpr;
+    size_t t = i / cpr;
     const int nr = t % BN;
     t /= BN;
     const int kb = t % KB;
@@ -482,22 +415,24 @@ __global__ void pack_tma_weight_kernel(const float* __restrict__ src, int ld, in
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int k = tap * Cin + slab * 32 + q * 4 + j;
+      const int k = tap * Cin + slab * cslab + q * 4 + j;
       float x = (n < Cout) ? src[(size_t)k * ld + n] : 0.f;
       v[j] = round_tf32 ? tf32_round(x) : x;
     }
-    const size_t tile = ((size_t)nt * KB + kb) * (size_t)BN * TM_ROW * (x3 ? 2 : 1);
-    const size_t off = (size_t)(nr >> 3) * 1024 + (size_t)(nr & 7) * 128 + (size_t)((q ^ (nr & 7)) << 4);
+    const size_t tile = ((size_t)nt * KB + kb) * (size_t)BN * rowb * (x3 ? 2 : 1);
+    // SWIZZLE_128B: chunk ^= row & 7 (address bits [7,10));  SWIZZLE_64B: chunk ^= (row >> 1) & 3 (bits [7,9))
+    const int sw = cslab == 32 ? (nr & 7) : ((nr >> 1) & 3);
+    const size_t off = (size_t)nr * rowb + (size_t)((q ^ sw) << 4);
     *reinterpret_cast<float4*>(dst + tile + off) = make_float4(v[0], v[1], v[2], v[3]);
     if (x3) {     // lo tile = residual of the tf32 rounding (round_tf32 is always set together with x3)
       float l[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int k = tap * Cin + slab * 32 + q * 4 + j;
+        const int k = tap * Cin + slab * cslab + q * 4 + j;
         const float x = (n < Cout) ? src[(size_t)k * ld + n] : 0.f;
         l[j] = tf32_round(x - v[j]);
       }
-      *reinterpret_cast<float4*>(dst + tile + (size_t)BN * TM_ROW + off) = make_float4(l[0], l[1], l[2], l[3]);
+      *reinterpret_cast<float4*>(dst + tile + (size_t)BN * rowb + off) = make_float4(l[0], l[1], l[2], l[3]);
     }
   }
 }
@@ -521,6 +456,8 @@ EncodeTiledFn get_encode() {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------- host side
+int tma_cslab(int Cin) { return (Cin % 32 == 0) ? 32 : 16; }
+
 int tma_tile_n(int CoutPad, int x3) {
   const int cap = x3 ? 128 : 256;     // x3 keeps the promoted sums of one row in 128 registers
   return CoutPad <= cap ? CoutPad : cap;
@@ -530,9 +467,10 @@ bool tma_conv_supported(const IgemmParams& p, int x3) {
   if (p.mode != IGEMM_NHWC_VEC) return false;
   if (!((p.kh == 1 && p.kw == 1 && p.pad == 0) || (p.kh == 3 && p.kw == 3 && p.pad == 1))) return false;
   if (p.stride != 1) return false;
-  if (p.Cin % 32) return false;
+  const int cs = tma_cslab(p.Cin);
+  if (p.Cin % cs) return false;
   for (int s = 0; s < p.nsrc; ++s)
-    if (p.srcC[s] % 32 || p.srcStride[s] % 4) return false;
+    if (p.srcC[s] % cs || p.srcStride[s] % 4) return false;
   if (p.kh == 3 && p.Win + 2 > 256) return false;
   const int bn = tma_tile_n(p.CoutPad, x3);
   if (bn % 16 || p.CoutPad % bn) return false;
@@ -540,7 +478,7 @@ bool tma_conv_supported(const IgemmParams& p, int x3) {
 }
 
 size_t tma_weight_bytes(int Cin, int taps, int CoutPad, int x3) {
-  return (size_t)CoutPad * (Cin / 32) * taps * TM_ROW * (x3 ? 2 : 1);
+  return (size_t)CoutPad * Cin * taps * 4 * (x3 ? 2 : 1);
 }
 
 int launch_pack_tma_weight(const float* src, int ld, int Cin, int taps, int Cout, int CoutPad, int round_tf32, int x3,
@@ -548,10 +486,11 @@ int launch_pack_tma_weight(const float* src, int ld, int Cin, int taps, int Cout
   const int bn = tma_tile_n(CoutPad, x3);
   if (x3) round_tf32 = 1;
   const int nt = CoutPad / bn;
-  size_t total = (size_t)nt * (Cin / 32) * taps * bn * 8;
+  const int cs = tma_cslab(Cin);
+  size_t total = (size_t)nt * (Cin / cs) * taps * bn * (cs / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
-  pack_tma_weight_kernel<<<blocks, 256, 0, s>>>(src, ld, Cin, taps, Cout, bn, nt, round_tf32, x3, (unsigned char*)dst);
+  pack_tma_weight_kernel<<<blocks, 256, 0, s>>>(src, ld, Cin, taps, Cout, bn, nt, round_tf32, x3, cs, (unsigned char*)dst);
   CP_LAUNCH_CHECK("pack_tma_weight_kernel");
   return CP_OK;
 }
@@ -563,24 +502,26 @@ int tma_conv_encode(const IgemmParams& p, int Bmax, void* maps_out) {
   CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(maps_out);
   const int Wt = p.Win + 2;
   const int boxh = (129 + 2 * Wt + Wt - 1) / Wt + 1;
+  const int cs = tma_cslab(p.Cin);
+  const CUtensorMapSwizzle swz = cs == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   for (int s = 0; s < p.nsrc; ++s) {
     CUresult r;
     if (p.kh == 3) {
       cuuint64_t dims[4] = {(cuuint64_t)p.srcC[s], (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)Bmax};
       cuuint64_t strides[3] = {(cuuint64_t)p.srcStride[s] * 4, (cuuint64_t)p.Win * p.srcStride[s] * 4,
                                (cuuint64_t)p.Hin * p.Win * p.srcStride[s] * 4};
-      cuuint32_t box[4] = {32, (cuuint32_t)Wt, (cuuint32_t)boxh, 1};
+      cuuint32_t box[4] = {(cuuint32_t)cs, (cuuint32_t)Wt, (cuuint32_t)boxh, 1};
       cuuint32_t es[4] = {1, 1, 1, 1};
       r = enc(&maps[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p.src[s], dims, strides, box, es,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
       cuuint64_t dims[2] = {(cuuint64_t)p.srcC[s], (cuuint64_t)Bmax * p.Hin * p.Win};
       cuuint64_t strides[1] = {(cuuint64_t)p.srcStride[s] * 4};
-      cuuint32_t box[2] = {32, TM_BM};
+      cuuint32_t box[2] = {(cuuint32_t)cs, TM_BM};
       cuuint32_t es[2] = {1, 1};
       r = enc(&maps[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p.src[s], dims, strides, box, es,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) return fail(CP_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
@@ -604,7 +545,8 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.CoutPad = p.CoutPad;
   q.BN = tma_tile_n(p.CoutPad, x3);
   q.x3 = x3;
-  q.group = TM_GROUP_X3;
+  q.cslab = tma_cslab(p.Cin);
+  q.group = TM_GROUP_X3 * (32 / q.cslab);       // same number of MMAs per TMEM accumulation group
   q.k = p.kh;
   q.Wt = p.Win + 2;
   q.boxh = (129 + 2 * q.Wt + q.Wt - 1) / q.Wt + 1;
@@ -612,16 +554,16 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   if (q.k == 3) {
     q.tiles_per_image = (p.Hin * q.Wt + TM_BM - 1) / TM_BM;
     m_tiles = (size_t)q.tiles_per_image * p.B;
-    q.slab_bytes = (uint32_t)q.boxh * q.Wt * TM_ROW;
+    q.slab_bytes = (uint32_t)q.boxh * q.Wt * (uint32_t)q.cslab * 4u;
   } else {
     q.tiles_per_image = 0;
     m_tiles = ((size_t)p.B * p.Hin * p.Win + TM_BM - 1) / TM_BM;
-    q.slab_bytes = TM_BM * TM_ROW;
+    q.slab_bytes = TM_BM * (uint32_t)q.cslab * 4u;
   }
   q.slab_stride = (q.slab_bytes + 1023u) & ~1023u;
-  const uint32_t btile = (uint32_t)q.BN * TM_ROW * (x3 ? 2u : 1u);
+  const uint32_t btile = (uint32_t)q.BN * (uint32_t)q.cslab * 4u * (x3 ? 2u : 1u);
   const uint32_t a_stage = q.slab_stride * (x3 ? 2u : 1u);
-  const size_t budget = 220 * 1024;
+  const size_t budget = 205 * 1024;
   q.SA = 2;
   if ((size_t)q.SA * a_stage + 2 * btile > budget) q.SA = 1;
   if ((size_t)q.SA * a_stage + 2 * btile > budget) return fail(CP_ERR_INVALID, "conv_tma: slab does not fit shared memory");
@@ -646,7 +588,7 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.round_tf32 = round_out_tf32;
   q.use_base_offset = use_base_offset;
   q.wtiles = (const unsigned char*)p.wgt_umma;
-  const size_t smem = 2048 + (size_t)q.SA * a_stage + (size_t)q.SB * btile;
+  const size_t smem = 512 + 4 * umma::kStageFloatsPerWarp * 4 + 2048 + (size_t)q.SA * a_stage + (size_t)q.SB * btile;
   static thread_local bool configured[2] = {false, false};
   if (!configured[x3 ? 1 : 0]) {
     if (x3)

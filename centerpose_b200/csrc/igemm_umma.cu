@@ -19,6 +19,7 @@
 //   PREC_TF32X3 kind::tf32, 3-term split  a_hi*b_hi + a_lo*b_hi + a_hi*b_lo     (fp32-equivalent mode)
 // Every mbarrier wait carries a clock64 watchdog that traps instead of hanging the GPU.
 #include "common.cuh"
+#include "umma_common.cuh"
 
 namespace cp {
 namespace {
@@ -29,64 +30,8 @@ constexpr int UM_THREADS = (UM_PROD_WARPS + 2) * 32;
 constexpr uint32_t ROW_BYTES = 128;        // one K block = 128 bytes per row (64 bf16 / 32 tf32)
 constexpr uint32_t A_TILE_BYTES = UM_BM * ROW_BYTES;
 
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+using namespace umma;
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the device
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("igemm_umma: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
-             parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 template <int KIND_TF32>
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   if (KIND_TF32) {
@@ -103,16 +48,6 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
         : "memory");
   }
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4, [16,30) LBO >> 4 (ignored for swizzled K-major, 1), [32,46) SBO >> 4 = 1024 B between
 //   8-row groups, [46,48) version = 1, [61,64) layout type = 2 (SWIZZLE_128B)
@@ -123,20 +58,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 // [7,10) / [10,13), K-major A and B (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29)
 __device__ __forceinline__ uint32_t make_idesc(int n, int fmt) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half <- a
-  return r;
-}
-__device__ __forceinline__ float tf32_round(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 struct UmmaSmem {   // control block at the head of dynamic smem (the tiles follow, 1024-byte aligned)
@@ -159,11 +80,11 @@ struct PrecTraits<1> {   // tf32 x 3
 
 // ------------------------------------------------------------------ the kernel
 template <int PREC, int MODE>
-__global__ void __launch_bounds__(UM_THREADS) igemm_umma_kernel(const IgemmParams p, const int BN, const int STAGES) {
+__global__ void __launch_bounds__(UM_THREADS) igemm_umma_kernel(const IgemmParams p, const int BN, const int STAGES, const int NACC) {
   using T = PrecTraits<PREC>;
   extern __shared__ __align__(1024) unsigned char smem[];
   UmmaSmem* ctl = reinterpret_cast<UmmaSmem*>(smem);
-  const uint32_t tiles0 = (smem_u32(smem) + 1024u + 1023u) & ~1023u;   // first tile, 1024-aligned
+  const uint32_t tiles0 = (smem_u32(smem) + 512u + 4u * kStageFloatsPerWarp * 4u + 1023u) & ~1023u;   // first tile, 1024-aligned
   const uint32_t b_tile_bytes = (uint32_t)BN * ROW_BYTES * T::kTilesA; // hi (+ lo) weight tiles of one stage
   const uint32_t a_bytes = A_TILE_BYTES * T::kTilesA;
   const uint32_t stage_bytes = a_bytes + b_tile_bytes;
@@ -187,7 +108,7 @@ __global__ void __launch_bounds__(UM_THREADS) igemm_umma_kernel(const IgemmParam
     fence_mbar_init();
   }
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < BN) tmem_cols <<= 1;
+  while ((int)tmem_cols < BN * NACC) tmem_cols <<= 1;
   if (warp == UM_PROD_WARPS) {
     tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     tmem_relinquish();
@@ -364,45 +285,41 @@ __global__ void __launch_bounds__(UM_THREADS) igemm_umma_kernel(const IgemmParam
     mbar_wait(smem_u32(&ctl->accum_full), 0u);
     tc_fence_after();
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t rr[16];
-      tmem_ld16(lane_base + (uint32_t)c0, rr);     // warp-collective: every lane participates
-      tmem_ld_wait();
-      const int nb = n_tile * BN + c0;
-      if (valid && nb < p.Cout) {
-        float vv[16];
+    float* stage = reinterpret_cast<float*>(smem + 512) + warp * kStageFloatsPerWarp;
+    EpiParams ep;
+    ep.bias = p.bias;
+    ep.residual = p.residual;
+    ep.resStride = p.resStride;
+    ep.relu = p.relu;
+    ep.res_after_relu = p.res_after_relu;
+    ep.round_tf32 = 0;
+    ep.out = p.out;
+    ep.outStride = p.outStride;
+    ep.out_nchw = p.out_nchw;
+    ep.Cout = p.Cout;
+    ep.CoutPad = p.CoutPad;
+    ep.H = p.Hout;
+    ep.W = p.Wout;
+    const int col_end = min(p.Cout, (n_tile + 1) * BN);
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float vv[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) vv[j] = __uint_as_float(rr[j]) + __ldg(p.bias + nb + j);
-        if (p.residual && !p.res_after_relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < p.Cout) vv[j] += __ldg(p.residual + (size_t)m * p.resStride + nb + j);
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) vv[j] = fmaxf(vv[j], 0.f);
-        }
-        if (p.residual && p.res_after_relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < p.Cout) vv[j] += __ldg(p.residual + (size_t)m * p.resStride + nb + j);
-        }
-        if (p.out_nchw) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < p.Cout) p.out[(((size_t)n * p.Cout + nb + j) * p.Hout + oy) * p.Wout + ox] = vv[j];
+      for (int j = 0; j < 32; ++j) vv[j] = 0.f;
+      // the K blocks were dealt round-robin to NACC TMEM accumulators (shorter truncating chains); sum them in fp32
+      for (int a = 0; a < NACC; ++a) {
+        uint32_t rr[32];
+        tmem_ld16(lane_base + (uint32_t)(a * BN + c0), rr);
+        if (c0 + 16 < BN) {
+          tmem_ld16(lane_base + (uint32_t)(a * BN + c0 + 16), rr + 16);
         } else {
-          float* o = p.out + (size_t)m * p.outStride + nb;
-          if (nb + 15 < p.Cout) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(vv[j], vv[j + 1], vv[j + 2], vv[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (nb + j < p.Cout) o[j] = vv[j];
-          }
+          for (int j = 16; j < 32; ++j) rr[j] = 0u;
         }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) vv[j] += __uint_as_float(rr[j]);
       }
+      epilogue_sub_tile(ep, stage, vv, lane, valid, m, n, oy, ox, n_tile * BN + c0, col_end);
     }
     }
   } else if (warp == UM_PROD_WARPS) {
@@ -417,16 +334,18 @@ __global__ void __launch_bounds__(UM_THREADS) igemm_umma_kernel(const IgemmParam
         const uint32_t a_hi = tiles0 + (uint32_t)stage * stage_bytes;
         const uint32_t b_hi = a_hi + a_bytes;
         const uint64_t da_hi = make_desc(a_hi), db_hi = make_desc(b_hi);
+        const uint32_t d_tmem = tmem_base + (uint32_t)((kb % NACC) * BN);
+        const bool fresh = kb < NACC;        // first K block of this accumulator overwrites it
 #pragma unroll
         for (int k = 0; k < 4; ++k) {       // 4 x 32-byte K slices per 128-byte row
           const uint64_t adv = (uint64_t)(k * 2);
           if (PREC == 0) {
-            umma<0>(tmem_base, da_hi + adv, db_hi + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma<0>(d_tmem, da_hi + adv, db_hi + adv, idesc, (!fresh || k > 0) ? 1u : 0u);
           } else {
             const uint64_t da_lo = make_desc(a_hi + A_TILE_BYTES), db_lo = make_desc(b_hi + (uint32_t)BN * ROW_BYTES);
-            umma<1>(tmem_base, da_lo + adv, db_hi + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            umma<1>(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
-            umma<1>(tmem_base, da_hi + adv, db_hi + adv, idesc, 1u);
+            umma<1>(d_tmem, da_lo + adv, db_hi + adv, idesc, (!fresh || k > 0) ? 1u : 0u);
+            umma<1>(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
+            umma<1>(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
           }
         }
         umma_commit(smem_u32(&ctl->empty[stage]));     // frees the stage when these MMAs have read it
@@ -552,13 +471,13 @@ int launch_igemm_umma(const IgemmParams& p, int prec, cudaStream_t stream) {
   const int bn = umma_tile_n(p.CoutPad);
   const int tilesA = prec == 0 ? 1 : 2;
   const size_t stage_bytes = (size_t)A_TILE_BYTES * tilesA + (size_t)bn * ROW_BYTES * tilesA;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  int stages = (int)((185 * 1024) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 2) return fail(CP_ERR_INVALID, "igemm_umma: tile does not fit shared memory");
-  const size_t smem = 2048 + stages * stage_bytes;
+  const size_t smem = 512 + 4 * umma::kStageFloatsPerWarp * 4 + 2048 + stages * stage_bytes;
   const int M = p.B * p.Hout * p.Wout;
   dim3 grid((unsigned)((size_t)(p.CoutPad / bn) * ((M + UM_BM - 1) / UM_BM)));
-  void (*kern)(const IgemmParams, const int, const int) = nullptr;
+  void (*kern)(const IgemmParams, const int, const int, const int) = nullptr;
   if (prec == 0)
     kern = (p.mode == IGEMM_DCN) ? igemm_umma_kernel<0, IGEMM_DCN> : igemm_umma_kernel<0, IGEMM_NHWC_VEC>;
   else
@@ -569,7 +488,16 @@ int launch_igemm_umma(const IgemmParams& p, int prec, cudaStream_t stream) {
     CP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured[slot] = true;
   }
-  kern<<<grid, UM_THREADS, smem, stream>>>(p, bn, stages);
+  int nacc = 1;                                   // tf32x3: split the K chain over up to 4 TMEM accumulators
+  if (prec == 1) {
+    nacc = 512 / bn;
+    if (nacc > 4) nacc = 4;
+    const int elems = 32;
+    const int KBn = (p.kh * p.kw * p.Cin + elems - 1) / elems;
+    if (nacc > KBn) nacc = KBn;
+    if (nacc < 1) nacc = 1;
+  }
+  kern<<<grid, UM_THREADS, smem, stream>>>(p, bn, stages, nacc);
   CP_LAUNCH_CHECK("igemm_umma_kernel");
   return CP_OK;
 }

@@ -1,0 +1,225 @@
+// PTX wrappers and epilogue helpers shared by the tcgen05 kernels (igemm_umma.cu, conv_tma.cu).  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace cp {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("tcgen05 kernel: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half <- a
+  return r;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4f(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogue store of a [32 rows x 32 columns] sub-tile owned by ONE warp (lane == row, tcgen05.ld layout) to an NHWC
+// tensor.  A lane holding its row in registers would issue 16-byte stores 32 rows apart (32 sectors per request);
+// instead the warp transposes through a private [32][36]-float staging area so that every store instruction writes
+// four full 128-byte row segments.  Must be called by all 32 lanes.
+//   stage    : this warp's staging area (32 * 36 floats, 16-byte aligned)
+//   vv       : the lane's 32 values, columns col0 .. col0+31 of its row
+//   valid, m : row validity and flattened output pixel of the lane's row
+//   col_end  : first column that must NOT be written (min(Cout, end of this CTA's N tile))
+constexpr int kStagePitch = 36;
+constexpr int kStageFloatsPerWarp = 32 * kStagePitch;
+
+__device__ __forceinline__ void warp_store_rows32(float* stage, const float (&vv)[32], int lane, bool valid, int m,
+                                                  float* __restrict__ out, int outStride, int col0, int col_end) {
+  const uint32_t sbase = smem_u32(stage);
+  const uint32_t srow = sbase + (uint32_t)lane * kStagePitch * 4u;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) st_shared_v4f(srow + q * 16, vv[4 * q], vv[4 * q + 1], vv[4 * q + 2], vv[4 * q + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3);
+    const int j4 = lane & 7;
+    const float4 v = ld_shared_v4f(sbase + (uint32_t)(r * kStagePitch + 4 * j4) * 4u);
+    const int mo = __shfl_sync(0xffffffffu, m, r);
+    const int vo = __shfl_sync(0xffffffffu, (int)valid, r);
+    const int col = col0 + 4 * j4;
+    if (vo && col < col_end) {
+      float* o = out + (size_t)mo * outStride + col;
+      if (col + 3 < col_end) {
+        *reinterpret_cast<float4*>(o) = v;
+      } else {
+        o[0] = v.x;
+        if (col + 1 < col_end) o[1] = v.y;
+        if (col + 2 < col_end) o[2] = v.z;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Coalesced read of the residual rows of the same [32 x 32] sub-tile: afterwards res[j] holds residual[m][col0 + j] of
+// the lane's own row (0 where the row / column is not valid).
+__device__ __forceinline__ void warp_load_rows32(float* stage, float (&res)[32], int lane, bool valid, int m,
+                                                 const float* __restrict__ src, int srcStride, int col0, int col_end) {
+  const uint32_t sbase = smem_u32(stage);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3);
+    const int j4 = lane & 7;
+    const int mo = __shfl_sync(0xffffffffu, m, r);
+    const int vo = __shfl_sync(0xffffffffu, (int)valid, r);
+    const int col = col0 + 4 * j4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vo && col < col_end) {
+      const float* s = src + (size_t)mo * srcStride + col;
+      if (col + 3 < col_end) {
+        v = __ldg(reinterpret_cast<const float4*>(s));
+      } else {
+        v.x = __ldg(s);
+        if (col + 1 < col_end) v.y = __ldg(s + 1);
+        if (col + 2 < col_end) v.z = __ldg(s + 2);
+      }
+    }
+    st_shared_v4f(sbase + (uint32_t)(r * kStagePitch + 4 * j4) * 4u, v.x, v.y, v.z, v.w);
+  }
+  __syncwarp();
+  const uint32_t srow = sbase + (uint32_t)lane * kStagePitch * 4u;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 v = ld_shared_v4f(srow + q * 16);
+    res[4 * q] = v.x;
+    res[4 * q + 1] = v.y;
+    res[4 * q + 2] = v.z;
+    res[4 * q + 3] = v.w;
+  }
+  __syncwarp();
+}
+
+// The fused epilogue of one [32 x 32] sub-tile: bias, residual (before or after the ReLU), ReLU, optional tf32
+// rounding, then an NHWC (transposed, coalesced) or NCHW (already coalesced across lanes) store.
+struct EpiParams {
+  const float* bias;
+  const float* residual;
+  int resStride, relu, res_after_relu, round_tf32;
+  float* out;
+  int outStride, out_nchw;
+  int Cout, CoutPad, H, W;   // Cout/H/W: NCHW addressing; CoutPad: length of the bias vector
+};
+
+__device__ __forceinline__ void epilogue_sub_tile(const EpiParams& e, float* stage, float (&vv)[32], int lane, bool valid,
+                                                  int m, int n, int oy, int ox, int col0, int col_end) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (col0 + j < e.CoutPad) vv[j] += __ldg(e.bias + col0 + j);
+  if (e.residual) {
+    float res[32];
+    warp_load_rows32(stage, res, lane, valid, m, e.residual, e.resStride, col0, col_end);
+    if (!e.res_after_relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) vv[j] += res[j];
+    }
+    if (e.relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) vv[j] = fmaxf(vv[j], 0.f);
+    }
+    if (e.res_after_relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) vv[j] += res[j];
+    }
+  } else if (e.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) vv[j] = fmaxf(vv[j], 0.f);
+  }
+  if (e.round_tf32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) vv[j] = tf32_round(vv[j]);
+  }
+  if (e.out_nchw) {
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < col_end) e.out[(((size_t)n * e.Cout + col0 + j) * e.H + oy) * e.W + ox] = vv[j];
+    }
+  } else {
+    warp_store_rows32(stage, vv, lane, valid, m, e.out, e.outStride, col0, col_end);
+  }
+}
+
+}  // namespace umma
+}  // namespace cp

@@ -471,7 +471,7 @@ int launch_igemm_umma(const IgemmParams& p, int prec, cudaStream_t stream) {
   const int bn = umma_tile_n(p.CoutPad);
   const int tilesA = prec == 0 ? 1 : 2;
   const size_t stage_bytes = (size_t)A_TILE_BYTES * tilesA + (size_t)bn * ROW_BYTES * tilesA;
-  int stages = (int)((185 * 1024) / stage_bytes);
+  int stages = (int)((204 * 1024) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 2) return fail(CP_ERR_INVALID, "igemm_umma: tile does not fit shared memory");
   const size_t smem = 512 + 4 * umma::kStageFloatsPerWarp * 4 + 2048 + stages * stage_bytes;

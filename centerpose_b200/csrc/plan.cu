@@ -629,6 +629,7 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
     }
     q.kh = op.kh;
     q.kw = op.kw;
+    q.Cin = op.Cin;          // selects 32- vs 16-channel slabs (SWIZZLE_128B / SWIZZLE_64B boxes)
     q.Hin = op.src[0].H;
     q.Win = op.src[0].W;
     op.tma_maps.resize(512 + 64);

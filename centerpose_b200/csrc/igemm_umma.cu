@@ -473,6 +473,9 @@ int launch_igemm_umma(const IgemmParams& p, int prec, cudaStream_t stream) {
   const size_t stage_bytes = (size_t)A_TILE_BYTES * tilesA + (size_t)bn * ROW_BYTES * tilesA;
   int stages = (int)((204 * 1024) / stage_bytes);
   if (stages > 6) stages = 6;
+  // deformable gather: neighbouring rows / taps sample overlapping 2x2 neighbourhoods (each input pixel is touched by
+  // up to 36 samples); a small pipeline leaves most of the 228 KB for L1 so those re-reads hit on chip
+  if (p.mode == IGEMM_DCN && stages > 2) stages = 2;
   if (stages < 2) return fail(CP_ERR_INVALID, "igemm_umma: tile does not fit shared memory");
   const size_t smem = 512 + 4 * umma::kStageFloatsPerWarp * 4 + 2048 + stages * stage_bytes;
   const int M = p.B * p.Hout * p.Wout;

@@ -557,6 +557,9 @@ int build_graph(cp_plan* P) {
       q.Win = op.src[0].W;
       const int gather_prec = P->prec == 2 ? 1 : P->prec;
       if (op.src[0].ext >= 0) continue;
+      // 16-channel layers (level0 / level1): 133 K single-tile CTAs of almost no MMA work are dominated by the fixed
+      // per-CTA cost of a tcgen05 kernel (measured 5.2 ms vs 2.5 ms on the FFMA kernel) -> keep them on CUDA cores
+      if (op.Cin < 32) continue;
       if ((P->prec == 2 || P->prec == 1) && tma_conv_supported(q, P->prec == 1)) {
         op.use_tma = true;
         op.umma_off = P->umma_bytes;

@@ -184,40 +184,52 @@ struct EpiParams {
 
 __device__ __forceinline__ void epilogue_sub_tile(const EpiParams& e, float* stage, float (&vv)[32], int lane, bool valid,
                                                   int m, int n, int oy, int ox, int col0, int col_end) {
+  (void)stage;
+  (void)lane;
 #pragma unroll
   for (int j = 0; j < 32; ++j)
     if (col0 + j < e.CoutPad) vv[j] += __ldg(e.bias + col0 + j);
-  if (e.residual) {
-    float res[32];
-    warp_load_rows32(stage, res, lane, valid, m, e.residual, e.resStride, col0, col_end);
-    if (!e.res_after_relu) {
+  // Measured on B200 (run 9 vs run 8, profiles/): routing the tile through shared memory so that stores are fully
+  // coalesced (warp_store_rows32) is SLOWER than letting every lane stream its own row with 16-byte stores -- the
+  // lane's consecutive float4 stores fill whole sectors back to back and L2 merges them, while the transpose costs
+  // two shared-memory round trips and 16 shuffles per sub-tile.  The direct path is used; the helpers stay for tests.
+  if (e.residual && valid && !e.res_after_relu) {
+    const float* r = e.residual + (size_t)m * e.resStride + col0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) vv[j] += res[j];
-    }
-    if (e.relu) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) vv[j] = fmaxf(vv[j], 0.f);
-    }
-    if (e.res_after_relu) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) vv[j] += res[j];
-    }
-  } else if (e.relu) {
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < col_end) vv[j] += __ldg(r + j);
+  }
+  if (e.relu) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) vv[j] = fmaxf(vv[j], 0.f);
+  }
+  if (e.residual && valid && e.res_after_relu) {
+    const float* r = e.residual + (size_t)m * e.resStride + col0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < col_end) vv[j] += __ldg(r + j);
   }
   if (e.round_tf32) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) vv[j] = tf32_round(vv[j]);
   }
+  if (!valid) return;
   if (e.out_nchw) {
-    if (valid) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < col_end) e.out[(((size_t)n * e.Cout + col0 + j) * e.H + oy) * e.W + ox] = vv[j];
-    }
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < col_end) e.out[(((size_t)n * e.Cout + col0 + j) * e.H + oy) * e.W + ox] = vv[j];
   } else {
-    warp_store_rows32(stage, vv, lane, valid, m, e.out, e.outStride, col0, col_end);
+    float* o = e.out + (size_t)m * e.outStride + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (col0 + j + 3 < col_end) {
+        *reinterpret_cast<float4*>(o + j) = make_float4(vv[j], vv[j + 1], vv[j + 2], vv[j + 3]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (col0 + j + t < col_end) o[j + t] = vv[j + t];
+      }
+    }
   }
 }
 

@@ -102,9 +102,10 @@ int launch_gru_gates(const float* xi, const float* hh, const float* hprev, float
 // x3 = 1: 3-term split with two-level accumulation (fp32-equivalent); x3 = 0: single tf32 pass
 bool tma_conv_supported(const IgemmParams& p, int x3);
 size_t tma_weight_bytes(int Cin, int taps, int CoutPad, int x3);
+int tma_cslab(const IgemmParams& p, int x3);     // channels per activation slab (32 or 16); needs Cin, kh, Win, CoutPad
 int launch_pack_tma_weight(const float* src_k_by_ld, int ld, int Cin, int taps, int Cout, int CoutPad, int round_tf32,
-                           int x3, void* dst, cudaStream_t s);
-int tma_conv_encode(const IgemmParams& p, int Bmax, void* maps_out /* 4 x 128 bytes */);
+                           int x3, int cslab, void* dst, cudaStream_t s);
+int tma_conv_encode(const IgemmParams& p, int Bmax, int x3, void* maps_out /* 4 x 128 bytes */);
 int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, int use_base_offset, int x3,
                     cudaStream_t stream);
 

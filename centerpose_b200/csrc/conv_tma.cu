@@ -456,7 +456,18 @@ EncodeTiledFn get_encode() {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------- host side
-int tma_cslab(int Cin) { return (Cin % 32 == 0) ? 32 : 16; }
+// Channels per activation slab.  32 (128-byte rows) by default; 16 (64-byte rows, SWIZZLE_64B) when Cin is not a
+// multiple of 32, or when the 3-term split (hi + lo slabs) could not be double-buffered with 32-channel slabs.
+int tma_cslab(const IgemmParams& p, int x3) {
+  if (p.Cin % 32) return 16;
+  if (!x3 || p.kh != 3) return 32;
+  const int Wt = p.Win + 2;
+  const int boxh = (129 + 2 * Wt + Wt - 1) / Wt + 1;
+  const size_t slab32 = ((size_t)boxh * Wt * 128 + 1023) / 1024 * 1024;
+  const int bn = p.CoutPad <= 128 ? p.CoutPad : 128;
+  const size_t need = 2 * (2 * slab32) + 2 * ((size_t)bn * 128 * 2);
+  return need > (size_t)205 * 1024 ? 16 : 32;
+}
 
 int tma_tile_n(int CoutPad, int x3) {
   const int cap = x3 ? 128 : 256;     // x3 keeps the promoted sums of one row in 128 registers
@@ -467,7 +478,7 @@ bool tma_conv_supported(const IgemmParams& p, int x3) {
   if (p.mode != IGEMM_NHWC_VEC) return false;
   if (!((p.kh == 1 && p.kw == 1 && p.pad == 0) || (p.kh == 3 && p.kw == 3 && p.pad == 1))) return false;
   if (p.stride != 1) return false;
-  const int cs = tma_cslab(p.Cin);
+  const int cs = tma_cslab(p, x3);
   if (p.Cin % cs) return false;
   for (int s = 0; s < p.nsrc; ++s)
     if (p.srcC[s] % cs || p.srcStride[s] % 4) return false;
@@ -482,11 +493,10 @@ size_t tma_weight_bytes(int Cin, int taps, int CoutPad, int x3) {
 }
 
 int launch_pack_tma_weight(const float* src, int ld, int Cin, int taps, int Cout, int CoutPad, int round_tf32, int x3,
-                           void* dst, cudaStream_t s) {
+                           int cs, void* dst, cudaStream_t s) {
   const int bn = tma_tile_n(CoutPad, x3);
   if (x3) round_tf32 = 1;
   const int nt = CoutPad / bn;
-  const int cs = tma_cslab(Cin);
   size_t total = (size_t)nt * (Cin / cs) * taps * bn * (cs / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
@@ -496,13 +506,13 @@ int launch_pack_tma_weight(const float* src, int ld, int Cin, int taps, int Cout
 }
 
 // Encodes the tensor maps of the op's sources into `maps_out` (4 x 128 bytes, host memory, reusable across launches).
-int tma_conv_encode(const IgemmParams& p, int Bmax, void* maps_out) {
+int tma_conv_encode(const IgemmParams& p, int Bmax, int x3, void* maps_out) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(CP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(maps_out);
   const int Wt = p.Win + 2;
   const int boxh = (129 + 2 * Wt + Wt - 1) / Wt + 1;
-  const int cs = tma_cslab(p.Cin);
+  const int cs = tma_cslab(p, x3);
   const CUtensorMapSwizzle swz = cs == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   for (int s = 0; s < p.nsrc; ++s) {
     CUresult r;
@@ -545,7 +555,7 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.CoutPad = p.CoutPad;
   q.BN = tma_tile_n(p.CoutPad, x3);
   q.x3 = x3;
-  q.cslab = tma_cslab(p.Cin);
+  q.cslab = tma_cslab(p, x3);
   q.group = TM_GROUP_X3 * (32 / q.cslab);       // same number of MMAs per TMEM accumulation group
   q.k = p.kh;
   q.Wt = p.Win + 2;

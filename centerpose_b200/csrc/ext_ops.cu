@@ -83,8 +83,8 @@ static int run_igemm(IgemmParams& p, int prec, int Kreal, cudaStream_t s) {
       const int taps = p.kh * p.kw;
       CP_CUDA_CHECK(cudaMallocAsync(&tiles, tma_weight_bytes(p.Cin, taps, p.CoutPad, x3), s));
       alignas(64) unsigned char maps[512];
-      int rc = tma_conv_encode(p, p.B, maps);
-      if (!rc) rc = launch_pack_tma_weight(p.wgt, p.CoutPad, p.Cin, taps, p.Cout, p.CoutPad, 1, x3, tiles, s);
+      int rc = tma_conv_encode(p, p.B, x3, maps);
+      if (!rc) rc = launch_pack_tma_weight(p.wgt, p.CoutPad, p.Cin, taps, p.Cout, p.CoutPad, 1, x3, tma_cslab(p, x3), tiles, s);
       if (!rc) {
         p.wgt_umma = tiles;
         const char* e = getenv("CP_TMA_BASE_OFFSET");

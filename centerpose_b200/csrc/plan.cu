@@ -55,6 +55,7 @@ struct Op {
   int w_ld = 0;            // leading dimension of the fp32 packed weight matrix
   bool use_umma = false;   // run on the tcgen05 gather kernel
   bool use_tma = false;    // run on the TMA-fed tcgen05 kernel (conv_tma.cu)
+  int tma_cslab = 32;
   std::vector<unsigned char> tma_maps;   // 4 CUtensorMap, encoded once the arena exists
   size_t umma_off = 0;     // bytes into the plan's tensor-core weight-tile buffer
   Act om;
@@ -632,12 +633,14 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
     }
     q.kh = op.kh;
     q.kw = op.kw;
-    q.Cin = op.Cin;          // selects 32- vs 16-channel slabs (SWIZZLE_128B / SWIZZLE_64B boxes)
+    q.Cin = op.Cin;          // Cin / kh / Win / CoutPad select 32- vs 16-channel slabs (tma_cslab)
+    q.CoutPad = op.CoutPad;
     q.Hin = op.src[0].H;
     q.Win = op.src[0].W;
+    op.tma_cslab = tma_cslab(q, P->prec == 1);
     op.tma_maps.resize(512 + 64);
     unsigned char* mp = (unsigned char*)(((uintptr_t)op.tma_maps.data() + 63) & ~(uintptr_t)63);
-    int rc2 = tma_conv_encode(q, P->B, mp);
+    int rc2 = tma_conv_encode(q, P->B, P->prec == 1, mp);
     if (rc2) return rc2;
   }
   int n = 0;
@@ -723,7 +726,7 @@ int cp_plan_load_weights(cp_plan* P, const char* const* names, const void* const
     if (op.type != OP_IGEMM) continue;
     if (op.use_tma) {
       if ((rc = launch_pack_tma_weight(P->wts + op.w_off, op.w_ld, op.Cin, op.kh * op.kw, op.Cout, op.CoutPad, 1,
-                                       P->prec == 1, P->umma_wts + op.umma_off, s)))
+                                       P->prec == 1, op.tma_cslab, P->umma_wts + op.umma_off, s)))
         return rc;
     } else if (op.use_umma) {
       if ((rc = launch_pack_umma_weight(P->wts + op.w_off, op.w_ld, op.kh * op.kw * op.Cin, op.Cout, op.CoutPad,

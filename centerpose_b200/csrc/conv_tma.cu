@@ -38,6 +38,7 @@ struct TmaConvParams {
   int k;              // 1 or 3
   int Wt, boxh;       // padded pitch and slab rows (k == 3)
   int tiles_per_image;
+  long long total_tiles;                // m tiles x n tiles (n fastest)
   uint32_t slab_bytes, slab_stride;   // TMA transaction bytes, 1024-aligned stage stride
   int SA, SB;
   const float* bias;
@@ -100,6 +101,33 @@ struct TmaCtl {
 
 constexpr int TM_THREADS_X3 = 384;    // + warps 8-11: hi/lo splitters
 
+// Tile geometry of one 128-position output tile.
+struct TileGeo {
+  int n_tile, img, g0, r_lo;
+  long long pos0;
+};
+__device__ __forceinline__ TileGeo decode_tile(const TmaConvParams& p, long long tile, int n_tiles) {
+  TileGeo g;
+  g.n_tile = (int)(tile % n_tiles);
+  const long long m_tile = tile / n_tiles;
+  g.img = 0;
+  g.g0 = 0;
+  g.r_lo = 0;
+  g.pos0 = 0;
+  if (p.k == 3) {
+    g.img = (int)(m_tile / p.tiles_per_image);
+    g.g0 = (int)(m_tile - (long long)g.img * p.tiles_per_image) * TM_BM;
+    const int t = g.g0 - 1;
+    g.r_lo = (t >= 0) ? t / p.Wt : -((-t + p.Wt - 1) / p.Wt);      // floor((g0 - 1) / Wt)
+  } else {
+    g.pos0 = m_tile * TM_BM;
+  }
+  return g;
+}
+
+// PERSISTENT kernel: gridDim.x = min(#tiles, #SMs); CTA c processes tiles c, c + gridDim.x, ...  Every role keeps its
+// pipeline state across tiles, so the TMA / split / MMA of tile i+1 overlap the epilogue of tile i and the fixed cost
+// of a CTA (barrier init, TMEM allocation, descriptor fetch, pipeline fill) is paid once per SM instead of per tile.
 template <bool X3>
 __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmaConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -113,23 +141,10 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = p.CoutPad / p.BN;
-  const int n_tile = blockIdx.x % n_tiles;
-  const int m_tile = blockIdx.x / n_tiles;
   const int taps = p.k * p.k;
   const int nslab = p.Cin / p.cslab;
   const int KB = nslab * taps;
-
-  // tile geometry
-  int img = 0, g0 = 0, r_lo = 0;
-  long long pos0 = 0;    // k == 1: first flattened pixel of the tile
-  if (p.k == 3) {
-    img = m_tile / p.tiles_per_image;
-    g0 = (m_tile - img * p.tiles_per_image) * TM_BM;
-    const int t = g0 - 1;
-    r_lo = (t >= 0) ? t / p.Wt : -((-t + p.Wt - 1) / p.Wt);      // floor((g0 - 1) / Wt)
-  } else {
-    pos0 = (long long)m_tile * TM_BM;
-  }
+  const long long total_tiles = p.total_tiles;
 
   if (tid == 0) {
     for (int s = 0; s < p.SA; ++s) {
@@ -137,19 +152,19 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
       mbar_init(smem_u32(&ctl->a_empty[s]), 1);
       mbar_init(smem_u32(&ctl->a_split[s]), 128);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&ctl->p_full[s]), 1);
-      mbar_init(smem_u32(&ctl->p_empty[s]), 128);
-    }
     for (int s = 0; s < p.SB; ++s) {
       mbar_init(smem_u32(&ctl->b_full[s]), 1);
       mbar_init(smem_u32(&ctl->b_empty[s]), 1);
     }
-    mbar_init(smem_u32(&ctl->accum_full), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&ctl->p_full[s]), 1);       // x3: accumulation group ready / x1: tile accumulator ready
+      mbar_init(smem_u32(&ctl->p_empty[s]), 128);    // drained by the 128 epilogue threads
+    }
     fence_mbar_init();
   }
+  // two TMEM accumulator buffers of BN columns: x1 ping-pongs whole tiles, x3 ping-pongs accumulation groups
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.BN * (X3 ? 2 : 1)) tmem_cols <<= 1;
+  while ((int)tmem_cols < p.BN * 2) tmem_cols <<= 1;
   if (warp == 2) {
     tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     tmem_relinquish();
@@ -164,23 +179,26 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int s = 0; s < nslab; ++s) {
-        int src = 0, cb = 0;
-        while (src + 1 < p.nsrc && s * p.cslab >= cb + p.srcC[src]) {
-          cb += p.srcC[src];
-          ++src;
-        }
-        mbar_wait(smem_u32(&ctl->a_empty[stage]), phase ^ 1u);
-        const uint32_t bar = smem_u32(&ctl->a_full[stage]);
-        mbar_arrive_expect_tx(bar, p.slab_bytes);
-        const uint32_t dst = slabs0 + (uint32_t)stage * a_stage;
-        if (p.k == 3)
-          tma_load_4d(dst, &p.amap[src], s * p.cslab - cb, -1, r_lo - 1, img, bar);
-        else
-          tma_load_2d(dst, &p.amap[src], s * p.cslab - cb, (int)pos0, bar);
-        if (++stage == p.SA) {
-          stage = 0;
-          phase ^= 1u;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileGeo g = decode_tile(p, tile, n_tiles);
+        for (int s = 0; s < nslab; ++s) {
+          int src = 0, cb = 0;
+          while (src + 1 < p.nsrc && s * p.cslab >= cb + p.srcC[src]) {
+            cb += p.srcC[src];
+            ++src;
+          }
+          mbar_wait(smem_u32(&ctl->a_empty[stage]), phase ^ 1u);
+          const uint32_t bar = smem_u32(&ctl->a_full[stage]);
+          mbar_arrive_expect_tx(bar, p.slab_bytes);
+          const uint32_t dst = slabs0 + (uint32_t)stage * a_stage;
+          if (p.k == 3)
+            tma_load_4d(dst, &p.amap[src], s * p.cslab - cb, -1, g.r_lo - 1, g.img, bar);
+          else
+            tma_load_2d(dst, &p.amap[src], s * p.cslab - cb, (int)g.pos0, bar);
+          if (++stage == p.SA) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
     }
@@ -188,17 +206,20 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   } else if (warp == 1) {
     // ===================== weight tiles =====================
     if (lane == 0) {
-      const unsigned char* wsrc = p.wtiles + (size_t)n_tile * KB * btile_bytes;
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < KB; ++kb) {
-        mbar_wait(smem_u32(&ctl->b_empty[stage]), phase ^ 1u);
-        const uint32_t bar = smem_u32(&ctl->b_full[stage]);
-        mbar_arrive_expect_tx(bar, btile_bytes);
-        bulk_g2s(btiles0 + (uint32_t)stage * btile_bytes, wsrc + (size_t)kb * btile_bytes, btile_bytes, bar);
-        if (++stage == p.SB) {
-          stage = 0;
-          phase ^= 1u;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = (int)(tile % n_tiles);
+        const unsigned char* wsrc = p.wtiles + (size_t)n_tile * KB * btile_bytes;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(smem_u32(&ctl->b_empty[stage]), phase ^ 1u);
+          const uint32_t bar = smem_u32(&ctl->b_full[stage]);
+          mbar_arrive_expect_tx(bar, btile_bytes);
+          bulk_g2s(btiles0 + (uint32_t)stage * btile_bytes, wsrc + (size_t)kb * btile_bytes, btile_bytes, bar);
+          if (++stage == p.SB) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
     }
@@ -209,62 +230,62 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
       const uint32_t idesc = make_idesc_tf32(p.BN);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      int kbi = 0;                       // running K-block index (slab-major, tap-minor)
       int buf = 0;
       uint32_t pe[2] = {0u, 0u};         // phases of p_empty
-      for (int s = 0; s < nslab; ++s) {
-        mbar_wait(smem_u32(X3 ? &ctl->a_split[sa] : &ctl->a_full[sa]), pa);
-        tc_fence_after();
-        const uint32_t slab = slabs0 + (uint32_t)sa * a_stage;
-        for (int t = 0; t < taps; ++t, ++kbi) {
-          bool first = (kbi == 0);
-          if (X3) {
-            first = (kbi % p.group == 0);
-            if (first) {                 // new accumulation group: the epilogue must have drained this TMEM buffer
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileGeo g = decode_tile(p, tile, n_tiles);
+        int kbi = 0;                     // K-block index inside the tile (slab-major, tap-minor)
+        for (int s = 0; s < nslab; ++s) {
+          mbar_wait(smem_u32(X3 ? &ctl->a_split[sa] : &ctl->a_full[sa]), pa);
+          tc_fence_after();
+          const uint32_t slab = slabs0 + (uint32_t)sa * a_stage;
+          for (int t = 0; t < taps; ++t, ++kbi) {
+            const bool first = X3 ? (kbi % p.group == 0) : (kbi == 0);
+            if (first) {                 // new accumulation group / tile: the epilogue must have drained this TMEM buffer
               mbar_wait(smem_u32(&ctl->p_empty[buf]), pe[buf] ^ 1u);
               tc_fence_after();
             }
-          }
-          mbar_wait(smem_u32(&ctl->b_full[sb]), pb);
-          tc_fence_after();
-          uint32_t a_addr = slab;
-          if (p.k == 3) {
-            const int ky = t / 3, kx = t - ky * 3;
-            a_addr += (uint32_t)(g0 + ky * p.Wt + kx - 1 - r_lo * p.Wt) * rowb;
-          }
-          const uint32_t b_addr = btiles0 + (uint32_t)sb * btile_bytes;
-          const uint32_t d_tmem = tmem_base + (X3 ? (uint32_t)(buf * p.BN) : 0u);
-          for (int ks = 0; ks < kslices; ++ks) {
-            const uint64_t da = make_desc(a_addr + ks * 32, p.use_base_offset, p.cslab);
-            const uint64_t db = make_desc(b_addr + ks * 32, 0, p.cslab);
-            if (X3) {
-              const uint64_t da_lo = make_desc(a_addr + p.slab_stride + ks * 32, p.use_base_offset, p.cslab);
-              const uint64_t db_lo = make_desc(b_addr + (uint32_t)p.BN * rowb + ks * 32, 0, p.cslab);
-              umma_tf32(d_tmem, da_lo, db, idesc, (first && ks == 0) ? 0u : 1u);
-              umma_tf32(d_tmem, da, db_lo, idesc, 1u);
-              umma_tf32(d_tmem, da, db, idesc, 1u);
-            } else {
-              umma_tf32(d_tmem, da, db, idesc, (first && ks == 0) ? 0u : 1u);
+            mbar_wait(smem_u32(&ctl->b_full[sb]), pb);
+            tc_fence_after();
+            uint32_t a_addr = slab;
+            if (p.k == 3) {
+              const int ky = t / 3, kx = t - ky * 3;
+              a_addr += (uint32_t)(g.g0 + ky * p.Wt + kx - 1 - g.r_lo * p.Wt) * rowb;
+            }
+            const uint32_t b_addr = btiles0 + (uint32_t)sb * btile_bytes;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
+            for (int ks = 0; ks < kslices; ++ks) {
+              const uint64_t da = make_desc(a_addr + ks * 32, p.use_base_offset, p.cslab);
+              const uint64_t db = make_desc(b_addr + ks * 32, 0, p.cslab);
+              if (X3) {
+                const uint64_t da_lo = make_desc(a_addr + p.slab_stride + ks * 32, p.use_base_offset, p.cslab);
+                const uint64_t db_lo = make_desc(b_addr + (uint32_t)p.BN * rowb + ks * 32, 0, p.cslab);
+                umma_tf32(d_tmem, da_lo, db, idesc, (first && ks == 0) ? 0u : 1u);
+                umma_tf32(d_tmem, da, db_lo, idesc, 1u);
+                umma_tf32(d_tmem, da, db, idesc, 1u);
+              } else {
+                umma_tf32(d_tmem, da, db, idesc, (first && ks == 0) ? 0u : 1u);
+              }
+            }
+            umma_commit(smem_u32(&ctl->b_empty[sb]));
+            if (++sb == p.SB) {
+              sb = 0;
+              pb ^= 1u;
+            }
+            const bool last = X3 ? ((kbi % p.group == p.group - 1) || kbi == KB - 1) : (kbi == KB - 1);
+            if (last) {
+              umma_commit(smem_u32(&ctl->p_full[buf]));     // group / tile finished -> epilogue
+              pe[buf] ^= 1u;
+              buf ^= 1;
             }
           }
-          umma_commit(smem_u32(&ctl->b_empty[sb]));
-          if (++sb == p.SB) {
-            sb = 0;
-            pb ^= 1u;
+          umma_commit(smem_u32(&ctl->a_empty[sa]));
+          if (++sa == p.SA) {
+            sa = 0;
+            pa ^= 1u;
           }
-          if (X3 && ((kbi % p.group == p.group - 1) || kbi == KB - 1)) {
-            umma_commit(smem_u32(&ctl->p_full[buf]));     // group finished -> epilogue promotes it
-            pe[buf] ^= 1u;
-            buf ^= 1;
-          }
-        }
-        umma_commit(smem_u32(&ctl->a_empty[sa]));
-        if (++sa == p.SA) {
-          sa = 0;
-          pa ^= 1u;
         }
       }
-      if (!X3) umma_commit(smem_u32(&ctl->accum_full));
     }
     __syncwarp();
   } else if (X3 && warp >= 8) {
@@ -273,53 +294,43 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t nchunk = p.slab_bytes >> 4;
-    for (int s = 0; s < nslab; ++s) {
-      mbar_wait(smem_u32(&ctl->a_full[stage]), phase);
-      const uint32_t hi = slabs0 + (uint32_t)stage * a_stage;
-      const uint32_t lo = hi + p.slab_stride;
-      for (uint32_t c = st; c < nchunk; c += 128) {
-        float4 v;
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi + (c << 4)));
-        float4 h, l;
-        h.x = tf32_round(v.x); l.x = tf32_round(v.x - h.x);
-        h.y = tf32_round(v.y); l.y = tf32_round(v.y - h.y);
-        h.z = tf32_round(v.z); l.z = tf32_round(v.z - h.z);
-        h.w = tf32_round(v.w); l.w = tf32_round(v.w - h.w);
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi + (c << 4)), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo + (c << 4)), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(smem_u32(&ctl->a_split[stage]));
-      if (++stage == p.SA) {
-        stage = 0;
-        phase ^= 1u;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int s = 0; s < nslab; ++s) {
+        mbar_wait(smem_u32(&ctl->a_full[stage]), phase);
+        const uint32_t hi = slabs0 + (uint32_t)stage * a_stage;
+        const uint32_t lo = hi + p.slab_stride;
+        for (uint32_t c0 = st; c0 < nchunk; c0 += 128 * 4) {
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)                       // 4 independent loads in flight per thread
+            if (c0 + u * 128 < nchunk) v[u] = ld_shared_v4f(hi + ((c0 + u * 128) << 4));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (c0 + u * 128 < nchunk) {
+              float4 h, l;
+              h.x = tf32_round(v[u].x); l.x = tf32_round(v[u].x - h.x);
+              h.y = tf32_round(v[u].y); l.y = tf32_round(v[u].y - h.y);
+              h.z = tf32_round(v[u].z); l.z = tf32_round(v[u].z - h.z);
+              h.w = tf32_round(v[u].w); l.w = tf32_round(v[u].w - h.w);
+              st_shared_v4f(hi + ((c0 + u * 128) << 4), h.x, h.y, h.z, h.w);
+              st_shared_v4f(lo + ((c0 + u * 128) << 4), l.x, l.y, l.z, l.w);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(smem_u32(&ctl->a_split[stage]));
+        if (++stage == p.SA) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================== epilogue: TMEM lane == flattened output position =====================
     const int q = warp & 3;
     const int i = q * 32 + lane;
-    bool valid;
-    int n, oy, ox;
-    if (p.k == 3) {
-      const int g = g0 + i;
-      oy = g / p.Wt;
-      const int xp = g - oy * p.Wt;
-      ox = xp - 1;
-      n = img;
-      valid = (oy < p.H) && (xp >= 1) && (xp <= p.W);
-    } else {
-      const long long pix = pos0 + i;
-      valid = pix < (long long)p.B * p.H * p.W;
-      const long long pp = valid ? pix : 0;
-      ox = (int)(pp % p.W);
-      const long long t = pp / p.W;
-      oy = (int)(t % p.H);
-      n = (int)(t / p.H);
-    }
-    const int m = (int)(((size_t)n * p.H + oy) * p.W + ox);
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* stage = reinterpret_cast<float*>(smem + 512) + q * kStageFloatsPerWarp;    // per-warp transpose area
+    float* stage = reinterpret_cast<float*>(smem + 512) + q * kStageFloatsPerWarp;    // per-warp scratch (unused by the direct store path)
     EpiParams ep;
     ep.bias = p.bias;
     ep.residual = p.residual;
@@ -334,60 +345,90 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     ep.CoutPad = p.CoutPad;
     ep.H = p.H;
     ep.W = p.W;
-    const int col_end = min(p.Cout, (n_tile + 1) * p.BN);
-    float sums[X3 ? 128 : 1];
-    if (X3) {
-      // two-level accumulation: the tensor core only ever sums `group` K blocks in TMEM (its accumulator truncates,
-      // error ~ chain length); every finished group is added into fp32 registers with round-to-nearest
+    int buf = 0;
+    uint32_t pf[2] = {0u, 0u};
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileGeo g = decode_tile(p, tile, n_tiles);
+      bool valid;
+      int n, oy, ox;
+      if (p.k == 3) {
+        const int gg = g.g0 + i;
+        oy = gg / p.Wt;
+        const int xp = gg - oy * p.Wt;
+        ox = xp - 1;
+        n = g.img;
+        valid = (oy < p.H) && (xp >= 1) && (xp <= p.W);
+      } else {
+        const long long pix = g.pos0 + i;
+        valid = pix < (long long)p.B * p.H * p.W;
+        const long long pp = valid ? pix : 0;
+        ox = (int)(pp % p.W);
+        const long long t = pp / p.W;
+        oy = (int)(t % p.H);
+        n = (int)(t / p.H);
+      }
+      const int m = (int)(((size_t)n * p.H + oy) * p.W + ox);
+      const int col_end = min(p.Cout, (g.n_tile + 1) * p.BN);
+      if (X3) {
+        // two-level accumulation: the tensor core only ever sums `group` K blocks in TMEM (its accumulator truncates,
+        // error ~ chain length); every finished group is added into fp32 registers with round-to-nearest
+        float sums[X3 ? 128 : 1];
 #pragma unroll
-      for (int j = 0; j < (X3 ? 128 : 1); ++j) sums[j] = 0.f;
-      const int ngroups = (KB + p.group - 1) / p.group;
-      int buf = 0;
-      uint32_t pf[2] = {0u, 0u};
-      for (int g = 0; g < ngroups; ++g) {
-        mbar_wait(smem_u32(&ctl->p_full[buf]), pf[buf]);
-        tc_fence_after();
+        for (int j = 0; j < (X3 ? 128 : 1); ++j) sums[j] = 0.f;
+        const int ngroups = (KB + p.group - 1) / p.group;
+        for (int gi = 0; gi < ngroups; ++gi) {
+          mbar_wait(smem_u32(&ctl->p_full[buf]), pf[buf]);
+          tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          if (c * 16 < p.BN) {
-            uint32_t rr[16];
-            tmem_ld16(lane_base + (uint32_t)(buf * p.BN + c * 16), rr);
-            tmem_ld_wait();
+          for (int c = 0; c < 8; ++c) {
+            if (c * 16 < p.BN) {
+              uint32_t rr[16];
+              tmem_ld16(lane_base + (uint32_t)(buf * p.BN + c * 16), rr);
+              tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) sums[(X3 ? c * 16 + j : 0)] += __uint_as_float(rr[j]);
+              for (int j = 0; j < 16; ++j) sums[(X3 ? c * 16 + j : 0)] += __uint_as_float(rr[j]);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(smem_u32(&ctl->p_empty[buf]));
+          pf[buf] ^= 1u;
+          buf ^= 1;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c0 = cc * 32;
+          if (c0 < p.BN) {
+            float vv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) vv[j] = sums[(X3 ? cc * 32 + j : 0)];
+            epilogue_sub_tile(ep, stage, vv, lane, valid, m, n, oy, ox, g.n_tile * p.BN + c0, col_end);
           }
         }
-        tc_fence_before();
-        mbar_arrive(smem_u32(&ctl->p_empty[buf]));
+      } else {
+        mbar_wait(smem_u32(&ctl->p_full[buf]), pf[buf]);
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          uint32_t rr[32];
+          tmem_ld16(lane_base + (uint32_t)(buf * p.BN + c0), rr);
+          if (c0 + 16 < p.BN) {
+            tmem_ld16(lane_base + (uint32_t)(buf * p.BN + c0 + 16), rr + 16);
+          } else {
+#pragma unroll
+            for (int j = 16; j < 32; ++j) rr[j] = 0u;
+          }
+          tmem_ld_wait();
+          if (c0 + 32 >= p.BN) {          // last chunk read: hand the TMEM buffer back before the (slow) global stores
+            tc_fence_before();
+            mbar_arrive(smem_u32(&ctl->p_empty[buf]));
+          }
+          float vv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(rr[j]);
+          epilogue_sub_tile(ep, stage, vv, lane, valid, m, n, oy, ox, g.n_tile * p.BN + c0, col_end);
+        }
         pf[buf] ^= 1u;
         buf ^= 1;
       }
-    } else {
-      mbar_wait(smem_u32(&ctl->accum_full), 0u);
-      tc_fence_after();
-    }
-#pragma unroll
-    for (int cc = 0; cc < (X3 ? 4 : 8); ++cc) {
-      const int c0 = cc * 32;
-      if (c0 >= p.BN) break;
-      float vv[32];
-      if (X3) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) vv[j] = sums[(X3 ? cc * 32 + j : 0)];
-      } else {
-        uint32_t rr[32];
-        tmem_ld16(lane_base + (uint32_t)c0, rr);
-        if (c0 + 16 < p.BN) {
-          tmem_ld16(lane_base + (uint32_t)(c0 + 16), rr + 16);
-        } else {
-#pragma unroll
-          for (int j = 16; j < 32; ++j) rr[j] = 0u;
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(rr[j]);
-      }
-      epilogue_sub_tile(ep, stage, vv, lane, valid, m, n, oy, ox, n_tile * p.BN + c0, col_end);
     }
   }
 
@@ -607,7 +648,14 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
       CP_CUDA_CHECK(cudaFuncSetAttribute(conv_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured[x3 ? 1 : 0] = true;
   }
-  dim3 grid((unsigned)(m_tiles * (size_t)(p.CoutPad / q.BN)));
+  q.total_tiles = (long long)m_tiles * (p.CoutPad / q.BN);
+  static thread_local int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    CP_CUDA_CHECK(cudaGetDevice(&dev));
+    CP_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  dim3 grid((unsigned)(q.total_tiles < num_sms ? q.total_tiles : num_sms));
   if (x3)
     conv_tma_kernel<true><<<grid, TM_THREADS_X3, smem, stream>>>(q);
   else

@@ -320,6 +320,25 @@ def main():
                                                             o["bytes"] / 1e6, o["flops"] / max(o["ms"], 1e-6) / 1e9,
                                                             o["bytes"] / max(o["ms"], 1e-6) / 1e6))
 
+    # ---- stage breakdown of one resident step (CUDA events, mean of 5)
+    from centerpose_b200.engine import decode_pnp
+
+    def ev_time(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    heads_out = eng.forward(x_buf)
+    breakdown = {"preprocess": ev_time(lambda: preprocess(dev_frames[0], 512, 512, opt.mean, opt.std, out=x_buf)),
+                 "forward": ev_time(lambda: eng.forward(x_buf)),
+                 "decode_softnms_pnp": ev_time(lambda: decode_pnp(heads_out, meta, prm, want_dets=False))}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = usable_cores()
@@ -357,6 +376,7 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks.summary(),
             "roofline": roofline,
+            "stage_ms": breakdown,
             "cpu_baseline": cpu_baseline,
             "network_gflop_per_image": GFLOP_PER_IMAGE,
         }

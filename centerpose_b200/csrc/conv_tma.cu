@@ -18,6 +18,7 @@
 // Reference semantics: nn.Conv2d(k, stride 1, padding k//2) + folded BatchNorm + residual + ReLU
 // (pose_dla_dcn.py:37-62, 153-168, 496-505).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "umma_common.cuh"
@@ -28,7 +29,6 @@ namespace {
 constexpr int TM_BM = 128;
 constexpr int TM_THREADS = 256;
 constexpr int TM_GROUP_X3 = 3;
-constexpr uint32_t TM_ROW = 128;      // bytes per position row: 32 fp32 channels
 
 struct TmaConvParams {
   CUtensorMap amap[4];
@@ -38,7 +38,9 @@ struct TmaConvParams {
   int k;              // 1 or 3
   int Wt, boxh;       // padded pitch and slab rows (k == 3)
   int tiles_per_image;
-  long long total_tiles;                // m tiles x n tiles (n fastest)
+  long long total_tiles;                // cluster tiles: m groups x n tiles (n fastest)
+  long long m_tiles;                    // real number of 128-position tiles
+  int cluster;                          // CTAs per cluster (1, 2 or 4): same N tile, consecutive M tiles, weight tiles multicast
   uint32_t slab_bytes, slab_stride;   // TMA transaction bytes, 1024-aligned stage stride
   int SA, SB;
   const float* bias;
@@ -73,6 +75,33 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy global -> the SAME shared-memory offset of every CTA in `mask`, completing on each CTA's own mbarrier
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit that arrives on the same-offset mbarrier of every CTA in `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
 // K-major SWIZZLE_128B descriptor; `saddr` may be any multiple of 16 bytes.  Measured on B200
 // (scripts/tma_diag.py): the tensor core applies the 128-byte swizzle to the ABSOLUTE shared-memory address bits
 // [7,10), exactly like TMA does when it writes the slab, so a matrix that starts at an arbitrary 128-byte row of
@@ -106,10 +135,13 @@ struct TileGeo {
   int n_tile, img, g0, r_lo;
   long long pos0;
 };
-__device__ __forceinline__ TileGeo decode_tile(const TmaConvParams& p, long long tile, int n_tiles) {
+// cluster tile `ct` -> this CTA's (n tile, m tile); m tiles past the end are clamped (computed redundantly, never stored)
+__device__ __forceinline__ TileGeo decode_tile(const TmaConvParams& p, long long ct, int n_tiles, int rank, bool* live) {
   TileGeo g;
-  g.n_tile = (int)(tile % n_tiles);
-  const long long m_tile = tile / n_tiles;
+  g.n_tile = (int)(ct % n_tiles);
+  long long m_tile = (ct / n_tiles) * p.cluster + rank;
+  *live = m_tile < p.m_tiles;
+  if (!*live) m_tile = p.m_tiles - 1;
   g.img = 0;
   g.g0 = 0;
   g.r_lo = 0;
@@ -145,6 +177,10 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   const int nslab = p.Cin / p.cslab;
   const int KB = nslab * taps;
   const long long total_tiles = p.total_tiles;
+  const int rank = (p.cluster > 1) ? (int)cluster_ctarank() : 0;
+  const long long cluster_id = blockIdx.x / p.cluster;
+  const long long num_clusters = gridDim.x / p.cluster;
+  const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
 
   if (tid == 0) {
     for (int s = 0; s < p.SA; ++s) {
@@ -154,7 +190,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     }
     for (int s = 0; s < p.SB; ++s) {
       mbar_init(smem_u32(&ctl->b_full[s]), 1);
-      mbar_init(smem_u32(&ctl->b_empty[s]), 1);
+      mbar_init(smem_u32(&ctl->b_empty[s]), p.cluster);      // every CTA of the cluster releases every CTA's slot
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&ctl->p_full[s]), 1);       // x3: accumulation group ready / x1: tile accumulator ready
@@ -172,6 +208,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.cluster > 1) cluster_sync_all();       // remote arrives / multicast writes need every CTA's barriers initialised
   const uint32_t tmem_base = ctl->tmem_base;
 
   if (warp == 0) {
@@ -179,8 +216,9 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileGeo g = decode_tile(p, tile, n_tiles);
+      for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        bool live;
+        const TileGeo g = decode_tile(p, tile, n_tiles, rank, &live);
         for (int s = 0; s < nslab; ++s) {
           int src = 0, cb = 0;
           while (src + 1 < p.nsrc && s * p.cslab >= cb + p.srcC[src]) {
@@ -208,14 +246,20 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = (int)(tile % n_tiles);
+      for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int n_tile = (int)(tile % n_tiles);       // identical for all CTAs of the cluster
         const unsigned char* wsrc = p.wtiles + (size_t)n_tile * KB * btile_bytes;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(smem_u32(&ctl->b_empty[stage]), phase ^ 1u);
           const uint32_t bar = smem_u32(&ctl->b_full[stage]);
-          mbar_arrive_expect_tx(bar, btile_bytes);
-          bulk_g2s(btiles0 + (uint32_t)stage * btile_bytes, wsrc + (size_t)kb * btile_bytes, btile_bytes, bar);
+          mbar_arrive_expect_tx(bar, btile_bytes);            // the whole tile lands here: one slice from every CTA
+          if (p.cluster > 1) {
+            const uint32_t slice = btile_bytes / (uint32_t)p.cluster;
+            bulk_g2s_multicast(btiles0 + (uint32_t)stage * btile_bytes + (uint32_t)rank * slice,
+                               wsrc + (size_t)kb * btile_bytes + (size_t)rank * slice, slice, bar, cmask);
+          } else {
+            bulk_g2s(btiles0 + (uint32_t)stage * btile_bytes, wsrc + (size_t)kb * btile_bytes, btile_bytes, bar);
+          }
           if (++stage == p.SB) {
             stage = 0;
             phase ^= 1u;
@@ -226,75 +270,89 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     __syncwarp();
   } else if (warp == 2) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(p.BN);
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      int buf = 0;
-      uint32_t pe[2] = {0u, 0u};         // phases of p_empty
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileGeo g = decode_tile(p, tile, n_tiles);
-        int kbi = 0;                     // K-block index inside the tile (slab-major, tap-minor)
-        for (int s = 0; s < nslab; ++s) {
-          mbar_wait(smem_u32(X3 ? &ctl->a_split[sa] : &ctl->a_full[sa]), pa);
-          tc_fence_after();
-          const uint32_t slab = slabs0 + (uint32_t)sa * a_stage;
-          for (int t = 0; t < taps; ++t, ++kbi) {
-            const bool first = X3 ? (kbi % p.group == 0) : (kbi == 0);
+    // The issue loop of this ONE warp bounds the kernel once the operand pipelines are deep enough (ncu stall sampling:
+    // the warp was busy executing descriptor arithmetic, not waiting).  So: the whole warp walks the warp-uniform loop
+    // (descriptors and barrier addresses stay in uniform registers), one elected lane issues, and a descriptor is a
+    // constant template plus (shared byte address >> 4) - stepping through taps and K slices is one add on the low word
+    // (the 14-bit address field cannot carry: shared addresses stay below 256 KB).
+    const uint32_t idesc = make_idesc_tf32(p.BN);
+    const uint64_t dtmpl = make_desc(0, 0, p.cslab);
+    const uint32_t rowu = rowb >> 4;                              // row pitch in descriptor units
+    const uint32_t a_lo_u = p.slab_stride >> 4;                   // x3: lo slab behind the hi slab
+    const uint32_t b_lo_u = ((uint32_t)p.BN * rowb) >> 4;         // x3: lo tile behind the hi tile
+    const int group = p.group;
+    int sa = 0, sb = 0, buf = 0;
+    uint32_t pa = 0, pb = 0, pe = 0;                              // pe bit b: phase of p_empty[b]
+    for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      bool live;
+      const TileGeo g = decode_tile(p, tile, n_tiles, rank, &live);
+      const uint32_t tap0 = (p.k == 3) ? (uint32_t)(g.g0 - 1 - g.r_lo * p.Wt) * rowu : 0u;
+      int kbi = 0, gk = 0;               // K-block index inside the tile (slab-major, tap-minor) / inside its group
+      for (int s = 0; s < nslab; ++s) {
+        mbar_wait(smem_u32(X3 ? &ctl->a_split[sa] : &ctl->a_full[sa]), pa);
+        tc_fence_after();
+        const uint64_t a_slab = dtmpl + (uint64_t)(((slabs0 + (uint32_t)sa * a_stage) >> 4) + tap0);
+        for (int ky = 0; ky < p.k; ++ky) {
+          for (int kx = 0; kx < p.k; ++kx, ++kbi) {
+            const bool first = X3 ? (gk == 0) : (kbi == 0);
             if (first) {                 // new accumulation group / tile: the epilogue must have drained this TMEM buffer
-              mbar_wait(smem_u32(&ctl->p_empty[buf]), pe[buf] ^ 1u);
-              tc_fence_after();
+              mbar_wait(smem_u32(&ctl->p_empty[buf]), ((pe >> buf) & 1u) ^ 1u);
             }
             mbar_wait(smem_u32(&ctl->b_full[sb]), pb);
             tc_fence_after();
-            uint32_t a_addr = slab;
-            if (p.k == 3) {
-              const int ky = t / 3, kx = t - ky * 3;
-              a_addr += (uint32_t)(g.g0 + ky * p.Wt + kx - 1 - g.r_lo * p.Wt) * rowb;
-            }
-            const uint32_t b_addr = btiles0 + (uint32_t)sb * btile_bytes;
+            const uint64_t da = a_slab + (uint64_t)((uint32_t)(ky * p.Wt + kx) * rowu);
+            const uint64_t db = dtmpl + (uint64_t)((btiles0 + (uint32_t)sb * btile_bytes) >> 4);
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
-            for (int ks = 0; ks < kslices; ++ks) {
-              const uint64_t da = make_desc(a_addr + ks * 32, p.use_base_offset, p.cslab);
-              const uint64_t db = make_desc(b_addr + ks * 32, 0, p.cslab);
-              if (X3) {
-                const uint64_t da_lo = make_desc(a_addr + p.slab_stride + ks * 32, p.use_base_offset, p.cslab);
-                const uint64_t db_lo = make_desc(b_addr + (uint32_t)p.BN * rowb + ks * 32, 0, p.cslab);
-                umma_tf32(d_tmem, da_lo, db, idesc, (first && ks == 0) ? 0u : 1u);
-                umma_tf32(d_tmem, da, db_lo, idesc, 1u);
-                umma_tf32(d_tmem, da, db, idesc, 1u);
-              } else {
-                umma_tf32(d_tmem, da, db, idesc, (first && ks == 0) ? 0u : 1u);
+            const bool last = X3 ? (gk == group - 1 || kbi == KB - 1) : (kbi == KB - 1);
+            const bool slab_done = (ky == p.k - 1) && (kx == p.k - 1);
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                if (ks < kslices) {
+                  const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+                  if (X3) {
+                    umma_tf32(d_tmem, da + a_lo_u + 2 * ks, db + 2 * ks, idesc, acc);
+                    umma_tf32(d_tmem, da + 2 * ks, db + b_lo_u + 2 * ks, idesc, 1u);
+                    umma_tf32(d_tmem, da + 2 * ks, db + 2 * ks, idesc, 1u);
+                  } else {
+                    umma_tf32(d_tmem, da + 2 * ks, db + 2 * ks, idesc, acc);
+                  }
+                }
               }
+              if (p.cluster > 1)
+                umma_commit_multicast(smem_u32(&ctl->b_empty[sb]), cmask);
+              else
+                umma_commit(smem_u32(&ctl->b_empty[sb]));
+              if (last) umma_commit(smem_u32(&ctl->p_full[buf]));        // group / tile finished -> epilogue
+              if (slab_done) umma_commit(smem_u32(&ctl->a_empty[sa]));
             }
-            umma_commit(smem_u32(&ctl->b_empty[sb]));
+            __syncwarp();
             if (++sb == p.SB) {
               sb = 0;
               pb ^= 1u;
             }
-            const bool last = X3 ? ((kbi % p.group == p.group - 1) || kbi == KB - 1) : (kbi == KB - 1);
             if (last) {
-              umma_commit(smem_u32(&ctl->p_full[buf]));     // group / tile finished -> epilogue
-              pe[buf] ^= 1u;
+              pe ^= 1u << buf;
               buf ^= 1;
+              gk = 0;
+            } else {
+              ++gk;
             }
           }
-          umma_commit(smem_u32(&ctl->a_empty[sa]));
-          if (++sa == p.SA) {
-            sa = 0;
-            pa ^= 1u;
-          }
+        }
+        if (++sa == p.SA) {
+          sa = 0;
+          pa ^= 1u;
         }
       }
     }
-    __syncwarp();
   } else if (X3 && warp >= 8) {
     // ===================== hi / lo splitters (x3): slab -> tf32-exact hi (in place) + lo slab =====================
     const int st = tid - 256;
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t nchunk = p.slab_bytes >> 4;
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       for (int s = 0; s < nslab; ++s) {
         mbar_wait(smem_u32(&ctl->a_full[stage]), phase);
         const uint32_t hi = slabs0 + (uint32_t)stage * a_stage;
@@ -346,9 +404,10 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     ep.H = p.H;
     ep.W = p.W;
     int buf = 0;
-    uint32_t pf[2] = {0u, 0u};
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileGeo g = decode_tile(p, tile, n_tiles);
+    uint32_t pf = 0;                     // bit b: phase of p_full[b]
+    for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      bool live;
+        const TileGeo g = decode_tile(p, tile, n_tiles, rank, &live);
       bool valid;
       int n, oy, ox;
       if (p.k == 3) {
@@ -357,10 +416,10 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
         const int xp = gg - oy * p.Wt;
         ox = xp - 1;
         n = g.img;
-        valid = (oy < p.H) && (xp >= 1) && (xp <= p.W);
+        valid = live && (oy < p.H) && (xp >= 1) && (xp <= p.W);
       } else {
         const long long pix = g.pos0 + i;
-        valid = pix < (long long)p.B * p.H * p.W;
+        valid = live && pix < (long long)p.B * p.H * p.W;
         const long long pp = valid ? pix : 0;
         ox = (int)(pp % p.W);
         const long long t = pp / p.W;
@@ -377,7 +436,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
         for (int j = 0; j < (X3 ? 128 : 1); ++j) sums[j] = 0.f;
         const int ngroups = (KB + p.group - 1) / p.group;
         for (int gi = 0; gi < ngroups; ++gi) {
-          mbar_wait(smem_u32(&ctl->p_full[buf]), pf[buf]);
+          mbar_wait(smem_u32(&ctl->p_full[buf]), (pf >> buf) & 1u);
           tc_fence_after();
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -391,7 +450,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
           }
           tc_fence_before();
           mbar_arrive(smem_u32(&ctl->p_empty[buf]));
-          pf[buf] ^= 1u;
+          pf ^= 1u << buf;
           buf ^= 1;
         }
 #pragma unroll
@@ -405,7 +464,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
           }
         }
       } else {
-        mbar_wait(smem_u32(&ctl->p_full[buf]), pf[buf]);
+        mbar_wait(smem_u32(&ctl->p_full[buf]), (pf >> buf) & 1u);
         tc_fence_after();
         for (int c0 = 0; c0 < p.BN; c0 += 32) {
           uint32_t rr[32];
@@ -426,7 +485,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
           for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(rr[j]);
           epilogue_sub_tile(ep, stage, vv, lane, valid, m, n, oy, ox, g.n_tile * p.BN + c0, col_end);
         }
-        pf[buf] ^= 1u;
+        pf ^= 1u << buf;
         buf ^= 1;
       }
     }
@@ -434,6 +493,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
 
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();       // nobody leaves while a peer may still multicast into / arrive on its smem
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
 }
 
@@ -648,18 +708,38 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
       CP_CUDA_CHECK(cudaFuncSetAttribute(conv_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured[x3 ? 1 : 0] = true;
   }
-  q.total_tiles = (long long)m_tiles * (p.CoutPad / q.BN);
+  q.m_tiles = (long long)m_tiles;
+  int cluster = 1;     // measured: multicast at cluster sizes 2/4 does not cut L2 traffic on this part and couples the CTAs
+  if (const char* e = getenv("CP_TMA_CLUSTER")) cluster = atoi(e);
+  if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 1;
+  while (cluster > 1 && ((long long)m_tiles < cluster || (btile / cluster) % 16)) cluster >>= 1;
+  q.cluster = cluster;
+  const long long m_groups = ((long long)m_tiles + cluster - 1) / cluster;
+  q.total_tiles = m_groups * (p.CoutPad / q.BN);
   static thread_local int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     CP_CUDA_CHECK(cudaGetDevice(&dev));
     CP_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  dim3 grid((unsigned)(q.total_tiles < num_sms ? q.total_tiles : num_sms));
+  long long nclusters = num_sms / cluster;
+  if (q.total_tiles < nclusters) nclusters = q.total_tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(nclusters * cluster));
+  cfg.blockDim = dim3(x3 ? TM_THREADS_X3 : TM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (x3)
-    conv_tma_kernel<true><<<grid, TM_THREADS_X3, smem, stream>>>(q);
+    CP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tma_kernel<true>, q));
   else
-    conv_tma_kernel<false><<<grid, TM_THREADS, smem, stream>>>(q);
+    CP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tma_kernel<false>, q));
   CP_LAUNCH_CHECK("conv_tma_kernel");
   return CP_OK;
 }

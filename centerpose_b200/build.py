@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcenterpose_b200.so")
-SOURCES = ["plan.cu", "igemm_fp32.cu", "elementwise.cu", "decode.cu", "ext_ops.cu", "igemm_umma.cu", "stem_conv.cu", "conv_tma.cu"]
+SOURCES = ["plan.cu", "igemm_fp32.cu", "elementwise.cu", "decode.cu", "ext_ops.cu", "igemm_umma.cu", "stem_conv.cu", "conv_tma.cu", "dcn_tma.cu"]
 HEADERS = ["common.cuh", "pose_core.h", os.path.join("..", "..", "include", "centerpose_b200.h")]
 
 NVCC_FLAGS = [

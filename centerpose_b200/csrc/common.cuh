@@ -104,7 +104,16 @@ bool tma_conv_supported(const IgemmParams& p, int x3);
 size_t tma_weight_bytes(int Cin, int taps, int CoutPad, int x3);
 int tma_cslab(const IgemmParams& p, int x3);     // channels per activation slab (32 or 16); needs Cin, kh, Win, CoutPad
 int launch_pack_tma_weight(const float* src_k_by_ld, int ld, int Cin, int taps, int Cout, int CoutPad, int round_tf32,
-                           int x3, int cslab, void* dst, cudaStream_t s);
+                           int x3, int cslab, void* dst, cudaStream_t s, int bn_override = 0);
+int tma_encode_nhwc_box(const float* base, int C, int W, int H, int B, int strideFloats, int boxC, int boxW, int boxH,
+                        int swizzle64, void* map_out /* 128 bytes, 64-byte aligned */);
+
+// TMA-staged deformable convolution (dcn_tma.cu): DCNv2 3x3 stride 1 pad 1 over one NHWC fp32 source, kind::tf32.
+// x3 = 1: 3-term split + promoted accumulation (fp32-equivalent);  x3 = 0: single pass.
+bool dcn_tma_supported(const IgemmParams& p, int x3);
+int dcn_tma_tile_n(int CoutPad, int x3);
+int dcn_tma_encode(const IgemmParams& p, int Bmax, void* map_out /* 128 bytes, 64-byte aligned */);
+int launch_dcn_tma(const IgemmParams& p, const void* map, int x3, int round_out_tf32, cudaStream_t stream);
 int tma_conv_encode(const IgemmParams& p, int Bmax, int x3, void* maps_out /* 4 x 128 bytes */);
 int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, int use_base_offset, int x3,
                     cudaStream_t stream);

@@ -58,68 +58,6 @@ struct TmaConvParams {
 
 using namespace umma;
 
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-               "l"(map), "r"(c0), "r"(c1), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// bulk copy global -> the SAME shared-memory offset of every CTA in `mask`, completing on each CTA's own mbarrier
-__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
-      : "memory");
-}
-// tcgen05.commit that arrives on the same-offset mbarrier of every CTA in `mask`
-__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(mask)
-               : "memory");
-}
-
-// K-major SWIZZLE_128B descriptor; `saddr` may be any multiple of 16 bytes.  Measured on B200
-// (scripts/tma_diag.py): the tensor core applies the 128-byte swizzle to the ABSOLUTE shared-memory address bits
-// [7,10), exactly like TMA does when it writes the slab, so a matrix that starts at an arbitrary 128-byte row of
-// the slab needs NO base-offset correction (setting the field to (addr >> 7) & 7 gives wrong results).
-// `use_base_offset` is kept only as a debug switch (CP_TMA_BASE_OFFSET=1).
-// cslab = 32: 128-byte rows, SWIZZLE_128B (layout type 2), 8-row groups 1024 bytes apart;
-// cslab = 16:  64-byte rows, SWIZZLE_64B  (layout type 4), 8-row groups  512 bytes apart.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int use_base_offset, int cslab) {
-  const uint64_t sbo = cslab == 32 ? (1024 >> 4) : (512 >> 4);
-  const uint64_t lay = cslab == 32 ? 2ull : 4ull;
-  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (lay << 61);
-  if (use_base_offset) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
-  return d;
-}
-__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM_BM >> 4) << 24);
-}
-
 struct TmaCtl {
   unsigned long long a_full[4], a_empty[4], a_split[4];
   unsigned long long b_full[8], b_empty[8];
@@ -594,8 +532,8 @@ size_t tma_weight_bytes(int Cin, int taps, int CoutPad, int x3) {
 }
 
 int launch_pack_tma_weight(const float* src, int ld, int Cin, int taps, int Cout, int CoutPad, int round_tf32, int x3,
-                           int cs, void* dst, cudaStream_t s) {
-  const int bn = tma_tile_n(CoutPad, x3);
+                           int cs, void* dst, cudaStream_t s, int bn_override) {
+  const int bn = bn_override > 0 ? bn_override : tma_tile_n(CoutPad, x3);
   if (x3) round_tf32 = 1;
   const int nt = CoutPad / bn;
   size_t total = (size_t)nt * (Cin / cs) * taps * bn * (cs / 4);
@@ -603,6 +541,23 @@ int launch_pack_tma_weight(const float* src, int ld, int Cin, int taps, int Cout
   if (blocks > 148 * 32) blocks = 148 * 32;
   pack_tma_weight_kernel<<<blocks, 256, 0, s>>>(src, ld, Cin, taps, Cout, bn, nt, round_tf32, x3, cs, (unsigned char*)dst);
   CP_LAUNCH_CHECK("pack_tma_weight_kernel");
+  return CP_OK;
+}
+
+// One 4-D fp32 NHWC tensor map {C, W, H, B} with box {boxC, boxW, boxH, 1}, un-swizzled or SWIZZLE_64B (dcn_tma.cu slabs).
+int tma_encode_nhwc_box(const float* base, int C, int W, int H, int B, int strideFloats, int boxC, int boxW, int boxH,
+                        int swizzle64, void* map_out) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(CP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)strideFloats * 4, (cuuint64_t)W * strideFloats * 4, (cuuint64_t)H * W * strideFloats * 4};
+  cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)boxW, (cuuint32_t)boxH, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box,
+                   es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CP_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return CP_OK;
 }
 

@@ -1,0 +1,602 @@
+// TMA-staged DCNv2 (modulated deformable 3x3 convolution, stride 1, pad 1, dilation 1, one deformable group)
+// on tcgen05, kind::tf32.  Reference semantics: dcn_v2_im2col_cuda.cu:125-195 (bilinear sampling with per-corner
+// bounds, modulation mask) followed by the GEMM of dcn_v2_cuda.cu:105-160, + folded BatchNorm + ReLU
+// (pose_dla_dcn.py:363-379 DeformConv).
+//
+// Why a second deformable kernel: the gather kernel (igemm_umma.cu) fetches the four bilinear corners of every
+// (position, tap, channel chunk) from global memory; each input pixel is re-fetched ~36 times through L1/L2 and the
+// producers sit on load latency (measured 1.08 ms for 64->64 @128x128, B=32: 16 B/clk/SM of L1 traffic).  Learned
+// offsets are small, so here the rows a tile can reach are STAGED ONCE in shared memory by TMA and the corners are
+// gathered from shared memory:
+//
+//   tile    = 128 consecutive output positions = R = 128 / W full rows of one image (W in {16, 32, 64, 128})
+//   slab    = 16 channels x W columns x (R + 6) rows  [rows y0-3 .. y0+R+2, zero-filled outside the image],
+//             64 bytes per position in TMA SWIZZLE_64B order (conflict-free 16-byte gathers); double buffered
+//   K order = slab-major, tap-minor (the weight tiles of conv_tma.cu with 16-channel slabs are reused unchanged)
+//   samples whose corner rows fall outside the slab (|dy| > ~2) are fetched from global memory instead - slow path,
+//   same arithmetic, so the result never depends on how large the offsets are.
+//
+//   warp 0      : TMA producer for slabs
+//   warp 1      : weight-tile producer (cp.async.bulk, pre-swizzled tiles)
+//   warp 2      : tcgen05.mma issuer + TMEM owner
+//   warp 3      : idle
+//   warps 4-7   : epilogue (TMEM lane == position); x3: promotes every accumulation group into fp32 registers.
+//                 Thread i also writes the sampling records (one 16-byte record per tap) of position i of the NEXT tile
+//   warps 8-15  : gather, one thread per position: 4 corners x 16 channels from the slab -> bilinear blend * mask ->
+//                 (hi, lo) tf32 split -> A tile in the UMMA SWIZZLE_64B K-major layout; warps 8-11 / 12-15 take
+//                 alternate K blocks and own one A stage each
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "umma_common.cuh"
+
+namespace cp {
+namespace {
+
+using namespace umma;
+
+constexpr int DT_BM = 128;
+constexpr int DT_THREADS = 512;
+constexpr int DT_CS = 16;            // channels per slab = one UMMA K block of 64-byte rows
+constexpr int DT_HALO = 3;           // slab rows above / below the tile
+constexpr int DT_GROUP = 6;          // x3: K blocks per TMEM accumulation group (= 36 MMAs, as in conv_tma.cu)
+constexpr uint32_t DT_COEF_BYTES = DT_BM * 9 * 16;
+
+struct DcnTmaParams {
+  CUtensorMap amap;
+  const float* src;
+  int srcStride;
+  const float* offmask;
+  int omStride, mask_is_logit;
+  int B, H, W, Cin, Cout, CoutPad, BN;
+  int R, SR, logW;                   // image rows per tile, slab rows, log2(W)
+  int tiles_per_image;
+  long long total_tiles;             // m tiles x n tiles (n fastest)
+  uint32_t slab_bytes, slab_stride;
+  int SB;
+  const float* bias;
+  const float* residual;
+  int resStride, relu, res_after_relu;
+  float* out;
+  int outStride, out_nchw, round_tf32;
+  int debug_drop_far;                // CP_DCN_DROP_FAR=1 (timing experiments only): samples outside the slab contribute zero
+  const unsigned char* wtiles;
+};
+
+struct DcnCtl {
+  unsigned long long s_full[2], s_empty[2];
+  unsigned long long a_full[2], a_empty[2];
+  unsigned long long c_full[2], c_empty[2];
+  unsigned long long b_full[8], b_empty[8];
+  unsigned long long p_full[2], p_empty[2];
+  uint32_t tmem_base;
+};
+
+// record bits: [0,14) slab position of the clamped top-left corner (in-slab) or (row << 7 | col) in the image
+// (global path);  14: right corner is +1 column;  15: bottom corner is +1 row;  16-19: corner weights alive;
+// 20: all corners inside the slab;  21: sample inside the image
+constexpr int RB_DX = 14, RB_DY = 15, RB_W = 16, RB_SLAB = 20, RB_LIVE = 21;
+
+// Sampling records of one output position (all 9 taps) -> shared memory.  dcn_v2_im2col_cuda.cu:160-195: the sample
+// (h_im, w_im) is used only when it lies in (-1, H) x (-1, W); every corner carries its own bounds test.
+__device__ __forceinline__ void coef_row(const DcnTmaParams& p, const float* __restrict__ om, int oy, int ox, int ys,
+                                         uint32_t dst) {
+  float o[27];
+#pragma unroll
+  for (int j = 0; j < 27; ++j) o[j] = __ldg(om + j);
+  const int H = p.H, W = p.W;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ky = tap / 3, kx = tap - ky * 3;
+    float mm = o[18 + tap];
+    if (p.mask_is_logit) mm = 1.0f / (1.0f + expf(-mm));
+    const float h_im = (float)(oy - 1 + ky) + o[2 * tap], w_im = (float)(ox - 1 + kx) + o[2 * tap + 1];
+    float lh = 0.f, lw = 0.f, mk = 0.f;
+    uint32_t pk = 0;
+    if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
+      const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+      lh = h_im - (float)h_low;
+      lw = w_im - (float)w_low;
+      const bool t_ok = h_low >= 0, b_ok = h_low + 1 <= H - 1, l_ok = w_low >= 0, r_ok = w_low + 1 <= W - 1;
+      const int hl = t_ok ? h_low : 0, hb = b_ok ? h_low + 1 : H - 1;
+      const int wl = l_ok ? w_low : 0, wr = r_ok ? w_low + 1 : W - 1;
+      const bool in_slab = (hl >= ys) && (hb < ys + p.SR);
+      pk = in_slab ? (uint32_t)((hl - ys) * W + wl) : (uint32_t)((hl << 7) | wl);
+      pk |= (uint32_t)(wr - wl) << RB_DX;
+      pk |= (uint32_t)(hb - hl) << RB_DY;
+      pk |= (uint32_t)((t_ok && l_ok) ? 1 : 0) << (RB_W + 0);
+      pk |= (uint32_t)((t_ok && r_ok) ? 1 : 0) << (RB_W + 1);
+      pk |= (uint32_t)((b_ok && l_ok) ? 1 : 0) << (RB_W + 2);
+      pk |= (uint32_t)((b_ok && r_ok) ? 1 : 0) << (RB_W + 3);
+      pk |= (uint32_t)(in_slab ? 1 : 0) << RB_SLAB;
+      pk |= 1u << RB_LIVE;
+      mk = mm;
+      if (p.debug_drop_far && !in_slab) pk = 0;
+    }
+    st_shared_v4(dst + (uint32_t)tap * 16u, __float_as_uint(lh), __float_as_uint(lw), __float_as_uint(mk), pk);
+  }
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_constant__ DcnTmaParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  DcnCtl* ctl = reinterpret_cast<DcnCtl*>(smem);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t coef0 = sbase + 1024u;
+  const uint32_t slabs0 = (coef0 + 2u * DT_COEF_BYTES + 1023u) & ~1023u;
+  const uint32_t a_stage = X3 ? 16384u : 8192u;                // hi (+ lo) tile of 128 rows x 64 bytes
+  const uint32_t atiles0 = slabs0 + 2u * p.slab_stride;
+  const uint32_t btile_bytes = (uint32_t)p.BN * 64u * (X3 ? 2u : 1u);
+  const uint32_t btiles0 = atiles0 + 2u * a_stage;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = p.CoutPad / p.BN;
+  const int nslab = p.Cin / DT_CS;
+  const int KB = nslab * 9;
+  const long long total_tiles = p.total_tiles;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&ctl->s_full[s]), 1);
+      mbar_init(smem_u32(&ctl->s_empty[s]), 8);      // one arrival per gather warp
+      mbar_init(smem_u32(&ctl->a_full[s]), 4);       // stage s is written by gather warps 8+4s .. 11+4s
+      mbar_init(smem_u32(&ctl->a_empty[s]), 1);
+      mbar_init(smem_u32(&ctl->c_full[s]), 4);       // one arrival per epilogue warp
+      mbar_init(smem_u32(&ctl->c_empty[s]), 8);
+      mbar_init(smem_u32(&ctl->p_full[s]), 1);
+      mbar_init(smem_u32(&ctl->p_empty[s]), 128);
+    }
+    for (int s = 0; s < p.SB; ++s) {
+      mbar_init(smem_u32(&ctl->b_full[s]), 1);
+      mbar_init(smem_u32(&ctl->b_empty[s]), 1);
+    }
+    fence_mbar_init();
+  }
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.BN * 2) tmem_cols <<= 1;
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ===================== slabs via TMA =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const long long m_tile = tile / n_tiles;
+        const int img = (int)(m_tile / p.tiles_per_image);
+        const int y0 = (int)(m_tile - (long long)img * p.tiles_per_image) * p.R;
+        for (int s = 0; s < nslab; ++s) {
+          mbar_wait(smem_u32(&ctl->s_empty[stage]), phase ^ 1u);
+          const uint32_t bar = smem_u32(&ctl->s_full[stage]);
+          mbar_arrive_expect_tx(bar, p.slab_bytes);
+          tma_load_4d(slabs0 + (uint32_t)stage * p.slab_stride, &p.amap, s * DT_CS, 0, y0 - DT_HALO, img, bar);
+          if (++stage == 2) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== weight tiles =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = (int)(tile % n_tiles);
+        const unsigned char* wsrc = p.wtiles + (size_t)n_tile * KB * btile_bytes;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(smem_u32(&ctl->b_empty[stage]), phase ^ 1u);
+          const uint32_t bar = smem_u32(&ctl->b_full[stage]);
+          mbar_arrive_expect_tx(bar, btile_bytes);
+          bulk_g2s(btiles0 + (uint32_t)stage * btile_bytes, wsrc + (size_t)kb * btile_bytes, btile_bytes, bar);
+          if (++stage == p.SB) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    const uint32_t idesc = make_idesc_tf32(p.BN);
+    const uint64_t dtmpl = make_desc(0, 0, DT_CS);
+    const uint32_t a_lo_u = 8192u >> 4;
+    const uint32_t b_lo_u = ((uint32_t)p.BN * 64u) >> 4;
+    int sa = 0, sb = 0, buf = 0;
+    uint32_t pa = 0, pb = 0, pe = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int gk = 0;
+      for (int kbi = 0; kbi < KB; ++kbi) {
+        const bool first = X3 ? (gk == 0) : (kbi == 0);
+        if (first) mbar_wait(smem_u32(&ctl->p_empty[buf]), ((pe >> buf) & 1u) ^ 1u);
+        mbar_wait(smem_u32(&ctl->a_full[sa]), pa);
+        mbar_wait(smem_u32(&ctl->b_full[sb]), pb);
+        tc_fence_after();
+        const uint64_t da = dtmpl + (uint64_t)((atiles0 + (uint32_t)sa * a_stage) >> 4);
+        const uint64_t db = dtmpl + (uint64_t)((btiles0 + (uint32_t)sb * btile_bytes) >> 4);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
+        const bool last = X3 ? (gk == DT_GROUP - 1 || kbi == KB - 1) : (kbi == KB - 1);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+            if (X3) {
+              umma_tf32(d_tmem, da + a_lo_u + 2 * ks, db + 2 * ks, idesc, acc);
+              umma_tf32(d_tmem, da + 2 * ks, db + b_lo_u + 2 * ks, idesc, 1u);
+              umma_tf32(d_tmem, da + 2 * ks, db + 2 * ks, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, da + 2 * ks, db + 2 * ks, idesc, acc);
+            }
+          }
+          umma_commit(smem_u32(&ctl->b_empty[sb]));
+          umma_commit(smem_u32(&ctl->a_empty[sa]));
+          if (last) umma_commit(smem_u32(&ctl->p_full[buf]));
+        }
+        __syncwarp();
+        if (++sb == p.SB) {
+          sb = 0;
+          pb ^= 1u;
+        }
+        if (++sa == 2) {
+          sa = 0;
+          pa ^= 1u;
+        }
+        if (last) {
+          pe ^= 1u << buf;
+          buf ^= 1;
+          gk = 0;
+        } else {
+          ++gk;
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // idle
+  } else if (warp >= 8) {
+    // ===================== gather: thread = one position of the tile; the two halves of the 8 warps take alternate K
+    // blocks (kb = half, half + 2, ...) and each half owns one A stage, so the record of a (position, tap) is decoded
+    // once for all 16 channels and a stage is synchronised once per 128-thread task =====================
+    const int gt = tid - 256;
+    const int half = gt >> 7;
+    const int row = gt & 127;
+    const uint32_t a_hi = atiles0 + (uint32_t)half * a_stage + (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 64u;
+    const uint32_t asw = (uint32_t)(row >> 1) & 3u;
+    const uint32_t a_full_bar = smem_u32(&ctl->a_full[half]), a_empty_bar = smem_u32(&ctl->a_empty[half]);
+    int ss = 0, cb = 0;
+    uint32_t ps = 0, pa = 0, pc = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const long long m_tile = tile / n_tiles;
+      const int img = (int)(m_tile / p.tiles_per_image);
+      mbar_wait(smem_u32(&ctl->c_full[cb]), pc);
+      const uint32_t crow = coef0 + (uint32_t)cb * DT_COEF_BYTES + (uint32_t)row * 144u;
+      const float* gimg = p.src + (size_t)img * p.H * p.W * p.srcStride;
+      int cur = -1;
+      uint32_t slab = 0;
+      for (int kb = half; kb < KB; kb += 2) {
+        const int s = kb / 9, t = kb - s * 9;
+        if (s != cur) {
+          if (cur >= 0) {                     // done with the previous slab
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&ctl->s_empty[ss]));
+            if (++ss == 2) {
+              ss = 0;
+              ps ^= 1u;
+            }
+          }
+          mbar_wait(smem_u32(&ctl->s_full[ss]), ps);
+          slab = slabs0 + (uint32_t)ss * p.slab_stride;
+          cur = s;
+        }
+        const float4 rec = ld_shared_v4f(crow + (uint32_t)t * 16u);
+        const uint32_t pk = __float_as_uint(rec.w);
+        float4 v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((pk >> RB_LIVE) & 1u) {
+          const float lh = rec.x, lw = rec.y, mk = rec.z;
+          const float hh = 1.f - lh, hw = 1.f - lw;
+          const float w1 = ((pk >> (RB_W + 0)) & 1u) ? hh * hw : 0.f;
+          const float w2 = ((pk >> (RB_W + 1)) & 1u) ? hh * lw : 0.f;
+          const float w3 = ((pk >> (RB_W + 2)) & 1u) ? lh * hw : 0.f;
+          const float w4 = ((pk >> (RB_W + 3)) & 1u) ? lh * lw : 0.f;
+          if ((pk >> RB_SLAB) & 1u) {
+            // slab rows are 64 bytes in TMA SWIZZLE_64B order: 16-byte chunk c of position q sits at c ^ ((q >> 1) & 3)
+            const uint32_t q1 = pk & 0x3FFFu, q2 = q1 + ((pk >> RB_DX) & 1u);
+            const uint32_t q3 = q1 + ((pk >> RB_DY) & 1u) * (uint32_t)p.W, q4 = q3 + ((pk >> RB_DX) & 1u);
+            const uint32_t b1 = slab + q1 * 64u, b2 = slab + q2 * 64u, b3 = slab + q3 * 64u, b4 = slab + q4 * 64u;
+            const uint32_t s1 = (q1 >> 1) & 3u, s2 = (q2 >> 1) & 3u, s3 = (q3 >> 1) & 3u, s4 = (q4 >> 1) & 3u;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 c1 = ld_shared_v4f(b1 + (((uint32_t)c ^ s1) << 4));
+              const float4 c2 = ld_shared_v4f(b2 + (((uint32_t)c ^ s2) << 4));
+              const float4 c3 = ld_shared_v4f(b3 + (((uint32_t)c ^ s3) << 4));
+              const float4 c4 = ld_shared_v4f(b4 + (((uint32_t)c ^ s4) << 4));
+              v[c].x = (w1 * c1.x + w2 * c2.x + w3 * c3.x + w4 * c4.x) * mk;
+              v[c].y = (w1 * c1.y + w2 * c2.y + w3 * c3.y + w4 * c4.y) * mk;
+              v[c].z = (w1 * c1.z + w2 * c2.z + w3 * c3.z + w4 * c4.z) * mk;
+              v[c].w = (w1 * c1.w + w2 * c2.w + w3 * c3.w + w4 * c4.w) * mk;
+            }
+          } else {      // corner rows outside the staged slab: same arithmetic from global memory
+            const int hl = (int)((pk >> 7) & 127u), wl = (int)(pk & 127u);
+            const float* g = gimg + ((size_t)hl * p.W + wl) * p.srcStride + s * DT_CS;
+            const size_t dx = (size_t)((pk >> RB_DX) & 1u) * p.srcStride;
+            const size_t dy = (size_t)((pk >> RB_DY) & 1u) * p.W * p.srcStride;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 c1 = __ldg(reinterpret_cast<const float4*>(g) + c);
+              const float4 c2 = __ldg(reinterpret_cast<const float4*>(g + dx) + c);
+              const float4 c3 = __ldg(reinterpret_cast<const float4*>(g + dy) + c);
+              const float4 c4 = __ldg(reinterpret_cast<const float4*>(g + dy + dx) + c);
+              v[c].x = (w1 * c1.x + w2 * c2.x + w3 * c3.x + w4 * c4.x) * mk;
+              v[c].y = (w1 * c1.y + w2 * c2.y + w3 * c3.y + w4 * c4.y) * mk;
+              v[c].z = (w1 * c1.z + w2 * c2.z + w3 * c3.z + w4 * c4.z) * mk;
+              v[c].w = (w1 * c1.w + w2 * c2.w + w3 * c3.w + w4 * c4.w) * mk;
+            }
+          }
+        }
+        mbar_wait(a_empty_bar, pa ^ 1u);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t off = ((uint32_t)c ^ asw) << 4;
+          float4 h;
+          h.x = tf32_round(v[c].x);
+          h.y = tf32_round(v[c].y);
+          h.z = tf32_round(v[c].z);
+          h.w = tf32_round(v[c].w);
+          st_shared_v4f(a_hi + off, h.x, h.y, h.z, h.w);
+          if (X3)
+            st_shared_v4f(a_hi + 8192u + off, tf32_round(v[c].x - h.x), tf32_round(v[c].y - h.y), tf32_round(v[c].z - h.z),
+                          tf32_round(v[c].w - h.w));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full_bar);
+        pa ^= 1u;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&ctl->s_empty[ss]));       // last slab of the tile
+        mbar_arrive(smem_u32(&ctl->c_empty[cb]));
+      }
+      if (++ss == 2) {
+        ss = 0;
+        ps ^= 1u;
+      }
+      if (++cb == 2) {
+        cb = 0;
+        pc ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 4-7): TMEM lane == position of the tile =====================
+    const int q = warp & 3;
+    const int i = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    EpiParams ep;
+    ep.bias = p.bias;
+    ep.residual = p.residual;
+    ep.resStride = p.resStride;
+    ep.relu = p.relu;
+    ep.res_after_relu = p.res_after_relu;
+    ep.round_tf32 = p.round_tf32;
+    ep.out = p.out;
+    ep.outStride = p.outStride;
+    ep.out_nchw = p.out_nchw;
+    ep.Cout = p.Cout;
+    ep.CoutPad = p.CoutPad;
+    ep.H = p.H;
+    ep.W = p.W;
+    int buf = 0;
+    uint32_t pf = 0;
+    // The epilogue threads are idle most of a tile, and thread i == position i: they also prepare the sampling records
+    // of the NEXT tile (double-buffered), so the gather warps never wait for them.
+    int cb = 0;
+    uint32_t pc = 0;
+    auto make_records = [&](long long t) {
+      const long long mt = t / n_tiles;
+      const int im = (int)(mt / p.tiles_per_image);
+      const int y0 = (int)(mt - (long long)im * p.tiles_per_image) * p.R;
+      mbar_wait(smem_u32(&ctl->c_empty[cb]), pc ^ 1u);
+      coef_row(p, p.offmask + (size_t)(mt * DT_BM + i) * p.omStride, y0 + (i >> p.logW), i & (p.W - 1), y0 - DT_HALO,
+               coef0 + (uint32_t)cb * DT_COEF_BYTES + (uint32_t)i * 144u);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ctl->c_full[cb]));
+      if (++cb == 2) {
+        cb = 0;
+        pc ^= 1u;
+      }
+    };
+    if ((long long)blockIdx.x < total_tiles) make_records(blockIdx.x);
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (tile + gridDim.x < total_tiles) make_records(tile + gridDim.x);
+      const int n_tile = (int)(tile % n_tiles);
+      const long long m_tile = tile / n_tiles;
+      const int n = (int)(m_tile / p.tiles_per_image);
+      const int pix = (int)(m_tile - (long long)n * p.tiles_per_image) * DT_BM + i;
+      const int oy = pix / p.W, ox = pix - oy * p.W;
+      const int m = (int)(m_tile * DT_BM + i);
+      const int col_end = min(p.Cout, (n_tile + 1) * p.BN);
+      if (X3) {
+        float sums[X3 ? 64 : 1];
+#pragma unroll
+        for (int j = 0; j < (X3 ? 64 : 1); ++j) sums[j] = 0.f;
+        const int ngroups = (KB + DT_GROUP - 1) / DT_GROUP;
+        for (int gi = 0; gi < ngroups; ++gi) {
+          mbar_wait(smem_u32(&ctl->p_full[buf]), (pf >> buf) & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c * 16 < p.BN) {
+              uint32_t rr[16];
+              tmem_ld16(lane_base + (uint32_t)(buf * p.BN + c * 16), rr);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) sums[(X3 ? c * 16 + j : 0)] += __uint_as_float(rr[j]);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(smem_u32(&ctl->p_empty[buf]));
+          pf ^= 1u << buf;
+          buf ^= 1;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c0 = cc * 32;
+          if (c0 < p.BN) {
+            float vv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) vv[j] = sums[(X3 ? cc * 32 + j : 0)];
+            epilogue_sub_tile(ep, nullptr, vv, lane, true, m, n, oy, ox, n_tile * p.BN + c0, col_end);
+          }
+        }
+      } else {
+        mbar_wait(smem_u32(&ctl->p_full[buf]), (pf >> buf) & 1u);
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          uint32_t rr[32];
+          tmem_ld16(lane_base + (uint32_t)(buf * p.BN + c0), rr);
+          if (c0 + 16 < p.BN) {
+            tmem_ld16(lane_base + (uint32_t)(buf * p.BN + c0 + 16), rr + 16);
+          } else {
+#pragma unroll
+            for (int j = 16; j < 32; ++j) rr[j] = 0u;
+          }
+          tmem_ld_wait();
+          if (c0 + 32 >= p.BN) {
+            tc_fence_before();
+            mbar_arrive(smem_u32(&ctl->p_empty[buf]));
+          }
+          float vv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(rr[j]);
+          epilogue_sub_tile(ep, nullptr, vv, lane, true, m, n, oy, ox, n_tile * p.BN + c0, col_end);
+        }
+        pf ^= 1u << buf;
+        buf ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+struct DcnGeo {
+  int R, SR;
+  uint32_t slab_bytes, slab_stride;
+};
+
+DcnGeo dcn_geo(int W) {
+  DcnGeo g;
+  g.R = DT_BM / W;
+  g.SR = g.R + 2 * DT_HALO;
+  g.slab_bytes = (uint32_t)g.SR * W * DT_CS * 4u;
+  g.slab_stride = (g.slab_bytes + 1023u) & ~1023u;
+  return g;
+}
+
+}  // namespace
+
+int dcn_tma_tile_n(int CoutPad, int x3) {
+  const int cap = x3 ? 64 : 256;      // x3: the promoted sums of one position live in 64 registers (512 threads / CTA)
+  return CoutPad <= cap ? CoutPad : cap;
+}
+
+bool dcn_tma_supported(const IgemmParams& p, int x3) {
+  if (p.mode != IGEMM_DCN || p.nsrc != 1) return false;
+  if (p.kh != 3 || p.kw != 3 || p.stride != 1 || p.pad != 1) return false;
+  if (p.Cin % DT_CS || p.srcStride[0] % 4) return false;
+  const int W = p.Win, H = p.Hin;
+  if (W < 16 || W > 128 || (DT_BM % W) || H > 128 || ((H * W) % DT_BM)) return false;
+  const int bn = dcn_tma_tile_n(p.CoutPad, x3);
+  if (bn % 16 || p.CoutPad % bn) return false;
+  return true;
+}
+
+int dcn_tma_encode(const IgemmParams& p, int Bmax, void* map_out) {
+  const DcnGeo g = dcn_geo(p.Win);
+  return tma_encode_nhwc_box(p.src[0], p.srcC[0], p.Win, p.Hin, Bmax, p.srcStride[0], DT_CS, p.Win, g.SR, 1, map_out);
+}
+
+int launch_dcn_tma(const IgemmParams& p, const void* map, int x3, int round_out_tf32, cudaStream_t stream) {
+  if (!p.wgt_umma) return fail(CP_ERR_INVALID, "dcn_tma: weight tiles missing");
+  if (!dcn_tma_supported(p, x3)) return fail(CP_ERR_INVALID, "dcn_tma: unsupported shape");
+  DcnTmaParams q;
+  memset(&q, 0, sizeof(q));
+  memcpy(&q.amap, map, sizeof(CUtensorMap));
+  const DcnGeo g = dcn_geo(p.Win);
+  q.src = p.src[0];
+  q.srcStride = p.srcStride[0];
+  q.offmask = p.offmask;
+  q.omStride = p.omStride;
+  q.mask_is_logit = p.mask_is_logit;
+  q.B = p.B;
+  q.H = p.Hin;
+  q.W = p.Win;
+  q.Cin = p.Cin;
+  q.Cout = p.Cout;
+  q.CoutPad = p.CoutPad;
+  q.BN = dcn_tma_tile_n(p.CoutPad, x3);
+  q.R = g.R;
+  q.logW = 0;
+  while ((1 << q.logW) < p.Win) ++q.logW;
+  q.SR = g.SR;
+  q.tiles_per_image = p.Hin * p.Win / DT_BM;
+  q.total_tiles = (long long)q.tiles_per_image * p.B * (p.CoutPad / q.BN);
+  q.slab_bytes = g.slab_bytes;
+  q.slab_stride = g.slab_stride;
+  const uint32_t a_stage = x3 ? 16384u : 8192u;
+  const uint32_t btile = (uint32_t)q.BN * 64u * (x3 ? 2u : 1u);
+  const size_t fixed = 1024 + 2 * (size_t)DT_COEF_BYTES + 1024 + 2 * (size_t)g.slab_stride + 2 * (size_t)a_stage;
+  const size_t budget = 226 * 1024;
+  if (fixed + 2 * (size_t)btile > budget) return fail(CP_ERR_INVALID, "dcn_tma: tile does not fit shared memory");
+  q.SB = (int)((budget - fixed) / btile);
+  if (q.SB > 8) q.SB = 8;
+  q.bias = p.bias;
+  q.residual = p.residual;
+  q.resStride = p.resStride;
+  q.relu = p.relu;
+  q.res_after_relu = p.res_after_relu;
+  q.out = p.out;
+  q.outStride = p.outStride;
+  q.out_nchw = p.out_nchw;
+  q.round_tf32 = round_out_tf32;
+  if (const char* e = getenv("CP_DCN_DROP_FAR")) q.debug_drop_far = atoi(e);
+  q.wtiles = (const unsigned char*)p.wgt_umma;
+  const size_t smem = fixed + (size_t)q.SB * btile;
+  static thread_local bool configured[2] = {false, false};
+  if (!configured[x3 ? 1 : 0]) {
+    if (x3)
+      CP_CUDA_CHECK(cudaFuncSetAttribute(dcn_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    else
+      CP_CUDA_CHECK(cudaFuncSetAttribute(dcn_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[x3 ? 1 : 0] = true;
+  }
+  static thread_local int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    CP_CUDA_CHECK(cudaGetDevice(&dev));
+    CP_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const unsigned grid = (unsigned)(q.total_tiles < num_sms ? q.total_tiles : num_sms);
+  if (x3)
+    dcn_tma_kernel<true><<<grid, DT_THREADS, smem, stream>>>(q);
+  else
+    dcn_tma_kernel<false><<<grid, DT_THREADS, smem, stream>>>(q);
+  CP_LAUNCH_CHECK("dcn_tma_kernel");
+  return CP_OK;
+}
+
+}  // namespace cp

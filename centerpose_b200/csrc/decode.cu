@@ -198,6 +198,201 @@ __device__ __forceinline__ void py_slice(int start, int stop, int n, int* s0, in
   *s1 = max(start, stop);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Warp-cooperative PnP.  One thread per detection (the first version) left ~4 ms of serial double-precision latency on
+// a handful of lanes: a 12x12 Jacobi eigen-solve and the LM loop with their matrices in local memory.  Here a WARP
+// owns a detection: the matrices live in shared memory, the Jacobi rotations are applied by 12 + 12 lanes, the LM
+// Jacobian is one point per lane, and the small dependent pieces (rotation angles, 6x6 Cholesky, Rodrigues) are
+// computed redundantly by every lane from identical inputs (bitwise identical results, so control flow stays uniform).
+// Same algorithm and iteration order as pose::dlt_init / pose::refine_lm (pose_core.h), which remain the host-tested
+// statement of the math.
+constexpr int PNP_SCRATCH = 320;      // doubles per warp: [0,288) Jacobi A|V or LM workspace, [288,320) image points
+
+__device__ void dlt_init_warp(const double* X, const double* uv, int n, double fx, double fy, double cx, double cy,
+                              double* R, double* t, double* sm, int lane) {
+  double* A = sm;
+  double* V = sm + 144;
+  for (int e = lane; e < 144; e += 32) {
+    const int a = e / 12, b = e - a * 12;
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double x = (uv[2 * i] - cx) / fx, y = (uv[2 * i + 1] - cy) / fy;
+      const double h[4] = {X[3 * i], X[3 * i + 1], X[3 * i + 2], 1.0};
+      const double r1a = a < 4 ? h[a] : (a < 8 ? 0.0 : -x * h[a - 8]);
+      const double r1b = b < 4 ? h[b] : (b < 8 ? 0.0 : -x * h[b - 8]);
+      const double r2a = a < 4 ? 0.0 : (a < 8 ? h[a - 4] : -y * h[a - 8]);
+      const double r2b = b < 4 ? 0.0 : (b < 8 ? h[b - 4] : -y * h[b - 8]);
+      acc += r1a * r1b + r2a * r2b;
+    }
+    A[e] = acc;
+    V[e] = (a == b) ? 1.0 : 0.0;
+  }
+  __syncwarp();
+  const int k = lane < 12 ? lane : lane - 12;       // lanes 0-11 rotate A, lanes 12-23 rotate V
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < 12; ++i) {
+      diag += A[i * 12 + i] * A[i * 12 + i];
+      for (int j = i + 1; j < 12; ++j) off += A[i * 12 + j] * A[i * 12 + j];
+    }
+    if (off <= 1e-60 * diag || off == 0.0) break;
+    for (int p = 0; p < 11; ++p)
+      for (int q = p + 1; q < 12; ++q) {
+        const double apq = A[p * 12 + q];
+        if (apq == 0.0) continue;
+        const double app = A[p * 12 + p], aqq = A[q * 12 + q];
+        const double theta = (aqq - app) / (2.0 * apq);
+        const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
+        __syncwarp();                                 // everybody has read A[p][q], A[p][p], A[q][q]
+        if (lane < 12) {
+          const double akp = A[k * 12 + p], akq = A[k * 12 + q];
+          A[k * 12 + p] = c * akp - s * akq;
+          A[k * 12 + q] = s * akp + c * akq;
+        } else if (lane < 24) {
+          const double vkp = V[k * 12 + p], vkq = V[k * 12 + q];
+          V[k * 12 + p] = c * vkp - s * vkq;
+          V[k * 12 + q] = s * vkp + c * vkq;
+        }
+        __syncwarp();
+        if (lane < 12) {
+          const double apk = A[p * 12 + k], aqk = A[q * 12 + k];
+          A[p * 12 + k] = c * apk - s * aqk;
+          A[q * 12 + k] = s * apk + c * aqk;
+        }
+        __syncwarp();
+      }
+  }
+  int m = 0;
+  for (int i = 1; i < 12; ++i)
+    if (A[i * 12 + i] < A[m * 12 + m]) m = i;
+  double pv[12];
+  for (int i = 0; i < 12; ++i) pv[i] = V[i * 12 + m];
+  __syncwarp();
+  pose::dlt_finish(pv, R, t);
+}
+
+// sum_i |project(R X_i + t) - uv_i|^2: one point per lane, summed in point order by every lane
+__device__ double reproj_cost_warp(const double* X, const double* uv, int n, const double* R, const double* t, double fx,
+                                   double fy, double cx, double cy, double* part, int lane) {
+  __syncwarp();
+  if (lane < n) {
+    const double* x = X + 3 * lane;
+    const double px = R[0] * x[0] + R[1] * x[1] + R[2] * x[2] + t[0];
+    const double py = R[3] * x[0] + R[4] * x[1] + R[5] * x[2] + t[1];
+    const double pz = R[6] * x[0] + R[7] * x[1] + R[8] * x[2] + t[2];
+    const double du = fx * px / pz + cx - uv[2 * lane];
+    const double dv = fy * py / pz + cy - uv[2 * lane + 1];
+    part[lane] = du * du + dv * dv;
+  }
+  __syncwarp();
+  double c = 0.0;
+  for (int i = 0; i < n; ++i) c += part[i];
+  return c;
+}
+
+__device__ double refine_lm_warp(const double* X, const double* uv, int n, double fx, double fy, double cx, double cy,
+                                 double* R, double* t, double* sm, int lane) {
+  double* J = sm;            // [16][14]: Ju[6], Jv[6], ru, rv
+  double* AG = sm + 224;     // 21 lower-triangle entries of J^T J, then 6 of J^T r
+  double* part = sm + 256;   // [16]
+  double lam = 1e-3;
+  double cost = reproj_cost_warp(X, uv, n, R, t, fx, fy, cx, cy, part, lane);
+  for (int iter = 0; iter < 200; ++iter) {
+    __syncwarp();
+    if (lane < n) {
+      const double* x = X + 3 * lane;
+      const double qx = R[0] * x[0] + R[1] * x[1] + R[2] * x[2];
+      const double qy = R[3] * x[0] + R[4] * x[1] + R[5] * x[2];
+      const double qz = R[6] * x[0] + R[7] * x[1] + R[8] * x[2];
+      const double px = qx + t[0], py = qy + t[1], pz = qz + t[2];
+      const double iz = 1.0 / pz;
+      const double du[3] = {fx * iz, 0.0, -fx * px * iz * iz};
+      const double dv[3] = {0.0, fy * iz, -fy * py * iz * iz};
+      double* Jr = J + lane * 14;
+      Jr[0] = du[1] * (-qz) + du[2] * qy;
+      Jr[1] = du[0] * qz + du[2] * (-qx);
+      Jr[2] = du[0] * (-qy) + du[1] * qx;
+      Jr[6] = dv[1] * (-qz) + dv[2] * qy;
+      Jr[7] = dv[0] * qz + dv[2] * (-qx);
+      Jr[8] = dv[0] * (-qy) + dv[1] * qx;
+      for (int kk = 0; kk < 3; ++kk) {
+        Jr[3 + kk] = du[kk];
+        Jr[9 + kk] = dv[kk];
+      }
+      Jr[12] = fx * px * iz + cx - uv[2 * lane];
+      Jr[13] = fy * py * iz + cy - uv[2 * lane + 1];
+    }
+    __syncwarp();
+    if (lane < 27) {
+      double val = 0.0;
+      if (lane < 21) {
+        int a = 0;
+        while ((a + 1) * (a + 2) / 2 <= lane) ++a;      // lower-triangle index -> (a, b), b <= a
+        const int b = lane - a * (a + 1) / 2;
+        for (int i = 0; i < n; ++i) val += J[i * 14 + a] * J[i * 14 + b] + J[i * 14 + 6 + a] * J[i * 14 + 6 + b];
+      } else {
+        const int a = lane - 21;
+        for (int i = 0; i < n; ++i) val += J[i * 14 + a] * J[i * 14 + 12] + J[i * 14 + 6 + a] * J[i * 14 + 13];
+      }
+      AG[lane] = val;
+    }
+    __syncwarp();
+    double A[36], g[6];
+    for (int a = 0; a < 6; ++a) {
+      g[a] = AG[21 + a];
+      for (int b = 0; b <= a; ++b) {
+        const double v = AG[a * (a + 1) / 2 + b];
+        A[a * 6 + b] = v;
+        A[b * 6 + a] = v;
+      }
+    }
+    bool improved = false;
+    double d[6], Rn[9], tn[3], cn = 0.0;
+    for (int tr = 0; tr < 30; ++tr) {
+      if (pose::solve6(A, g, lam, d)) {
+        double E[9];
+        pose::rodrigues(d, E);
+        pose::mat3_mul(E, R, Rn);
+        for (int kk = 0; kk < 3; ++kk) tn[kk] = t[kk] + d[3 + kk];
+        cn = reproj_cost_warp(X, uv, n, Rn, tn, fx, fy, cx, cy, part, lane);
+        if (cn == cn && cn <= cost && fabs(cn) < 1e300) {
+          improved = true;
+          break;
+        }
+      }
+      lam *= 10.0;
+    }
+    if (!improved) break;
+    double step = 0.0;
+    for (int kk = 0; kk < 6; ++kk) step += d[kk] * d[kk];
+    step = sqrt(step);
+    for (int kk = 0; kk < 9; ++kk) R[kk] = Rn[kk];
+    for (int kk = 0; kk < 3; ++kk) t[kk] = tn[kk];
+    const double dec = cost - cn;
+    cost = cn;
+    lam = lam * 0.1;
+    if (lam < 1e-12) lam = 1e-12;
+    if (step < 1e-13 || dec <= 1e-28 * (cost > 1e-300 ? cost : 1e-300)) break;
+  }
+  return cost;
+}
+
+// pose::solve_and_shell, executed by a whole warp; every lane ends with the same PnPOut
+__device__ void solve_and_shell_warp(const double* pts, int n_in, const float* obj_scale, const double* Kc, double width,
+                                     double height, int visible_thresh, int opencv_return, pose::PnPOut* o, double* sm,
+                                     int lane) {
+  double V[24], X[48], uv[32];
+  const int n = pose::pnp_collect(pts, n_in, obj_scale, V, X, uv);
+  o->n_pts = n;
+  o->status = CP_PNP_FEW_POINTS;
+  if (n < 6) return;
+  double R[9], t[3];
+  dlt_init_warp(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t, sm, lane);
+  const double cost = refine_lm_warp(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t, sm, lane);
+  pose::pnp_finish(V, R, t, cost, n, Kc, width, height, visible_thresh, opencv_return, o);
+}
+
 __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
   const cp_decode_params& P = a.prm;
   const int b = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
@@ -412,7 +607,7 @@ __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
   __syncthreads();
   const int n1 = s_n1;
 
-  // ---------------- phase F: records + PnP, one thread per surviving detection
+  // ---------------- phase F: records, one thread per surviving detection
   for (int i = tid; i < n1; i += NT) {
     const int k = nb_perm[i];
     const float* d = dets + (size_t)k * CP_DETS_RECORD;
@@ -452,38 +647,54 @@ __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
       o[CP_P_OBJ_SCALE_UNC + t] = d[CP_D_OBJ_SCALE_UNC + t];
     }
     for (int t = 0; t < 2; ++t) o[CP_P_TRACKING + t] = __fmul_rn(d[CP_D_TRACKING + t], ratio);
-
-    pose::PnPOut po;
-    po.status = CP_PNP_NOT_RUN;
-    po.n_pts = 0;
-    if (P.use_pnp) {
-      double pts[32];
-      int n_in;
-      if (P.rep_mode == 1) {
-        n_in = 16;
-        for (int j = 0; j < 8; ++j) {
-          pts[4 * j] = dmean[2 * j];
-          pts[4 * j + 1] = dmean[2 * j + 1];
-          pts[4 * j + 2] = hmean[2 * j];
-          pts[4 * j + 3] = hmean[2 * j + 1];
+  }
+  // ---------------- phase G: PnP, one WARP per surviving detection
+  {
+    extern __shared__ double pnp_scratch[];
+    const int warp = tid >> 5, lane = tid & 31, NW = NT >> 5;
+    double* sm = pnp_scratch + warp * PNP_SCRATCH;
+    double* pts = sm + 288;
+    for (int i = warp; i < n1; i += NW) {
+      const int k = nb_perm[i];
+      const float* d = dets + (size_t)k * CP_DETS_RECORD;
+      float* o = poses + (size_t)i * CP_POSE_RECORD;
+      pose::PnPOut po;
+      po.status = CP_PNP_NOT_RUN;
+      po.n_pts = 0;
+      if (P.use_pnp) {
+        const int n_in = (P.rep_mode == 1) ? 16 : 8;
+        __syncwarp();
+        if (lane < n_in) {
+          // rep_mode 1: point 2j = displacement mean of joint j, point 2j+1 = heat-map mean; else point j = kps[j]
+          const int j = (P.rep_mode == 1) ? (lane >> 1) : lane;
+          const int off = (P.rep_mode == 1) ? ((lane & 1) ? CP_D_KPS_HM_MEAN : CP_D_KPS_DISP_MEAN) : CP_D_KPS;
+          const float x = d[off + 2 * j], y = d[off + 2 * j + 1];
+          double X0 = -10000.0, Y0 = -10000.0;
+          if (!(x == SENT && y == SENT)) {
+            X0 = aff * (double)x + tx;
+            Y0 = aff * (double)y + ty;
+          }
+          pts[2 * lane] = X0;
+          pts[2 * lane + 1] = Y0;
         }
-      } else {
-        n_in = 8;
-        for (int t = 0; t < 16; ++t) pts[t] = kps[t];
+        __syncwarp();
+        float sc[3] = {d[CP_D_OBJ_SCALE], d[CP_D_OBJ_SCALE + 1], d[CP_D_OBJ_SCALE + 2]};
+        solve_and_shell_warp(pts, n_in, sc, meta + 5, img_w, img_h, P.visible_thresh, P.opencv_return, &po, sm, lane);
       }
-      float sc[3] = {d[CP_D_OBJ_SCALE], d[CP_D_OBJ_SCALE + 1], d[CP_D_OBJ_SCALE + 2]};
-      pose::solve_and_shell(pts, n_in, sc, meta + 5, img_w, img_h, P.visible_thresh, P.opencv_return, &po);
+      if (lane == 0) {
+        o[CP_P_STATUS] = (float)po.status;
+        o[CP_P_NPTS] = (float)po.n_pts;
+        const bool has_pose = (po.status == CP_PNP_OK || po.status == CP_PNP_INVISIBLE);
+        const bool has_proj = has_pose || po.status == CP_PNP_BEHIND;
+        for (int t = 0; t < 3; ++t) o[CP_P_LOCATION + t] = has_pose ? (float)po.loc[t] : 0.0f;
+        for (int t = 0; t < 4; ++t) o[CP_P_QUAT + t] = has_pose ? (float)po.quat[t] : 0.0f;
+        o[CP_P_REPROJ] = has_proj ? (float)po.reproj : 0.0f;
+        for (int t = 0; t < 16; ++t) o[CP_P_PROJ_CUBOID + t] = has_proj ? (float)po.proj[t] : 0.0f;
+        for (int t = 0; t < 27; ++t) o[CP_P_KPS_3D_CAM + t] = has_pose ? (float)po.kps3d[t] : 0.0f;
+        for (int t = 0; t < 18; ++t) o[CP_P_KPS_PNP + t] = has_pose ? (float)po.kpspnp[t] : 0.0f;
+      }
+      __syncwarp();
     }
-    o[CP_P_STATUS] = (float)po.status;
-    o[CP_P_NPTS] = (float)po.n_pts;
-    const bool has_pose = (po.status == CP_PNP_OK || po.status == CP_PNP_INVISIBLE);
-    const bool has_proj = has_pose || po.status == CP_PNP_BEHIND;
-    for (int t = 0; t < 3; ++t) o[CP_P_LOCATION + t] = has_pose ? (float)po.loc[t] : 0.0f;
-    for (int t = 0; t < 4; ++t) o[CP_P_QUAT + t] = has_pose ? (float)po.quat[t] : 0.0f;
-    o[CP_P_REPROJ] = has_proj ? (float)po.reproj : 0.0f;
-    for (int t = 0; t < 16; ++t) o[CP_P_PROJ_CUBOID + t] = has_proj ? (float)po.proj[t] : 0.0f;
-    for (int t = 0; t < 27; ++t) o[CP_P_KPS_3D_CAM + t] = has_pose ? (float)po.kps3d[t] : 0.0f;
-    for (int t = 0; t < 18; ++t) o[CP_P_KPS_PNP + t] = has_pose ? (float)po.kpspnp[t] : 0.0f;
   }
   // zero the unused slots so the all-gathered tensor is deterministic
   for (int i = n1 * CP_POSE_RECORD + tid; i < K * CP_POSE_RECORD; i += NT) poses[i] = 0.0f;
@@ -571,7 +782,12 @@ int cp_decode_pnp(const cp_decode_params* prm, const cp_heads* heads, const doub
   ga.dets = dets_buf;
   ga.poses = poses;
   ga.n_valid = n_valid;
-  group_pose_kernel<<<prm->batch, 256, 0, s>>>(ga);
+  static thread_local bool pose_configured = false;
+  if (!pose_configured) {      // static (~29 KB) + dynamic (20 KB) shared memory crosses the 48 KB default
+    CP_CUDA_CHECK(cudaFuncSetAttribute(group_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    pose_configured = true;
+  }
+  group_pose_kernel<<<prm->batch, 256, 8 * PNP_SCRATCH * sizeof(double), s>>>(ga);
   CP_LAUNCH_CHECK("group_pose_kernel");
   return CP_OK;
 }

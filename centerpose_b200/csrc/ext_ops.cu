@@ -76,6 +76,20 @@ static int run_igemm(IgemmParams& p, int prec, int Kreal, cudaStream_t s) {
   if (prec == 2 || prec == 1) {
     const int x3 = prec == 1;
     const char* force_gather = getenv("CP_FORCE_GATHER");
+    if (p.mode == IGEMM_DCN && dcn_tma_supported(p, x3) && !(force_gather && atoi(force_gather))) {
+      void* tiles = nullptr;
+      CP_CUDA_CHECK(cudaMallocAsync(&tiles, tma_weight_bytes(p.Cin, 9, p.CoutPad, x3), s));
+      alignas(64) unsigned char map[128];
+      int rc = dcn_tma_encode(p, p.B, map);
+      if (!rc) rc = launch_pack_tma_weight(p.wgt, p.CoutPad, p.Cin, 9, p.Cout, p.CoutPad, 1, x3, 16, tiles, s,
+                                           dcn_tma_tile_n(p.CoutPad, x3));
+      if (!rc) {
+        p.wgt_umma = tiles;
+        rc = launch_dcn_tma(p, map, x3, 0, s);
+      }
+      cudaFreeAsync(tiles, s);
+      return rc;
+    }
     if (!tma_conv_supported(p, x3) || (force_gather && atoi(force_gather))) {
       prec = 1;     // deformable / strided ops: 3-term split gather kernel
     } else {

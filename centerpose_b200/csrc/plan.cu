@@ -55,6 +55,7 @@ struct Op {
   int w_ld = 0;            // leading dimension of the fp32 packed weight matrix
   bool use_umma = false;   // run on the tcgen05 gather kernel
   bool use_tma = false;    // run on the TMA-fed tcgen05 kernel (conv_tma.cu)
+  bool use_dcn_tma = false;   // deformable conv on the TMA-staged tcgen05 kernel (dcn_tma.cu)
   int tma_cslab = 32;
   std::vector<unsigned char> tma_maps;   // 4 CUtensorMap, encoded once the arena exists
   size_t umma_off = 0;     // bytes into the plan's tensor-core weight-tile buffer
@@ -112,6 +113,7 @@ struct cp_plan {
   size_t decode_ws_bytes = 0;
   double* gn_stats = nullptr;
   int prec = -1;                 // -1 fp32 CUDA cores, 0 bf16 tcgen05, 1 tf32x3 tcgen05, 2 tf32 (TMA) + tf32x3 elsewhere
+  bool no_dcn_tma = false;       // CP_NO_DCN_TMA=1: deformable convs on the global-gather kernel (A/B measurements)
   int tma_base_offset = 0;       // measured on B200: UMMA swizzles on absolute smem address bits, the field must stay 0
   unsigned char* umma_wts = nullptr;
   size_t umma_bytes = 0;
@@ -561,7 +563,12 @@ int build_graph(cp_plan* P) {
       // 16-channel layers (level0 / level1): 133 K single-tile CTAs of almost no MMA work are dominated by the fixed
       // per-CTA cost of a tcgen05 kernel (measured 5.2 ms vs 2.5 ms on the FFMA kernel) -> keep them on CUDA cores
       if (op.Cin < 32) continue;
-      if ((P->prec == 2 || P->prec == 1) && tma_conv_supported(q, P->prec == 1)) {
+      q.Hin = op.src[0].H;
+      if ((P->prec == 2 || P->prec == 1) && !P->no_dcn_tma && dcn_tma_supported(q, P->prec == 1)) {
+        op.use_dcn_tma = true;
+        op.umma_off = P->umma_bytes;
+        P->umma_bytes += (tma_weight_bytes(op.Cin, 9, op.CoutPad, P->prec == 1) + 1023) / 1024 * 1024;
+      } else if ((P->prec == 2 || P->prec == 1) && tma_conv_supported(q, P->prec == 1)) {
         op.use_tma = true;
         op.umma_off = P->umma_bytes;
         P->umma_bytes += (tma_weight_bytes(op.Cin, op.kh * op.kw, op.CoutPad, P->prec == 1) + 1023) / 1024 * 1024;
@@ -614,6 +621,7 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
   P->W = cfg->width;
   P->prec = cfg->precision == CP_PREC_BF16 ? 0 : (cfg->precision == CP_PREC_TF32X3 ? 1 : (cfg->precision == CP_PREC_TF32 ? 2 : -1));
   if (const char* e = getenv("CP_TMA_BASE_OFFSET")) P->tma_base_offset = atoi(e);
+  if (const char* e = getenv("CP_NO_DCN_TMA")) P->no_dcn_tma = atoi(e) != 0;
   CP_CUDA_CHECK(cudaSetDevice(cfg->device));
   int rc = build_graph(P.get());
   if (rc) return rc;
@@ -622,6 +630,20 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
   CP_CUDA_CHECK(cudaMemset(P->wts, 0, P->w_floats * sizeof(float)));
   CP_CUDA_CHECK(cudaMalloc(&P->gn_stats, sizeof(double) * (size_t)P->B * 64 * 2));
   if (P->umma_bytes) CP_CUDA_CHECK(cudaMalloc(&P->umma_wts, P->umma_bytes));
+  for (auto& op : P->ops) {
+    if (!op.use_dcn_tma) continue;
+    IgemmParams q{};
+    q.nsrc = 1;
+    q.src[0] = P->act + op.src[0].off;
+    q.srcC[0] = op.src[0].C;
+    q.srcStride[0] = op.src[0].stride;
+    q.Hin = op.src[0].H;
+    q.Win = op.src[0].W;
+    op.tma_maps.resize(512 + 64);
+    unsigned char* mp = (unsigned char*)(((uintptr_t)op.tma_maps.data() + 63) & ~(uintptr_t)63);
+    int rc2 = dcn_tma_encode(q, P->B, mp);
+    if (rc2) return rc2;
+  }
   for (auto& op : P->ops) {
     if (!op.use_tma) continue;
     IgemmParams q{};
@@ -724,7 +746,11 @@ int cp_plan_load_weights(cp_plan* P, const char* const* names, const void* const
   // second pass: tensor-core weight tiles are cut from the finished fp32 matrices (merged matrices are complete now)
   for (auto& op : P->ops) {
     if (op.type != OP_IGEMM) continue;
-    if (op.use_tma) {
+    if (op.use_dcn_tma) {
+      if ((rc = launch_pack_tma_weight(P->wts + op.w_off, op.w_ld, op.Cin, 9, op.Cout, op.CoutPad, 1, P->prec == 1, 16,
+                                       P->umma_wts + op.umma_off, s, dcn_tma_tile_n(op.CoutPad, P->prec == 1))))
+        return rc;
+    } else if (op.use_tma) {
       if ((rc = launch_pack_tma_weight(P->wts + op.w_off, op.w_ld, op.Cin, op.kh * op.kw, op.Cout, op.CoutPad, 1,
                                        P->prec == 1, op.tma_cslab, P->umma_wts + op.umma_off, s)))
         return rc;
@@ -800,7 +826,11 @@ static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* 
           p.mask_is_logit = 1;
         }
         p.mode = op.mode;
-        if (op.use_tma) {
+        if (op.use_dcn_tma) {
+          p.wgt_umma = P->umma_wts + op.umma_off;
+          const unsigned char* mp = (const unsigned char*)(((uintptr_t)op.tma_maps.data() + 63) & ~(uintptr_t)63);
+          if ((rc = launch_dcn_tma(p, mp, P->prec == 1, P->prec == 2, s))) return rc;
+        } else if (op.use_tma) {
           p.wgt_umma = P->umma_wts + op.umma_off;
           const unsigned char* mp = (const unsigned char*)(((uintptr_t)op.tma_maps.data() + 63) & ~(uintptr_t)63);
           if ((rc = launch_conv_tma(p, mp, P->prec == 2, P->tma_base_offset, P->prec == 1, s))) return rc;

@@ -220,21 +220,8 @@ CP_HD double reproj_cost(const double* X, const double* uv, int n, const double*
   return c;
 }
 
-// DLT start (OpenCV findExtrinsicCameraParams2, non-planar branch)
-CP_HDN void dlt_init(const double* X, const double* uv, int n, double fx, double fy, double cx, double cy, double* R,
-                     double* t) {
-  double A[144];
-  for (int i = 0; i < 144; ++i) A[i] = 0.0;
-  for (int i = 0; i < n; ++i) {
-    double x = (uv[2 * i] - cx) / fx, y = (uv[2 * i + 1] - cy) / fy;
-    double Xi = X[3 * i], Yi = X[3 * i + 1], Zi = X[3 * i + 2];
-    double r1[12] = {Xi, Yi, Zi, 1, 0, 0, 0, 0, -x * Xi, -x * Yi, -x * Zi, -x};
-    double r2[12] = {0, 0, 0, 0, Xi, Yi, Zi, 1, -y * Xi, -y * Yi, -y * Zi, -y};
-    for (int a = 0; a < 12; ++a)
-      for (int b = 0; b < 12; ++b) A[a * 12 + b] += r1[a] * r1[b] + r2[a] * r2[b];
-  }
-  double V[144], p[12];
-  jacobi_min_eigvec<12>(A, V, p);
+// second half of the DLT start: null vector p (3x4 projection, row-major) -> nearest rotation + scaled translation
+CP_HDN void dlt_finish(const double* p, double* R, double* t) {
   double RR[9] = {p[0], p[1], p[2], p[4], p[5], p[6], p[8], p[9], p[10]};
   double tt[3] = {p[3], p[7], p[11]};
   if (mat3_det(RR) < 0) {
@@ -261,6 +248,24 @@ CP_HDN void dlt_init(const double* X, const double* uv, int n, double fx, double
   for (int i = 0; i < 9; ++i) R[i] = Xm[i];
   double f = 1.7320508075688772 / sc;  // ||R_orth||_F / ||RR||_F
   for (int i = 0; i < 3; ++i) t[i] = tt[i] * f;
+}
+
+// DLT start (OpenCV findExtrinsicCameraParams2, non-planar branch)
+CP_HDN void dlt_init(const double* X, const double* uv, int n, double fx, double fy, double cx, double cy, double* R,
+                     double* t) {
+  double A[144];
+  for (int i = 0; i < 144; ++i) A[i] = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double x = (uv[2 * i] - cx) / fx, y = (uv[2 * i + 1] - cy) / fy;
+    double Xi = X[3 * i], Yi = X[3 * i + 1], Zi = X[3 * i + 2];
+    double r1[12] = {Xi, Yi, Zi, 1, 0, 0, 0, 0, -x * Xi, -x * Yi, -x * Zi, -x};
+    double r2[12] = {0, 0, 0, 0, Xi, Yi, Zi, 1, -y * Xi, -y * Yi, -y * Zi, -y};
+    for (int a = 0; a < 12; ++a)
+      for (int b = 0; b < 12; ++b) A[a * 12 + b] += r1[a] * r1[b] + r2[a] * r2[b];
+  }
+  double V[144], p[12];
+  jacobi_min_eigvec<12>(A, V, p);
+  dlt_finish(p, R, t);
 }
 
 // Levenberg-Marquardt on the pixel reprojection error, update R <- exp([dw]x) R, t <- t + dt
@@ -334,15 +339,15 @@ CP_HDN double refine_lm(const double* X, const double* uv, int n, double fx, dou
   return cost;
 }
 
-// solve_pnp + pnp_shell for one detection.
+// solve_pnp + pnp_shell for one detection, in three steps so that the CUDA decode kernel can run the two heavy ones
+// (DLT eigen-solve, LM) warp-cooperatively (decode.cu) while host tests run the serial chain below.
 //   pts: n_in x 2 image points (n_in = 8 or 16; 3-D vertex of point i is V[i / (n_in/8)])
 //   Kc:  camera matrix row-major; width/height: image size for kps_pnp normalisation
 //   visible_thresh: 6 / 3 / 0 (see cp_decode_params)
-CP_HDN void solve_and_shell(const double* pts, int n_in, const float* obj_scale, const double* Kc, double width,
-                            double height, int visible_thresh, int opencv_return, PnPOut* o) {
-  double V[24];
+// pnp_collect: cuboid vertices + the points that are not the -10000 sentinel; returns their number.
+CP_HDN int pnp_collect(const double* pts, int n_in, const float* obj_scale, double* V /*24*/, double* X /*48*/,
+                       double* uv /*32*/) {
   cuboid_vertices(obj_scale, V);
-  double X[48], uv[32];
   int n = 0;
   const int per = n_in / 8;
   for (int i = 0; i < n_in; ++i) {
@@ -355,13 +360,13 @@ CP_HDN void solve_and_shell(const double* pts, int n_in, const float* obj_scale,
     X[3 * n + 2] = v[2];
     ++n;
   }
-  o->n_pts = n;
-  o->status = 4;  // CP_PNP_FEW_POINTS
-  if (n < 6) return;
+  return n;
+}
+
+// pnp_finish: everything after the solver (cuboid_pnp_solver.py:190-239, cuboid_pnp_shell.py:24-93)
+CP_HDN void pnp_finish(const double* V, const double* R, const double* t, double cost, int n, const double* Kc,
+                       double width, double height, int visible_thresh, int opencv_return, PnPOut* o) {
   const double fx = Kc[0], fy = Kc[4], cx = Kc[2], cy = Kc[5];
-  double R[9], t[3];
-  dlt_init(X, uv, n, fx, fy, cx, cy, R, t);
-  double cost = refine_lm(X, uv, n, fx, fy, cx, cy, R, t);
   bool finite = (cost == cost) && fabs(cost) < 1e300;
   for (int i = 0; i < 9; ++i) finite = finite && (R[i] == R[i]);
   for (int i = 0; i < 3; ++i) finite = finite && (t[i] == t[i]);
@@ -433,6 +438,19 @@ CP_HDN void solve_and_shell(const double* pts, int n_in, const float* obj_scale,
     if (nv >= visible_thresh) o->status = 2;
   }
   if (!(o->kpspnp[0] > 0 && o->kpspnp[0] < 1 && o->kpspnp[1] > 0 && o->kpspnp[1] < 1)) o->status = 2;
+}
+
+CP_HDN void solve_and_shell(const double* pts, int n_in, const float* obj_scale, const double* Kc, double width,
+                            double height, int visible_thresh, int opencv_return, PnPOut* o) {
+  double V[24], X[48], uv[32];
+  const int n = pnp_collect(pts, n_in, obj_scale, V, X, uv);
+  o->n_pts = n;
+  o->status = 4;  // CP_PNP_FEW_POINTS
+  if (n < 6) return;
+  double R[9], t[3];
+  dlt_init(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t);
+  const double cost = refine_lm(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t);
+  pnp_finish(V, R, t, cost, n, Kc, width, height, visible_thresh, opencv_return, o);
 }
 
 // ---- Gaussian soft-NMS (object_pose.py:27-124, method=2, sigma=0.5) ----------------

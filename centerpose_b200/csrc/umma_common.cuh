@@ -1,5 +1,6 @@
 // PTX wrappers and epilogue helpers shared by the tcgen05 kernels (igemm_umma.cu, conv_tma.cu).  sm_100a only.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -91,6 +92,70 @@ __device__ __forceinline__ float4 ld_shared_v4f(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+
+// ---- TMA tensor loads, tcgen05.mma kind::tf32, clusters, shared-memory matrix descriptors (conv_tma.cu, dcn_tma.cu)
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy global -> the SAME shared-memory offset of every CTA in `mask`, completing on each CTA's own mbarrier
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit that arrives on the same-offset mbarrier of every CTA in `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
+// K-major SWIZZLE_128B descriptor; `saddr` may be any multiple of 16 bytes.  Measured on B200
+// (scripts/tma_diag.py): the tensor core applies the 128-byte swizzle to the ABSOLUTE shared-memory address bits
+// [7,10), exactly like TMA does when it writes the slab, so a matrix that starts at an arbitrary 128-byte row of
+// the slab needs NO base-offset correction (setting the field to (addr >> 7) & 7 gives wrong results).
+// `use_base_offset` is kept only as a debug switch (CP_TMA_BASE_OFFSET=1).
+// cslab = 32: 128-byte rows, SWIZZLE_128B (layout type 2), 8-row groups 1024 bytes apart;
+// cslab = 16:  64-byte rows, SWIZZLE_64B  (layout type 4), 8-row groups  512 bytes apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int use_base_offset, int cslab) {
+  const uint64_t sbo = cslab == 32 ? (1024 >> 4) : (512 >> 4);
+  const uint64_t lay = cslab == 32 ? 2ull : 4ull;
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (lay << 61);
+  if (use_base_offset) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
 
 // ---------------------------------------------------------------------------------------------------------------
 // Epilogue store of a [32 rows x 32 columns] sub-tile owned by ONE warp (lane == row, tcgen05.ld layout) to an NHWC

@@ -81,6 +81,28 @@ def test_dcn_tensor_core(prec, cplib):
         assert err <= TOL[prec]
 
 
+@pytest.mark.parametrize("prec", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("off_std", [0.5, 4.0])
+def test_dcn_tma_staged(prec, off_std, cplib):
+    """Shapes the TMA-staged deformable kernel (dcn_tma.cu) takes: W in {16, 32, 64, 128}, H*W % 128 == 0.
+    off_std 0.5 keeps the corners inside the staged slab, 4.0 sends a large share through the global-memory path;
+    both must match the fp64 restatement of dcn_v2_im2col_cuda.cu."""
+    from oracle import net_ref
+    g = torch.Generator().manual_seed(23)
+    for (B, C, H, W, Co) in ((2, 64, 16, 16, 64), (1, 32, 8, 32, 48), (1, 128, 4, 64, 128), (1, 16, 3, 128, 16),
+                             (3, 64, 32, 32, 256)):
+        x = torch.randn(B, C, H, W, generator=g)
+        off = torch.randn(B, 18, H, W, generator=g) * off_std
+        mask = torch.rand(B, 9, H, W, generator=g)
+        w = torch.randn(Co, C, 3, 3, generator=g) / np.sqrt(C * 9)
+        b = torch.randn(Co, generator=g) * 0.1
+        want = net_ref.dcn_v2_forward_ref(x.double(), off.double(), mask.double(), w.double(), b.double()).float()
+        got = cpb.dcn_v2_forward(x.cuda(), w.cuda(), b.cuda(), off.cuda(), mask.cuda(), precision=prec).cpu()
+        err = (got - want).abs().max().item() / want.abs().max().item()
+        print("dcn_tma %s %s off_std %.1f: rel err %.3e" % ((B, C, H, W, Co), prec, off_std, err))
+        assert err <= TOL[prec], "dcn_tma %s %s off by %.3e" % ((B, C, H, W, Co), prec, err)
+
+
 def _net(arch, trk, wseed, prec):
     opt = cpb.default_opt(arch, tracking_task=trk)
     m = cpb.create_model(opt.arch, opt.heads, opt.head_conv, opt)

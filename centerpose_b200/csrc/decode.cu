@@ -298,7 +298,7 @@ __device__ double refine_lm_warp(const double* X, const double* uv, int n, doubl
   double* part = sm + 256;   // [16]
   double lam = 1e-3;
   double cost = reproj_cost_warp(X, uv, n, R, t, fx, fy, cx, cy, part, lane);
-  for (int iter = 0; iter < 200; ++iter) {
+  for (int iter = 0; iter < 20; ++iter) {       // cv2 TermCriteria MAX_ITER, see pose::refine_lm
     __syncwarp();
     if (lane < n) {
       const double* x = X + 3 * lane;
@@ -373,7 +373,7 @@ __device__ double refine_lm_warp(const double* X, const double* uv, int n, doubl
     cost = cn;
     lam = lam * 0.1;
     if (lam < 1e-12) lam = 1e-12;
-    if (step < 1e-13 || dec <= 1e-28 * (cost > 1e-300 ? cost : 1e-300)) break;
+    if (step < 1e-10 || dec <= 1e-28 * (cost > 1e-300 ? cost : 1e-300)) break;
   }
   return cost;
 }

@@ -273,7 +273,10 @@ CP_HDN double refine_lm(const double* X, const double* uv, int n, double fx, dou
                         double* t) {
   double lam = 1e-3;
   double cost = reproj_cost(X, uv, n, R, t, fx, fy, cx, cy);
-  for (int iter = 0; iter < 200; ++iter) {
+  // cv2's SOLVEPNP_ITERATIVE runs its LM under TermCriteria(MAX_ITER + EPS, 20, FLT_EPSILON).  Well-posed inputs
+  // converge in < 10 steps (agreement with cv2 <= 5e-8); on inconsistent keypoints cv2 stops unconverged, and stopping
+  // after 20 accepted steps stays closest to what it returns (measured: |dR| 2e-2 vs 6e-1 for a 200-step run).
+  for (int iter = 0; iter < 20; ++iter) {
     double A[36], g[6];
     for (int i = 0; i < 36; ++i) A[i] = 0.0;
     for (int i = 0; i < 6; ++i) g[i] = 0.0;
@@ -334,7 +337,7 @@ CP_HDN double refine_lm(const double* X, const double* uv, int n, double fx, dou
     cost = cn;
     lam = lam * 0.1;
     if (lam < 1e-12) lam = 1e-12;
-    if (step < 1e-13 || dec <= 1e-28 * (cost > 1e-300 ? cost : 1e-300)) break;
+    if (step < 1e-10 || dec <= 1e-28 * (cost > 1e-300 ? cost : 1e-300)) break;
   }
   return cost;
 }

@@ -146,10 +146,12 @@ def dlt_init(X, uv, Kc):
     return R, tt
 
 
-def refine_lm(X, uv, Kc, R, t, max_iter=200):
+def refine_lm(X, uv, Kc, R, t, max_iter=20):
     """Levenberg-Marquardt on the pixel reprojection error with a left
     multiplicative rotation update R <- exp([dw]x) R (the minimiser does not
-    depend on the parametrisation)."""
+    depend on the parametrisation).  max_iter = 20 accepted steps mirrors cv2's
+    TermCriteria(MAX_ITER + EPS, 20, FLT_EPSILON): converged cases are unaffected
+    (agreement with cv2 <= 1e-8), unconverged ones stay close to what cv2 returns."""
     def resid(R, t):
         return (project(X, R, t, Kc) - uv).reshape(-1)
 
@@ -193,7 +195,7 @@ def refine_lm(X, uv, Kc, R, t, max_iter=200):
         dec = cost - cn
         cost = cn
         lam = max(lam * 0.1, 1e-12)
-        if step < 1e-13 or dec <= 1e-28 * max(cost, 1e-300):
+        if step < 1e-10 or dec <= 1e-28 * max(cost, 1e-300):
             break
     return R, t, cost
 

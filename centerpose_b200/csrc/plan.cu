@@ -113,6 +113,7 @@ struct cp_plan {
   size_t decode_ws_bytes = 0;
   double* gn_stats = nullptr;
   int prec = -1;                 // -1 fp32 CUDA cores, 0 bf16 tcgen05, 1 tf32x3 tcgen05, 2 tf32 (TMA) + tf32x3 elsewhere
+  int min_tc_cin = 32;           // ops with fewer input channels stay on the CUDA-core kernels (CP_MIN_TC_CIN overrides)
   bool no_dcn_tma = false;       // CP_NO_DCN_TMA=1: deformable convs on the global-gather kernel (A/B measurements)
   int tma_base_offset = 0;       // measured on B200: UMMA swizzles on absolute smem address bits, the field must stay 0
   unsigned char* umma_wts = nullptr;
@@ -562,7 +563,7 @@ int build_graph(cp_plan* P) {
       if (op.src[0].ext >= 0) continue;
       // 16-channel layers (level0 / level1): 133 K single-tile CTAs of almost no MMA work are dominated by the fixed
       // per-CTA cost of a tcgen05 kernel (measured 5.2 ms vs 2.5 ms on the FFMA kernel) -> keep them on CUDA cores
-      if (op.Cin < 32) continue;
+      if (op.Cin < P->min_tc_cin) continue;
       q.Hin = op.src[0].H;
       if ((P->prec == 2 || P->prec == 1) && !P->no_dcn_tma && dcn_tma_supported(q, P->prec == 1)) {
         op.use_dcn_tma = true;
@@ -621,6 +622,7 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
   P->W = cfg->width;
   P->prec = cfg->precision == CP_PREC_BF16 ? 0 : (cfg->precision == CP_PREC_TF32X3 ? 1 : (cfg->precision == CP_PREC_TF32 ? 2 : -1));
   if (const char* e = getenv("CP_TMA_BASE_OFFSET")) P->tma_base_offset = atoi(e);
+  if (const char* e = getenv("CP_MIN_TC_CIN")) P->min_tc_cin = atoi(e);
   if (const char* e = getenv("CP_NO_DCN_TMA")) P->no_dcn_tma = atoi(e) != 0;
   CP_CUDA_CHECK(cudaSetDevice(cfg->device));
   int rc = build_graph(P.get());

@@ -117,9 +117,13 @@ def _flag(opt, name):
 
 
 class DLASegB200(nn.Module):
-    """B200-native DLASeg (pose_dla_dcn.py:457-570)."""
+    """B200-native DLASeg (pose_dla_dcn.py:457-570).
 
-    def __init__(self, heads, head_conv=256, use_convGRU=False, opt=None, precision="fp32"):
+    `precision` selects the kernels of the plan (include/centerpose_b200.h cp_precision): "tf32x3" (default: tcgen05
+    3-term split with promoted accumulation, fp32-equivalent - meets the same parity bar as "fp32"), "fp32" (CUDA-core
+    FFMA), "tf32" (tcgen05 single pass), "bf16"."""
+
+    def __init__(self, heads, head_conv=256, use_convGRU=False, opt=None, precision="tf32x3"):
         super().__init__()
         self.opt = opt
         self.heads = dict(heads)

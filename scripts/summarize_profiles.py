@@ -26,6 +26,9 @@ KEYS = [
     "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers",
     "launch__occupancy_limit_shared_mem", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
     "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "smsp__sass_inst_executed_op_shared_ld.sum", "smsp__sass_inst_executed_op_shared_st.sum",
 ]
 
 
@@ -63,20 +66,34 @@ def full(rep, tag, title, note=""):
             if k in d:
                 f.write("| %s | %s | %s |\n" % (k, d[k][0], d[k][1]))
         try:
-            rd = float(d["dram__bytes_read.sum"][0].replace(",", ""))
-            wr = float(d["dram__bytes_write.sum"][0].replace(",", ""))
-            f.write("\nDRAM traffic (read + write) = %.3f %s per launch.\n" % (rd + wr, d["dram__bytes_read.sum"][1]))
+            sc = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd = float(d["dram__bytes_read.sum"][0].replace(",", "")) * sc[d["dram__bytes_read.sum"][1]]
+            wr = float(d["dram__bytes_write.sum"][0].replace(",", "")) * sc[d["dram__bytes_write.sum"][1]]
+            f.write("\nDRAM traffic (read + write) = %.4f GB per launch.\n" % ((rd + wr) / 1e9))
         except Exception:
             pass
     print("wrote", "%s_%s_ncu.md" % (tag, name))
+    try:
+        return d["Kernel Name"][0], rd + wr, "byte"
+    except Exception:
+        return None
 
 
 if __name__ == "__main__":
+    # usage: summarize_profiles.py <tag> [file ...]   (files relative to gpurun_out/; default: everything there)
     tag = sys.argv[1]
     os.makedirs(OUT, exist_ok=True)
-    for fn in sorted(os.listdir(GP)):
+    files = sys.argv[2:] or sorted(os.listdir(GP))
+    traffic = {}
+    for fn in files:
         if fn.startswith("launches") and fn.endswith(".csv"):
             launches(os.path.join(GP, fn), tag + "_" + fn[:-4].replace("launches_", "").replace("launches", "bench"),
                      "Launch list, " + fn)
         if fn.endswith(".ncu-rep"):
-            full(os.path.join(GP, fn), tag, "ncu full capture: " + fn)
+            r = full(os.path.join(GP, fn), tag, "ncu full capture: " + fn)
+            if r:
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[2], 1.0)
+                traffic[fn[:-8]] = {"kernel": r[0], "dram_bytes_per_launch": r[1] * scale}
+    if traffic:
+        import json
+        json.dump(traffic, open(os.path.join(OUT, tag + "_ncu_traffic.json"), "w"), indent=1)

@@ -199,7 +199,7 @@ class DLASegB200(nn.Module):
         if device.type != "cuda":
             raise RuntimeError("centerpose_b200: the network only runs on CUDA (sm_100a); "
                                "there is no CPU fallback -- move the model with .to('cuda')")
-        key = (height, width, device.index if device.index is not None else torch.cuda.current_device())
+        key = (height, width, device.index if device.index is not None else torch.cuda.current_device(), self.precision)
         eng = self._engines.get(key)
         if eng is None or eng.max_batch < batch:
             if eng is not None:

@@ -36,6 +36,7 @@ struct TmaConvParams {
   int srcC[4];
   int B, H, W, Cin, Cout, CoutPad, BN;
   int k;              // 1 or 3
+  int tile_m;         // output positions per tile: 128 (x1) or 256 (x3: two M sub-tiles share every weight tile)
   int Wt, boxh;       // padded pitch and slab rows (k == 3)
   int tiles_per_image;
   long long total_tiles;                // cluster tiles: m groups x n tiles (n fastest)
@@ -66,7 +67,7 @@ struct TmaCtl {
   uint32_t tmem_base;
 };
 
-constexpr int TM_THREADS_X3 = 384;    // + warps 8-11: hi/lo splitters
+constexpr int TM_THREADS_X3 = 512;    // x3: warps 4-11 epilogue (two 128-row sub-tiles), warps 12-15 hi/lo splitters
 
 // Tile geometry of one 128-position output tile.
 struct TileGeo {
@@ -86,11 +87,11 @@ __device__ __forceinline__ TileGeo decode_tile(const TmaConvParams& p, long long
   g.pos0 = 0;
   if (p.k == 3) {
     g.img = (int)(m_tile / p.tiles_per_image);
-    g.g0 = (int)(m_tile - (long long)g.img * p.tiles_per_image) * TM_BM;
+    g.g0 = (int)(m_tile - (long long)g.img * p.tiles_per_image) * p.tile_m;
     const int t = g.g0 - 1;
     g.r_lo = (t >= 0) ? t / p.Wt : -((-t + p.Wt - 1) / p.Wt);      // floor((g0 - 1) / Wt)
   } else {
-    g.pos0 = m_tile * TM_BM;
+    g.pos0 = m_tile * p.tile_m;
   }
   return g;
 }
@@ -102,7 +103,10 @@ template <bool X3>
 __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmaConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   TmaCtl* ctl = reinterpret_cast<TmaCtl*>(smem);
-  const uint32_t slabs0 = (smem_u32(smem) + 512u + 4u * kStageFloatsPerWarp * 4u + 1023u) & ~1023u;
+  // x3 computes TWO 128-row M sub-tiles per weight tile (tile = 256 positions): the weight stream from L2, the measured
+  // limiter, is halved per MMA.  The sub-tiles are two accumulators side by side in TMEM and two sets of epilogue warps.
+  constexpr int MS = X3 ? 2 : 1;
+  const uint32_t slabs0 = (smem_u32(smem) + 512u + 1023u) & ~1023u;
   const uint32_t rowb = (uint32_t)p.cslab * 4u;                               // bytes per position row
   const int kslices = p.cslab / 8;                                            // tf32 MMA K = 8
   const uint32_t btile_bytes = (uint32_t)p.BN * rowb * (X3 ? 2u : 1u);         // hi (+ lo) weight tile
@@ -132,13 +136,13 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&ctl->p_full[s]), 1);       // x3: accumulation group ready / x1: tile accumulator ready
-      mbar_init(smem_u32(&ctl->p_empty[s]), 128);    // drained by the 128 epilogue threads
+      mbar_init(smem_u32(&ctl->p_empty[s]), 128 * MS);   // drained by the epilogue threads
     }
     fence_mbar_init();
   }
   // two TMEM accumulator buffers of BN columns: x1 ping-pongs whole tiles, x3 ping-pongs accumulation groups
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.BN * 2) tmem_cols <<= 1;
+  while ((int)tmem_cols < p.BN * 2 * MS) tmem_cols <<= 1;
   if (warp == 2) {
     tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     tmem_relinquish();
@@ -149,6 +153,11 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   if (p.cluster > 1) cluster_sync_all();       // remote arrives / multicast writes need every CTA's barriers initialised
   const uint32_t tmem_base = ctl->tmem_base;
 
+  // x3: 512 threads leave 128 registers per thread, but an epilogue thread carries the 128 promoted sums of its row.
+  // Warpgroup 0 (control warps) and 3 (splitters) hand registers to warpgroups 1-2 (epilogue) with setmaxnreg; the
+  // role code sits inside the branch that executed it so that ptxas allocates per branch.
+  if (warp < 4) {
+  if (X3) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ===================== activation slabs via TMA =====================
     if (lane == 0) {
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
             tc_fence_after();
             const uint64_t da = a_slab + (uint64_t)((uint32_t)(ky * p.Wt + kx) * rowu);
             const uint64_t db = dtmpl + (uint64_t)((btiles0 + (uint32_t)sb * btile_bytes) >> 4);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN * MS);
             const bool last = X3 ? (gk == group - 1 || kbi == KB - 1) : (kbi == KB - 1);
             const bool slab_done = (ky == p.k - 1) && (kx == p.k - 1);
             if (elect_one()) {
@@ -249,9 +258,14 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
                 if (ks < kslices) {
                   const uint32_t acc = (first && ks == 0) ? 0u : 1u;
                   if (X3) {
-                    umma_tf32(d_tmem, da + a_lo_u + 2 * ks, db + 2 * ks, idesc, acc);
-                    umma_tf32(d_tmem, da + 2 * ks, db + b_lo_u + 2 * ks, idesc, 1u);
-                    umma_tf32(d_tmem, da + 2 * ks, db + 2 * ks, idesc, 1u);
+#pragma unroll
+                    for (int sub = 0; sub < MS; ++sub) {          // rows [128 sub, 128 sub + 128) of the tile
+                      const uint64_t das = da + (uint64_t)(sub * (TM_BM * (int)rowu)) + 2 * ks;
+                      const uint32_t dt = d_tmem + (uint32_t)(sub * p.BN);
+                      umma_tf32(dt, das + a_lo_u, db + 2 * ks, idesc, acc);
+                      umma_tf32(dt, das, db + b_lo_u + 2 * ks, idesc, 1u);
+                      umma_tf32(dt, das, db + 2 * ks, idesc, 1u);
+                    }
                   } else {
                     umma_tf32(d_tmem, da + 2 * ks, db + 2 * ks, idesc, acc);
                   }
@@ -284,9 +298,11 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
         }
       }
     }
-  } else if (X3 && warp >= 8) {
+  }
+  } else if (X3 && warp >= 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     // ===================== hi / lo splitters (x3): slab -> tf32-exact hi (in place) + lo slab =====================
-    const int st = tid - 256;
+    const int st = tid - 384;
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t nchunk = p.slab_bytes >> 4;
@@ -321,12 +337,14 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 4 + 4 * MS) {
+    if (X3) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     // ===================== epilogue: TMEM lane == flattened output position =====================
-    const int q = warp & 3;
-    const int i = q * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* stage = reinterpret_cast<float*>(smem + 512) + q * kStageFloatsPerWarp;    // per-warp scratch (unused by the direct store path)
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int sub = (warp - 4) >> 2;              // M sub-tile (x3 only: 0 / 1)
+    const int i = sub * TM_BM + q * 32 + lane;    // position inside the tile
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * p.BN);
+    float* stage = nullptr;                       // (the direct store path needs no scratch)
     EpiParams ep;
     ep.bias = p.bias;
     ep.residual = p.residual;
@@ -380,7 +398,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
           for (int c = 0; c < 8; ++c) {
             if (c * 16 < p.BN) {
               uint32_t rr[16];
-              tmem_ld16(lane_base + (uint32_t)(buf * p.BN + c * 16), rr);
+              tmem_ld16(lane_base + (uint32_t)(buf * p.BN * MS + c * 16), rr);
               tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 16; ++j) sums[(X3 ? c * 16 + j : 0)] += __uint_as_float(rr[j]);
@@ -497,15 +515,18 @@ EncodeTiledFn get_encode() {
 // ---------------------------------------------------------------------------------------------------- host side
 // Channels per activation slab.  32 (128-byte rows) by default; 16 (64-byte rows, SWIZZLE_64B) when Cin is not a
 // multiple of 32, or when the 3-term split (hi + lo slabs) could not be double-buffered with 32-channel slabs.
+static int tma_tile_m(int x3) { return x3 ? 256 : TM_BM; }
+static int tma_boxh(int Wt, int x3) { return (tma_tile_m(x3) + 1 + 2 * Wt + Wt - 1) / Wt + 1; }
+
 int tma_cslab(const IgemmParams& p, int x3) {
   if (p.Cin % 32) return 16;
   if (!x3 || p.kh != 3) return 32;
   const int Wt = p.Win + 2;
-  const int boxh = (129 + 2 * Wt + Wt - 1) / Wt + 1;
+  const int boxh = tma_boxh(Wt, x3);
   const size_t slab32 = ((size_t)boxh * Wt * 128 + 1023) / 1024 * 1024;
   const int bn = p.CoutPad <= 128 ? p.CoutPad : 128;
   const size_t need = 2 * (2 * slab32) + 2 * ((size_t)bn * 128 * 2);
-  return need > (size_t)205 * 1024 ? 16 : 32;
+  return need > (size_t)222 * 1024 ? 16 : 32;
 }
 
 int tma_tile_n(int CoutPad, int x3) {
@@ -567,7 +588,7 @@ int tma_conv_encode(const IgemmParams& p, int Bmax, int x3, void* maps_out) {
   if (!enc) return fail(CP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(maps_out);
   const int Wt = p.Win + 2;
-  const int boxh = (129 + 2 * Wt + Wt - 1) / Wt + 1;
+  const int boxh = tma_boxh(Wt, x3);
   const int cs = tma_cslab(p, x3);
   const CUtensorMapSwizzle swz = cs == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   for (int s = 0; s < p.nsrc; ++s) {
@@ -584,7 +605,7 @@ int tma_conv_encode(const IgemmParams& p, int Bmax, int x3, void* maps_out) {
     } else {
       cuuint64_t dims[2] = {(cuuint64_t)p.srcC[s], (cuuint64_t)Bmax * p.Hin * p.Win};
       cuuint64_t strides[1] = {(cuuint64_t)p.srcStride[s] * 4};
-      cuuint32_t box[2] = {(cuuint32_t)cs, TM_BM};
+      cuuint32_t box[2] = {(cuuint32_t)cs, (cuuint32_t)tma_tile_m(x3)};
       cuuint32_t es[2] = {1, 1};
       r = enc(&maps[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p.src[s], dims, strides, box, es,
               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -615,21 +636,22 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.group = TM_GROUP_X3 * (32 / q.cslab);       // same number of MMAs per TMEM accumulation group
   q.k = p.kh;
   q.Wt = p.Win + 2;
-  q.boxh = (129 + 2 * q.Wt + q.Wt - 1) / q.Wt + 1;
+  q.tile_m = tma_tile_m(x3);
+  q.boxh = tma_boxh(q.Wt, x3);
   size_t m_tiles;
   if (q.k == 3) {
-    q.tiles_per_image = (p.Hin * q.Wt + TM_BM - 1) / TM_BM;
+    q.tiles_per_image = (p.Hin * q.Wt + q.tile_m - 1) / q.tile_m;
     m_tiles = (size_t)q.tiles_per_image * p.B;
     q.slab_bytes = (uint32_t)q.boxh * q.Wt * (uint32_t)q.cslab * 4u;
   } else {
     q.tiles_per_image = 0;
-    m_tiles = ((size_t)p.B * p.Hin * p.Win + TM_BM - 1) / TM_BM;
-    q.slab_bytes = TM_BM * (uint32_t)q.cslab * 4u;
+    m_tiles = ((size_t)p.B * p.Hin * p.Win + q.tile_m - 1) / q.tile_m;
+    q.slab_bytes = (uint32_t)q.tile_m * (uint32_t)q.cslab * 4u;
   }
   q.slab_stride = (q.slab_bytes + 1023u) & ~1023u;
   const uint32_t btile = (uint32_t)q.BN * (uint32_t)q.cslab * 4u * (x3 ? 2u : 1u);
   const uint32_t a_stage = q.slab_stride * (x3 ? 2u : 1u);
-  const size_t budget = 205 * 1024;
+  const size_t budget = 222 * 1024;
   q.SA = 2;
   if ((size_t)q.SA * a_stage + 2 * btile > budget) q.SA = 1;
   if ((size_t)q.SA * a_stage + 2 * btile > budget) return fail(CP_ERR_INVALID, "conv_tma: slab does not fit shared memory");
@@ -654,7 +676,7 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.round_tf32 = round_out_tf32;
   q.use_base_offset = use_base_offset;
   q.wtiles = (const unsigned char*)p.wgt_umma;
-  const size_t smem = 512 + 4 * umma::kStageFloatsPerWarp * 4 + 2048 + (size_t)q.SA * a_stage + (size_t)q.SB * btile;
+  const size_t smem = 512 + 2048 + (size_t)q.SA * a_stage + (size_t)q.SB * btile;
   static thread_local bool configured[2] = {false, false};
   if (!configured[x3 ? 1 : 0]) {
     if (x3)

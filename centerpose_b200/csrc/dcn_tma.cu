@@ -9,11 +9,11 @@
 // offsets are small, so here the rows a tile can reach are STAGED ONCE in shared memory by TMA and the corners are
 // gathered from shared memory:
 //
-//   tile    = 128 consecutive output positions = R = 128 / W full rows of one image (W in {16, 32, 64, 128})
-//   slab    = 16 channels x W columns x (R + 6) rows  [rows y0-3 .. y0+R+2, zero-filled outside the image],
+//   tile    = an 8 x 16 patch of output positions of one image (128 positions = the 128 TMEM lanes)
+//   slab    = 16 channels x 32 columns x 24 rows around it (halo 8 in x and y, zero-filled outside the image),
 //             64 bytes per position in TMA SWIZZLE_64B order (conflict-free 16-byte gathers); double buffered
 //   K order = slab-major, tap-minor (the weight tiles of conv_tma.cu with 16-channel slabs are reused unchanged)
-//   samples whose corner rows fall outside the slab (|dy| > ~2) are fetched from global memory instead - slow path,
+//   samples with a corner outside the slab (|offset| > ~7 px) are fetched from global memory instead - slow path,
 //   same arithmetic, so the result never depends on how large the offsets are.
 //
 //   warp 0      : TMA producer for slabs
@@ -39,7 +39,10 @@ using namespace umma;
 constexpr int DT_BM = 128;
 constexpr int DT_THREADS = 512;
 constexpr int DT_CS = 16;            // channels per slab = one UMMA K block of 64-byte rows
-constexpr int DT_HALO = 3;           // slab rows above / below the tile
+constexpr int DT_PH = 8, DT_PW = 16;  // output patch (rows x columns) = 128 positions
+constexpr int DT_HALO = 8;           // slab margin around the patch, both directions
+constexpr int DT_SH = DT_PH + 2 * DT_HALO, DT_SW = DT_PW + 2 * DT_HALO;     // slab rows x columns (24 x 32)
+constexpr uint32_t DT_SLAB_BYTES = DT_SH * DT_SW * DT_CS * 4;               // 49152
 constexpr int DT_GROUP = 6;          // x3: K blocks per TMEM accumulation group (= 36 MMAs, as in conv_tma.cu)
 constexpr uint32_t DT_COEF_BYTES = DT_BM * 9 * 16;
 
@@ -50,10 +53,8 @@ struct DcnTmaParams {
   const float* offmask;
   int omStride, mask_is_logit;
   int B, H, W, Cin, Cout, CoutPad, BN;
-  int R, SR, logW;                   // image rows per tile, slab rows, log2(W)
-  int tiles_per_image;
+  int tiles_x, tiles_per_image;      // patches per image row / per image
   long long total_tiles;             // m tiles x n tiles (n fastest)
-  uint32_t slab_bytes, slab_stride;
   int SB;
   const float* bias;
   const float* residual;
@@ -81,7 +82,7 @@ constexpr int RB_DX = 14, RB_DY = 15, RB_W = 16, RB_SLAB = 20, RB_LIVE = 21;
 // Sampling records of one output position (all 9 taps) -> shared memory.  dcn_v2_im2col_cuda.cu:160-195: the sample
 // (h_im, w_im) is used only when it lies in (-1, H) x (-1, W); every corner carries its own bounds test.
 __device__ __forceinline__ void coef_row(const DcnTmaParams& p, const float* __restrict__ om, int oy, int ox, int ys,
-                                         uint32_t dst) {
+                                         int xs, uint32_t dst) {
   float o[27];
 #pragma unroll
   for (int j = 0; j < 27; ++j) o[j] = __ldg(om + j);
@@ -101,8 +102,8 @@ __device__ __forceinline__ void coef_row(const DcnTmaParams& p, const float* __r
       const bool t_ok = h_low >= 0, b_ok = h_low + 1 <= H - 1, l_ok = w_low >= 0, r_ok = w_low + 1 <= W - 1;
       const int hl = t_ok ? h_low : 0, hb = b_ok ? h_low + 1 : H - 1;
       const int wl = l_ok ? w_low : 0, wr = r_ok ? w_low + 1 : W - 1;
-      const bool in_slab = (hl >= ys) && (hb < ys + p.SR);
-      pk = in_slab ? (uint32_t)((hl - ys) * W + wl) : (uint32_t)((hl << 7) | wl);
+      const bool in_slab = (hl >= ys) && (hb < ys + DT_SH) && (wl >= xs) && (wr < xs + DT_SW);
+      pk = in_slab ? (uint32_t)((hl - ys) * DT_SW + (wl - xs)) : (uint32_t)((hl << 7) | wl);
       pk |= (uint32_t)(wr - wl) << RB_DX;
       pk |= (uint32_t)(hb - hl) << RB_DY;
       pk |= (uint32_t)((t_ok && l_ok) ? 1 : 0) << (RB_W + 0);
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
   const uint32_t coef0 = sbase + 1024u;
   const uint32_t slabs0 = (coef0 + 2u * DT_COEF_BYTES + 1023u) & ~1023u;
   const uint32_t a_stage = X3 ? 16384u : 8192u;                // hi (+ lo) tile of 128 rows x 64 bytes
-  const uint32_t atiles0 = slabs0 + 2u * p.slab_stride;
+  const uint32_t atiles0 = slabs0 + 2u * DT_SLAB_BYTES;
   const uint32_t btile_bytes = (uint32_t)p.BN * 64u * (X3 ? 2u : 1u);
   const uint32_t btiles0 = atiles0 + 2u * a_stage;
 
@@ -172,12 +173,13 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const long long m_tile = tile / n_tiles;
         const int img = (int)(m_tile / p.tiles_per_image);
-        const int y0 = (int)(m_tile - (long long)img * p.tiles_per_image) * p.R;
+        const int pt = (int)(m_tile - (long long)img * p.tiles_per_image);
+        const int y0 = (pt / p.tiles_x) * DT_PH, x0 = (pt % p.tiles_x) * DT_PW;
         for (int s = 0; s < nslab; ++s) {
           mbar_wait(smem_u32(&ctl->s_empty[stage]), phase ^ 1u);
           const uint32_t bar = smem_u32(&ctl->s_full[stage]);
-          mbar_arrive_expect_tx(bar, p.slab_bytes);
-          tma_load_4d(slabs0 + (uint32_t)stage * p.slab_stride, &p.amap, s * DT_CS, 0, y0 - DT_HALO, img, bar);
+          mbar_arrive_expect_tx(bar, DT_SLAB_BYTES);
+          tma_load_4d(slabs0 + (uint32_t)stage * DT_SLAB_BYTES, &p.amap, s * DT_CS, x0 - DT_HALO, y0 - DT_HALO, img, bar);
           if (++stage == 2) {
             stage = 0;
             phase ^= 1u;
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
             }
           }
           mbar_wait(smem_u32(&ctl->s_full[ss]), ps);
-          slab = slabs0 + (uint32_t)ss * p.slab_stride;
+          slab = slabs0 + (uint32_t)ss * DT_SLAB_BYTES;
           cur = s;
         }
         const float4 rec = ld_shared_v4f(crow + (uint32_t)t * 16u);
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
           if ((pk >> RB_SLAB) & 1u) {
             // slab rows are 64 bytes in TMA SWIZZLE_64B order: 16-byte chunk c of position q sits at c ^ ((q >> 1) & 3)
             const uint32_t q1 = pk & 0x3FFFu, q2 = q1 + ((pk >> RB_DX) & 1u);
-            const uint32_t q3 = q1 + ((pk >> RB_DY) & 1u) * (uint32_t)p.W, q4 = q3 + ((pk >> RB_DX) & 1u);
+            const uint32_t q3 = q1 + ((pk >> RB_DY) & 1u) * (uint32_t)DT_SW, q4 = q3 + ((pk >> RB_DX) & 1u);
             const uint32_t b1 = slab + q1 * 64u, b2 = slab + q2 * 64u, b3 = slab + q3 * 64u, b4 = slab + q4 * 64u;
             const uint32_t s1 = (q1 >> 1) & 3u, s2 = (q2 >> 1) & 3u, s3 = (q3 >> 1) & 3u, s4 = (q4 >> 1) & 3u;
 #pragma unroll
@@ -406,9 +408,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
     auto make_records = [&](long long t) {
       const long long mt = t / n_tiles;
       const int im = (int)(mt / p.tiles_per_image);
-      const int y0 = (int)(mt - (long long)im * p.tiles_per_image) * p.R;
+      const int pt = (int)(mt - (long long)im * p.tiles_per_image);
+      const int y0 = (pt / p.tiles_x) * DT_PH, x0 = (pt % p.tiles_x) * DT_PW;
+      const int oy = y0 + (i >> 4), ox = x0 + (i & 15);
       mbar_wait(smem_u32(&ctl->c_empty[cb]), pc ^ 1u);
-      coef_row(p, p.offmask + (size_t)(mt * DT_BM + i) * p.omStride, y0 + (i >> p.logW), i & (p.W - 1), y0 - DT_HALO,
+      coef_row(p, p.offmask + ((size_t)((size_t)im * p.H + oy) * p.W + ox) * p.omStride, oy, ox, y0 - DT_HALO, x0 - DT_HALO,
                coef0 + (uint32_t)cb * DT_COEF_BYTES + (uint32_t)i * 144u);
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&ctl->c_full[cb]));
@@ -423,9 +427,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
       const int n_tile = (int)(tile % n_tiles);
       const long long m_tile = tile / n_tiles;
       const int n = (int)(m_tile / p.tiles_per_image);
-      const int pix = (int)(m_tile - (long long)n * p.tiles_per_image) * DT_BM + i;
-      const int oy = pix / p.W, ox = pix - oy * p.W;
-      const int m = (int)(m_tile * DT_BM + i);
+      const int pt = (int)(m_tile - (long long)n * p.tiles_per_image);
+      const int oy = (pt / p.tiles_x) * DT_PH + (i >> 4), ox = (pt % p.tiles_x) * DT_PW + (i & 15);
+      const int m = (n * p.H + oy) * p.W + ox;
       const int col_end = min(p.Cout, (n_tile + 1) * p.BN);
       if (X3) {
         float sums[X3 ? 64 : 1];
@@ -493,20 +497,6 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-struct DcnGeo {
-  int R, SR;
-  uint32_t slab_bytes, slab_stride;
-};
-
-DcnGeo dcn_geo(int W) {
-  DcnGeo g;
-  g.R = DT_BM / W;
-  g.SR = g.R + 2 * DT_HALO;
-  g.slab_bytes = (uint32_t)g.SR * W * DT_CS * 4u;
-  g.slab_stride = (g.slab_bytes + 1023u) & ~1023u;
-  return g;
-}
-
 }  // namespace
 
 int dcn_tma_tile_n(int CoutPad, int x3) {
@@ -519,15 +509,14 @@ bool dcn_tma_supported(const IgemmParams& p, int x3) {
   if (p.kh != 3 || p.kw != 3 || p.stride != 1 || p.pad != 1) return false;
   if (p.Cin % DT_CS || p.srcStride[0] % 4) return false;
   const int W = p.Win, H = p.Hin;
-  if (W < 16 || W > 128 || (DT_BM % W) || H > 128 || ((H * W) % DT_BM)) return false;
+  if (W > 128 || H > 128 || (W % DT_PW) || (H % DT_PH)) return false;     // records pack image coordinates in 7 bits
   const int bn = dcn_tma_tile_n(p.CoutPad, x3);
   if (bn % 16 || p.CoutPad % bn) return false;
   return true;
 }
 
 int dcn_tma_encode(const IgemmParams& p, int Bmax, void* map_out) {
-  const DcnGeo g = dcn_geo(p.Win);
-  return tma_encode_nhwc_box(p.src[0], p.srcC[0], p.Win, p.Hin, Bmax, p.srcStride[0], DT_CS, p.Win, g.SR, 1, map_out);
+  return tma_encode_nhwc_box(p.src[0], p.srcC[0], p.Win, p.Hin, Bmax, p.srcStride[0], DT_CS, DT_SW, DT_SH, 1, map_out);
 }
 
 int launch_dcn_tma(const IgemmParams& p, const void* map, int x3, int round_out_tf32, cudaStream_t stream) {
@@ -536,7 +525,6 @@ int launch_dcn_tma(const IgemmParams& p, const void* map, int x3, int round_out_
   DcnTmaParams q;
   memset(&q, 0, sizeof(q));
   memcpy(&q.amap, map, sizeof(CUtensorMap));
-  const DcnGeo g = dcn_geo(p.Win);
   q.src = p.src[0];
   q.srcStride = p.srcStride[0];
   q.offmask = p.offmask;
@@ -549,17 +537,12 @@ int launch_dcn_tma(const IgemmParams& p, const void* map, int x3, int round_out_
   q.Cout = p.Cout;
   q.CoutPad = p.CoutPad;
   q.BN = dcn_tma_tile_n(p.CoutPad, x3);
-  q.R = g.R;
-  q.logW = 0;
-  while ((1 << q.logW) < p.Win) ++q.logW;
-  q.SR = g.SR;
-  q.tiles_per_image = p.Hin * p.Win / DT_BM;
+  q.tiles_x = p.Win / DT_PW;
+  q.tiles_per_image = q.tiles_x * (p.Hin / DT_PH);
   q.total_tiles = (long long)q.tiles_per_image * p.B * (p.CoutPad / q.BN);
-  q.slab_bytes = g.slab_bytes;
-  q.slab_stride = g.slab_stride;
   const uint32_t a_stage = x3 ? 16384u : 8192u;
   const uint32_t btile = (uint32_t)q.BN * 64u * (x3 ? 2u : 1u);
-  const size_t fixed = 1024 + 2 * (size_t)DT_COEF_BYTES + 1024 + 2 * (size_t)g.slab_stride + 2 * (size_t)a_stage;
+  const size_t fixed = 1024 + 2 * (size_t)DT_COEF_BYTES + 1024 + 2 * (size_t)DT_SLAB_BYTES + 2 * (size_t)a_stage;
   const size_t budget = 226 * 1024;
   if (fixed + 2 * (size_t)btile > budget) return fail(CP_ERR_INVALID, "dcn_tma: tile does not fit shared memory");
   q.SB = (int)((budget - fixed) / btile);

@@ -24,7 +24,7 @@
 //                 Thread i also writes the sampling records (one 16-byte record per tap) of position i of the NEXT tile
 //   warps 8-15  : gather, one thread per position: 4 corners x 16 channels from the slab -> bilinear blend * mask ->
 //                 (hi, lo) tf32 split -> A tile in the UMMA SWIZZLE_64B K-major layout; warps 8-11 / 12-15 take
-//                 alternate K blocks and own one A stage each
+//                 alternate K blocks and own two A stages each
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -67,7 +67,7 @@ struct DcnTmaParams {
 
 struct DcnCtl {
   unsigned long long s_full[2], s_empty[2];
-  unsigned long long a_full[2], a_empty[2];
+  unsigned long long a_full[4], a_empty[4];       // stages 2h, 2h+1 belong to gather half h
   unsigned long long c_full[2], c_empty[2];
   unsigned long long b_full[8], b_empty[8];
   unsigned long long p_full[2], p_empty[2];
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
   const uint32_t a_stage = X3 ? 16384u : 8192u;                // hi (+ lo) tile of 128 rows x 64 bytes
   const uint32_t atiles0 = slabs0 + 2u * DT_SLAB_BYTES;
   const uint32_t btile_bytes = (uint32_t)p.BN * 64u * (X3 ? 2u : 1u);
-  const uint32_t btiles0 = atiles0 + 2u * a_stage;
+  const uint32_t btiles0 = atiles0 + 4u * a_stage;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = p.CoutPad / p.BN;
@@ -141,8 +141,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&ctl->s_full[s]), 1);
       mbar_init(smem_u32(&ctl->s_empty[s]), 8);      // one arrival per gather warp
-      mbar_init(smem_u32(&ctl->a_full[s]), 4);       // stage s is written by gather warps 8+4s .. 11+4s
+      mbar_init(smem_u32(&ctl->a_full[s]), 4);       // written by the four gather warps of one half
       mbar_init(smem_u32(&ctl->a_empty[s]), 1);
+      mbar_init(smem_u32(&ctl->a_full[2 + s]), 4);
+      mbar_init(smem_u32(&ctl->a_empty[2 + s]), 1);
       mbar_init(smem_u32(&ctl->c_full[s]), 4);       // one arrival per epilogue warp
       mbar_init(smem_u32(&ctl->c_empty[s]), 8);
       mbar_init(smem_u32(&ctl->p_full[s]), 1);
@@ -215,14 +217,17 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
     const uint64_t dtmpl = make_desc(0, 0, DT_CS);
     const uint32_t a_lo_u = 8192u >> 4;
     const uint32_t b_lo_u = ((uint32_t)p.BN * 64u) >> 4;
-    int sa = 0, sb = 0, buf = 0;
-    uint32_t pa = 0, pb = 0, pe = 0;
+    int sb = 0, buf = 0;
+    uint32_t pb = 0, pe = 0;
+    uint32_t cnt0 = 0, cnt1 = 0;          // K blocks consumed from gather half 0 / 1 (K block kbi of a tile belongs to half kbi & 1)
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int gk = 0;
       for (int kbi = 0; kbi < KB; ++kbi) {
         const bool first = X3 ? (gk == 0) : (kbi == 0);
         if (first) mbar_wait(smem_u32(&ctl->p_empty[buf]), ((pe >> buf) & 1u) ^ 1u);
-        mbar_wait(smem_u32(&ctl->a_full[sa]), pa);
+        const uint32_t hcnt = (kbi & 1) ? cnt1 : cnt0;
+        const int sa = (kbi & 1) * 2 + (int)(hcnt & 1u);
+        mbar_wait(smem_u32(&ctl->a_full[sa]), (hcnt >> 1) & 1u);
         mbar_wait(smem_u32(&ctl->b_full[sb]), pb);
         tc_fence_after();
         const uint64_t da = dtmpl + (uint64_t)((atiles0 + (uint32_t)sa * a_stage) >> 4);
@@ -250,10 +255,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
           sb = 0;
           pb ^= 1u;
         }
-        if (++sa == 2) {
-          sa = 0;
-          pa ^= 1u;
-        }
+        if (kbi & 1)
+          ++cnt1;
+        else
+          ++cnt0;
         if (last) {
           pe ^= 1u << buf;
           buf ^= 1;
@@ -272,11 +277,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
     const int gt = tid - 256;
     const int half = gt >> 7;
     const int row = gt & 127;
-    const uint32_t a_hi = atiles0 + (uint32_t)half * a_stage + (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 64u;
+    const uint32_t a_row = atiles0 + (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 64u;
     const uint32_t asw = (uint32_t)(row >> 1) & 3u;
-    const uint32_t a_full_bar = smem_u32(&ctl->a_full[half]), a_empty_bar = smem_u32(&ctl->a_empty[half]);
     int ss = 0, cb = 0;
-    uint32_t ps = 0, pa = 0, pc = 0;
+    uint32_t ps = 0, pc = 0;
+    uint32_t cnt = 0;                      // K blocks this half has produced; stage = 2 half + (cnt & 1)
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const long long m_tile = tile / n_tiles;
       const int img = (int)(m_tile / p.tiles_per_image);
@@ -347,7 +352,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
             }
           }
         }
-        mbar_wait(a_empty_bar, pa ^ 1u);
+        const int sa = half * 2 + (int)(cnt & 1u);
+        const uint32_t a_hi = a_row + (uint32_t)sa * a_stage;
+        mbar_wait(smem_u32(&ctl->a_empty[sa]), ((cnt >> 1) & 1u) ^ 1u);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const uint32_t off = ((uint32_t)c ^ asw) << 4;
@@ -363,8 +370,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_full_bar);
-        pa ^= 1u;
+        if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[sa]));
+        ++cnt;
       }
       __syncwarp();
       if (lane == 0) {
@@ -542,7 +549,7 @@ int launch_dcn_tma(const IgemmParams& p, const void* map, int x3, int round_out_
   q.total_tiles = (long long)q.tiles_per_image * p.B * (p.CoutPad / q.BN);
   const uint32_t a_stage = x3 ? 16384u : 8192u;
   const uint32_t btile = (uint32_t)q.BN * 64u * (x3 ? 2u : 1u);
-  const size_t fixed = 1024 + 2 * (size_t)DT_COEF_BYTES + 1024 + 2 * (size_t)DT_SLAB_BYTES + 2 * (size_t)a_stage;
+  const size_t fixed = 1024 + 2 * (size_t)DT_COEF_BYTES + 1024 + 2 * (size_t)DT_SLAB_BYTES + 4 * (size_t)a_stage;
   const size_t budget = 226 * 1024;
   if (fixed + 2 * (size_t)btile > budget) return fail(CP_ERR_INVALID, "dcn_tma: tile does not fit shared memory");
   q.SB = (int)((budget - fixed) / btile);

@@ -90,7 +90,8 @@ def test_dcn_tma_staged(prec, off_std, cplib):
     from oracle import net_ref
     g = torch.Generator().manual_seed(23)
     for (B, C, H, W, Co) in ((2, 64, 16, 16, 64), (1, 32, 8, 32, 48), (1, 128, 8, 64, 128), (1, 16, 8, 128, 16),
-                             (2, 64, 24, 48, 64), (3, 64, 32, 32, 256)):
+                             (2, 64, 24, 48, 64), (3, 64, 32, 32, 256),
+                             (4, 48, 64, 128, 32)):     # 256 tiles > 148 CTAs with an odd number of K blocks
         x = torch.randn(B, C, H, W, generator=g)
         off = torch.randn(B, 18, H, W, generator=g) * off_std
         mask = torch.rand(B, 9, H, W, generator=g)

@@ -68,6 +68,8 @@ struct IgemmParams {
 int launch_igemm_fp32(const IgemmParams& p, cudaStream_t stream);
 
 // dedicated 7x7 stem kernel (stem_conv.cu); consumes the same packed fp32 weights as the generic kernel
+bool conv3_c16_supported(const IgemmParams& p);     // direct 3x3 16 -> 16 NHWC convolution (stem_conv.cu)
+int launch_conv3_c16(const IgemmParams& p, cudaStream_t stream);
 bool stem_supported(const IgemmParams& p);
 int launch_stem_conv(const IgemmParams& p, cudaStream_t s);
 

@@ -72,7 +72,7 @@ static int prec_code(int32_t precision, int* prec) {
 
 // run one implicit-GEMM launch with the kernel family selected by `prec` (weights already packed as fp32 [K][CoutPad])
 static int run_igemm(IgemmParams& p, int prec, int Kreal, cudaStream_t s) {
-  if (prec < 0) return launch_igemm_fp32(p, s);
+  if (prec < 0) return conv3_c16_supported(p) ? launch_conv3_c16(p, s) : launch_igemm_fp32(p, s);
   if (prec == 2 || prec == 1) {
     const int x3 = prec == 1;
     const char* force_gather = getenv("CP_FORCE_GATHER");

@@ -841,6 +841,8 @@ static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* 
           if ((rc = launch_igemm_umma(p, P->prec == 2 ? 1 : P->prec, s))) return rc;
         } else if (stem_supported(p)) {
           if ((rc = launch_stem_conv(p, s))) return rc;
+        } else if (conv3_c16_supported(p)) {
+          if ((rc = launch_conv3_c16(p, s))) return rc;
         } else if ((rc = launch_igemm_fp32(p, s))) {
           return rc;
         }

@@ -40,6 +40,7 @@ CONV_SHAPES = [
     (3, 16, 16, 64, 512, 3, 1, 1, True, False),       # 2 N tiles of 256, merged-heads-like
     (1, 8, 8, 512, 256, 3, 1, 1, True, False),        # long K (72 / 144 K blocks)
     (2, 24, 40, 16, 16, 3, 1, 1, True, False),        # level0: 16 -> 16 (64-byte rows / SWIZZLE_64B on the TMA path)
+    (1, 20, 150, 16, 16, 3, 1, 1, False, False),      # level0 over several 64 x 16 tiles of the direct kernel (fp32 leg)
     (2, 16, 16, 128, 128, 3, 1, 1, True, True),       # BasicBlock conv2 with residual through the coalesced loader
     (1, 32, 32, 192, 64, 1, 1, 0, True, False),       # root-like 1x1 over a wide input
 ]

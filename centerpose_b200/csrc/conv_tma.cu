@@ -545,6 +545,11 @@ bool tma_conv_supported(const IgemmParams& p, int x3) {
   if (p.kh == 3 && p.Win + 2 > 256) return false;
   const int bn = tma_tile_n(p.CoutPad, x3);
   if (bn % 16 || p.CoutPad % bn) return false;
+  // one single-buffered slab stage (+ its lo copy in x3) and two weight tiles must fit shared memory
+  const size_t slab = p.kh == 3 ? (size_t)tma_boxh(p.Win + 2, x3) * (p.Win + 2) * cs * 4 : (size_t)tma_tile_m(x3) * cs * 4;
+  const size_t a_stage = ((slab + 1023) / 1024 * 1024) * (x3 ? 2 : 1);
+  const size_t btile = (size_t)bn * cs * 4 * (x3 ? 2 : 1);
+  if (a_stage + 2 * btile > (size_t)222 * 1024) return false;
   return get_encode() != nullptr;
 }
 

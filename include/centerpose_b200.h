@@ -66,11 +66,12 @@ enum cp_arch {
 
 enum cp_precision {
   CP_PREC_FP32 = 0,         /* fp32 operands and accumulation on CUDA cores (parity mode)      */
-  CP_PREC_TF32X3 = 1,       /* tcgen05 kind::tf32, 3-term split: fp32-equivalent tensor cores  */
+  CP_PREC_TF32X3 = 1,       /* tcgen05 kind::tf32, 3-term split + promoted accumulation: fp32-equivalent
+                             * tensor-core mode, meets the same parity bar as CP_PREC_FP32; the Python host's
+                             * default                                                                      */
   CP_PREC_BF16 = 2,         /* tcgen05 kind::f16 bf16 operands, fp32 accumulation (fast mode)  */
-  CP_PREC_TF32 = 3          /* tcgen05 kind::tf32 single pass, TMA-fed where the op allows it -- the math
-                             * PyTorch's cuDNN convolutions use by default (allow_tf32); deformable / strided
-                             * ops run the 3-term split kernel                                             */
+  CP_PREC_TF32 = 3          /* tcgen05 kind::tf32 single pass -- the math PyTorch's cuDNN convolutions use by
+                             * default (allow_tf32); stride-2 convs run the 3-term split gather kernel     */
 };
 
 #define CP_MAX_HEADS 16

@@ -56,6 +56,7 @@ struct DcnTmaParams {
   int tiles_x, tiles_per_image;      // patches per image row / per image
   long long total_tiles;             // m tiles x n tiles (n fastest)
   int SB;
+  int AH;                            // A stages per gather half (1 or 2)
   const float* bias;
   const float* residual;
   int resStride, relu, res_after_relu;
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
   const uint32_t a_stage = X3 ? 16384u : 8192u;                // hi (+ lo) tile of 128 rows x 64 bytes
   const uint32_t atiles0 = slabs0 + 2u * DT_SLAB_BYTES;
   const uint32_t btile_bytes = (uint32_t)p.BN * 64u * (X3 ? 2u : 1u);
-  const uint32_t btiles0 = atiles0 + 4u * a_stage;
+  const uint32_t btiles0 = atiles0 + 2u * (uint32_t)p.AH * a_stage;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = p.CoutPad / p.BN;
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
     fence_mbar_init();
   }
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.BN * 2) tmem_cols <<= 1;
+  while ((int)tmem_cols < p.BN * (X3 ? 3 : 2)) tmem_cols <<= 1;     // x3: + BN columns of promoted sums
   if (warp == 2) {
     tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     tmem_relinquish();
@@ -226,11 +227,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
         const bool first = X3 ? (gk == 0) : (kbi == 0);
         if (first) mbar_wait(smem_u32(&ctl->p_empty[buf]), ((pe >> buf) & 1u) ^ 1u);
         const uint32_t hcnt = (kbi & 1) ? cnt1 : cnt0;
-        const int sa = (kbi & 1) * 2 + (int)(hcnt & 1u);
-        mbar_wait(smem_u32(&ctl->a_full[sa]), (hcnt >> 1) & 1u);
+        const int sa = (kbi & 1) * 2 + (int)(hcnt & (uint32_t)(p.AH - 1));
+        mbar_wait(smem_u32(&ctl->a_full[sa]), (hcnt >> (p.AH - 1)) & 1u);
         mbar_wait(smem_u32(&ctl->b_full[sb]), pb);
         tc_fence_after();
-        const uint64_t da = dtmpl + (uint64_t)((atiles0 + (uint32_t)sa * a_stage) >> 4);
+        const uint64_t da = dtmpl + (uint64_t)((atiles0 + (uint32_t)((kbi & 1) * p.AH + (sa & 1)) * a_stage) >> 4);
         const uint64_t db = dtmpl + (uint64_t)((btiles0 + (uint32_t)sb * btile_bytes) >> 4);
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
         const bool last = X3 ? (gk == DT_GROUP - 1 || kbi == KB - 1) : (kbi == KB - 1);
@@ -352,9 +353,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
             }
           }
         }
-        const int sa = half * 2 + (int)(cnt & 1u);
-        const uint32_t a_hi = a_row + (uint32_t)sa * a_stage;
-        mbar_wait(smem_u32(&ctl->a_empty[sa]), ((cnt >> 1) & 1u) ^ 1u);
+        const int sa = half * 2 + (int)(cnt & (uint32_t)(p.AH - 1));          // barrier index; tile slot = half * AH + (sa & 1)
+        const uint32_t a_hi = a_row + (uint32_t)(half * p.AH + (sa & 1)) * a_stage;
+        mbar_wait(smem_u32(&ctl->a_empty[sa]), ((cnt >> (p.AH - 1)) & 1u) ^ 1u);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const uint32_t off = ((uint32_t)c ^ asw) << 4;
@@ -439,37 +440,45 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
       const int m = (n * p.H + oy) * p.W + ox;
       const int col_end = min(p.Cout, (n_tile + 1) * p.BN);
       if (X3) {
-        float sums[X3 ? 64 : 1];
-#pragma unroll
-        for (int j = 0; j < (X3 ? 64 : 1); ++j) sums[j] = 0.f;
+        // two-level accumulation (see conv_tma.cu): every finished group of <= 36 MMAs is added, with round-to-nearest,
+        // into running sums.  The sums live in a third TMEM region (columns [2 BN, 3 BN)) instead of registers, so the
+        // tile can be 128 columns wide with 128 epilogue threads: ld group + ld sum -> add -> st sum, 16 columns at a time.
+        const uint32_t sum_base = lane_base + (uint32_t)(2 * p.BN);
         const int ngroups = (KB + DT_GROUP - 1) / DT_GROUP;
         for (int gi = 0; gi < ngroups; ++gi) {
           mbar_wait(smem_u32(&ctl->p_full[buf]), (pf >> buf) & 1u);
           tc_fence_after();
+          for (int c = 0; c * 16 < p.BN; ++c) {
+            uint32_t rr[16], ss[16];
+            tmem_ld16(lane_base + (uint32_t)(buf * p.BN + c * 16), rr);
+            if (gi > 0) tmem_ld16(sum_base + (uint32_t)(c * 16), ss);
+            tmem_ld_wait();
+            if (gi > 0) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c * 16 < p.BN) {
-              uint32_t rr[16];
-              tmem_ld16(lane_base + (uint32_t)(buf * p.BN + c * 16), rr);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) sums[(X3 ? c * 16 + j : 0)] += __uint_as_float(rr[j]);
+              for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(__uint_as_float(ss[j]) + __uint_as_float(rr[j]));
             }
+            tmem_st16(sum_base + (uint32_t)(c * 16), rr);
           }
+          tmem_st_wait();
           tc_fence_before();
           mbar_arrive(smem_u32(&ctl->p_empty[buf]));
           pf ^= 1u << buf;
           buf ^= 1;
         }
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          uint32_t rr[32];
+          tmem_ld16(sum_base + (uint32_t)c0, rr);
+          if (c0 + 16 < p.BN) {
+            tmem_ld16(sum_base + (uint32_t)(c0 + 16), rr + 16);
+          } else {
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c0 = cc * 32;
-          if (c0 < p.BN) {
-            float vv[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) vv[j] = sums[(X3 ? cc * 32 + j : 0)];
-            epilogue_sub_tile(ep, nullptr, vv, lane, true, m, n, oy, ox, n_tile * p.BN + c0, col_end);
+            for (int j = 16; j < 32; ++j) rr[j] = 0u;
           }
+          tmem_ld_wait();
+          float vv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(rr[j]);
+          epilogue_sub_tile(ep, nullptr, vv, lane, true, m, n, oy, ox, n_tile * p.BN + c0, col_end);
         }
       } else {
         mbar_wait(smem_u32(&ctl->p_full[buf]), (pf >> buf) & 1u);
@@ -507,7 +516,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
 }  // namespace
 
 int dcn_tma_tile_n(int CoutPad, int x3) {
-  const int cap = x3 ? 64 : 256;      // x3: the promoted sums of one position live in 64 registers (512 threads / CTA)
+  const int cap = x3 ? 128 : 256;     // x3: 2 BN columns of group accumulators + BN columns of promoted sums <= 512
   return CoutPad <= cap ? CoutPad : cap;
 }
 
@@ -548,8 +557,9 @@ int launch_dcn_tma(const IgemmParams& p, const void* map, int x3, int round_out_
   q.tiles_per_image = q.tiles_x * (p.Hin / DT_PH);
   q.total_tiles = (long long)q.tiles_per_image * p.B * (p.CoutPad / q.BN);
   const uint32_t a_stage = x3 ? 16384u : 8192u;
+  q.AH = x3 ? 1 : 2;                  // shared memory: x3 tiles are twice as large
   const uint32_t btile = (uint32_t)q.BN * 64u * (x3 ? 2u : 1u);
-  const size_t fixed = 1024 + 2 * (size_t)DT_COEF_BYTES + 1024 + 2 * (size_t)DT_SLAB_BYTES + 4 * (size_t)a_stage;
+  const size_t fixed = 1024 + 2 * (size_t)DT_COEF_BYTES + 1024 + 2 * (size_t)DT_SLAB_BYTES + 2 * (size_t)q.AH * a_stage;
   const size_t budget = 226 * 1024;
   if (fixed + 2 * (size_t)btile > budget) return fail(CP_ERR_INVALID, "dcn_tma: tile does not fit shared memory");
   q.SB = (int)((budget - fixed) / btile);

@@ -32,6 +32,11 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+# stdout carries exactly ONE JSON line: anything the host code prints while it sets up (the detector mirrors the
+# reference's "Creating model..." message) goes to stderr
+_REAL_STDOUT = sys.stdout
+sys.stdout = sys.stderr
+
 METRIC = "images/sec at 512x512 DLA-34 (dla_34 + DCNv2, 7 heads, decode + PnP)"
 UNIT = "images/s"
 GFLOP_PER_IMAGE = 85.11          # BASELINE.md section 2 (reference graph, 2*MAC)
@@ -180,7 +185,8 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_REAL_STDOUT)
+    _REAL_STDOUT.flush()
     return 0
 
 
@@ -425,7 +431,8 @@ def main():
             "cpu_baseline": cpu_baseline,
             "network_gflop_per_image": GFLOP_PER_IMAGE,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=_REAL_STDOUT)
+        _REAL_STDOUT.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -315,15 +315,18 @@ def main():
     kname = {"fp32": "igemm_fp32_kernel<64,NHWC>", "tf32": "conv_tma_kernel<x1>", "tf32x3": "conv_tma_kernel<x3>"}.get(
         args.precision, "igemm_umma_kernel")
     traffic = None
+    pipe_pct = None
     tpath = os.path.join(ROOT, "profiles", "r01_dominant_traffic.json")
     if os.path.exists(tpath):          # dram__bytes_read + dram__bytes_write of this launch, from the committed ncu capture
-        traffic = json.load(open(tpath)).get(kname + "@" + dom["name"])
+        tj = json.load(open(tpath))
+        traffic = tj.get(kname + "@" + dom["name"])
+        pipe_pct = tj.get("tensor_pipe_active_pct", {}).get(kname + "@" + dom["name"])
     mma_passes = 3 if args.precision == "tf32x3" else 1
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "kernel": kname + " @ " + dom["name"],
                 "tensor_work_tflops": achieved * mma_passes,     # tf32x3 issues 3 MMAs per algorithmic MAC
-                "frac_of_tf32_dense_peak": achieved * mma_passes / (peak / 2.0),
+                "tensor_pipe_active_pct_ncu": pipe_pct,          # sm__pipe_tensor_cycles_active of the committed capture
                 "ms_per_launch": dom_ms,
                 "share_of_forward": dom_ms / tot_ms, "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)",
                 "algorithmic_flops_per_launch": dom["flops"],

@@ -117,8 +117,7 @@ int dcn_tma_tile_n(int CoutPad, int x3);
 int dcn_tma_encode(const IgemmParams& p, int Bmax, void* map_out /* 128 bytes, 64-byte aligned */);
 int launch_dcn_tma(const IgemmParams& p, const void* map, int x3, int round_out_tf32, cudaStream_t stream);
 int tma_conv_encode(const IgemmParams& p, int Bmax, int x3, void* maps_out /* 4 x 128 bytes */);
-int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, int use_base_offset, int x3,
-                    cudaStream_t stream);
+int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, int x3, cudaStream_t stream);
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 

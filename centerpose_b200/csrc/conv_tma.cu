@@ -50,7 +50,6 @@ struct TmaConvParams {
   float* out;
   int outStride, out_nchw;
   int round_tf32;     // round the stored outputs to tf32 (consumers feed them to kind::tf32 untouched)
-  int use_base_offset;
   int cslab;          // channels per slab: 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B; Cin = 16 layers)
   int x3;             // 3-term split (fp32-equivalent): hi/lo slabs + hi/lo weight tiles, BN <= 128
   int group;          // x3: K blocks per TMEM accumulation group (promoted into fp32 registers after each group)
@@ -621,8 +620,7 @@ int tma_conv_encode(const IgemmParams& p, int Bmax, int x3, void* maps_out) {
   return CP_OK;
 }
 
-int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, int use_base_offset, int x3,
-                    cudaStream_t stream) {
+int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, int x3, cudaStream_t stream) {
   if (!p.wgt_umma) return fail(CP_ERR_INVALID, "conv_tma: weight tiles missing");
   TmaConvParams q;
   memset(&q, 0, sizeof(q));
@@ -679,7 +677,6 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.outStride = p.outStride;
   q.out_nchw = p.out_nchw;
   q.round_tf32 = round_out_tf32;
-  q.use_base_offset = use_base_offset;
   q.wtiles = (const unsigned char*)p.wgt_umma;
   const size_t smem = 512 + 2048 + (size_t)q.SA * a_stage + (size_t)q.SB * btile;
   static thread_local bool configured[2] = {false, false};

@@ -62,7 +62,6 @@ struct DcnTmaParams {
   int resStride, relu, res_after_relu;
   float* out;
   int outStride, out_nchw, round_tf32;
-  int debug_drop_far;                // CP_DCN_DROP_FAR=1 (timing experiments only): samples outside the slab contribute zero
   const unsigned char* wtiles;
 };
 
@@ -114,7 +113,6 @@ __device__ __forceinline__ void coef_row(const DcnTmaParams& p, const float* __r
       pk |= (uint32_t)(in_slab ? 1 : 0) << RB_SLAB;
       pk |= 1u << RB_LIVE;
       mk = mm;
-      if (p.debug_drop_far && !in_slab) pk = 0;
     }
     st_shared_v4(dst + (uint32_t)tap * 16u, __float_as_uint(lh), __float_as_uint(lw), __float_as_uint(mk), pk);
   }
@@ -573,7 +571,6 @@ int launch_dcn_tma(const IgemmParams& p, const void* map, int x3, int round_out_
   q.outStride = p.outStride;
   q.out_nchw = p.out_nchw;
   q.round_tf32 = round_out_tf32;
-  if (const char* e = getenv("CP_DCN_DROP_FAR")) q.debug_drop_far = atoi(e);
   q.wtiles = (const unsigned char*)p.wgt_umma;
   const size_t smem = fixed + (size_t)q.SB * btile;
   static thread_local bool configured[2] = {false, false};

@@ -101,8 +101,7 @@ static int run_igemm(IgemmParams& p, int prec, int Kreal, cudaStream_t s) {
       if (!rc) rc = launch_pack_tma_weight(p.wgt, p.CoutPad, p.Cin, taps, p.Cout, p.CoutPad, 1, x3, tma_cslab(p, x3), tiles, s);
       if (!rc) {
         p.wgt_umma = tiles;
-        const char* e = getenv("CP_TMA_BASE_OFFSET");
-        rc = launch_conv_tma(p, maps, 0, e ? atoi(e) : 0, x3, s);
+        rc = launch_conv_tma(p, maps, 0, x3, s);
       }
       cudaFreeAsync(tiles, s);
       return rc;

@@ -115,7 +115,6 @@ struct cp_plan {
   int prec = -1;                 // -1 fp32 CUDA cores, 0 bf16 tcgen05, 1 tf32x3 tcgen05, 2 tf32 (TMA) + tf32x3 elsewhere
   int min_tc_cin = 32;           // ops with fewer input channels stay on the CUDA-core kernels (CP_MIN_TC_CIN overrides)
   bool no_dcn_tma = false;       // CP_NO_DCN_TMA=1: deformable convs on the global-gather kernel (A/B measurements)
-  int tma_base_offset = 0;       // measured on B200: UMMA swizzles on absolute smem address bits, the field must stay 0
   unsigned char* umma_wts = nullptr;
   size_t umma_bytes = 0;
 };
@@ -621,7 +620,6 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
   P->H = cfg->height;
   P->W = cfg->width;
   P->prec = cfg->precision == CP_PREC_BF16 ? 0 : (cfg->precision == CP_PREC_TF32X3 ? 1 : (cfg->precision == CP_PREC_TF32 ? 2 : -1));
-  if (const char* e = getenv("CP_TMA_BASE_OFFSET")) P->tma_base_offset = atoi(e);
   if (const char* e = getenv("CP_MIN_TC_CIN")) P->min_tc_cin = atoi(e);
   if (const char* e = getenv("CP_NO_DCN_TMA")) P->no_dcn_tma = atoi(e) != 0;
   CP_CUDA_CHECK(cudaSetDevice(cfg->device));
@@ -835,7 +833,7 @@ static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* 
         } else if (op.use_tma) {
           p.wgt_umma = P->umma_wts + op.umma_off;
           const unsigned char* mp = (const unsigned char*)(((uintptr_t)op.tma_maps.data() + 63) & ~(uintptr_t)63);
-          if ((rc = launch_conv_tma(p, mp, P->prec == 2, P->tma_base_offset, P->prec == 1, s))) return rc;
+          if ((rc = launch_conv_tma(p, mp, P->prec == 2, P->prec == 1, s))) return rc;
         } else if (op.use_umma) {
           p.wgt_umma = P->umma_wts + op.umma_off;
           if ((rc = launch_igemm_umma(p, P->prec == 2 ? 1 : P->prec, s))) return rc;

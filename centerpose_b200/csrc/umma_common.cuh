@@ -150,7 +150,6 @@ __device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mas
 // (scripts/tma_diag.py): the tensor core applies the 128-byte swizzle to the ABSOLUTE shared-memory address bits
 // [7,10), exactly like TMA does when it writes the slab, so a matrix that starts at an arbitrary 128-byte row of
 // the slab needs NO base-offset correction (setting the field to (addr >> 7) & 7 gives wrong results).
-// `use_base_offset` is kept only as a debug switch (CP_TMA_BASE_OFFSET=1).
 // cslab = 32: 128-byte rows, SWIZZLE_128B (layout type 2), 8-row groups 1024 bytes apart;
 // cslab = 16:  64-byte rows, SWIZZLE_64B  (layout type 4), 8-row groups  512 bytes apart.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int use_base_offset, int cslab) {

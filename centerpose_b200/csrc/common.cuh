@@ -63,6 +63,14 @@ struct IgemmParams {
   int mask_is_logit;     // 1: apply sigmoid to channels 18..26
   int mode;
   const void* wgt_umma;  // tcgen05 path: pre-swizzled weight tiles (igemm_umma.cu), else null
+  // conv_tma only: the per-head 1x1 convolutions fused into the epilogue of the merged heads 3x3 conv.  Head h owns the
+  // output columns [h * fuse_hidden, (h + 1) * fuse_hidden); its 1x1 weights are [fuse_hidden][16] fp32 (rows = hidden
+  // channel, 16 padded outputs), bias [16], output NCHW [B, fuse_cout[h], Hout, Wout].  fuse_n == 0: not fused.
+  int fuse_n, fuse_hidden;
+  const float* fuse_w[16];
+  const float* fuse_b[16];
+  float* fuse_out[16];
+  int fuse_cout[16];
 };
 
 int launch_igemm_fp32(const IgemmParams& p, cudaStream_t stream);
@@ -104,6 +112,7 @@ int launch_gru_gates(const float* xi, const float* hh, const float* hprev, float
 // x3 = 1: 3-term split with two-level accumulation (fp32-equivalent); x3 = 0: single tf32 pass
 bool tma_conv_supported(const IgemmParams& p, int x3);
 size_t tma_weight_bytes(int Cin, int taps, int CoutPad, int x3);
+int tma_tile_n(int CoutPad, int x3);             // N tile of conv_tma for this output width
 int tma_cslab(const IgemmParams& p, int x3);     // channels per activation slab (32 or 16); needs Cin, kh, Win, CoutPad
 int launch_pack_tma_weight(const float* src_k_by_ld, int ld, int Cin, int taps, int Cout, int CoutPad, int round_tf32,
                            int x3, int cslab, void* dst, cudaStream_t s, int bn_override = 0);

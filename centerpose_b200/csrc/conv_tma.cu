@@ -54,6 +54,12 @@ struct TmaConvParams {
   int x3;             // 3-term split (fp32-equivalent): hi/lo slabs + hi/lo weight tiles, BN <= 128
   int group;          // x3: K blocks per TMEM accumulation group (promoted into fp32 registers after each group)
   const unsigned char* wtiles;
+  // fused per-head 1x1 (see IgemmParams): tph = N tiles per head, processed back to back by the same CTA
+  int fuse, tph;
+  const float* fuse_w[16];
+  const float* fuse_b[16];
+  float* fuse_out[16];
+  int fuse_cout[16];
 };
 
 using namespace umma;
@@ -95,6 +101,17 @@ __device__ __forceinline__ TileGeo decode_tile(const TmaConvParams& p, long long
   return g;
 }
 
+// fused 1x1 epilogue: outputs of one position of one head -> NCHW [B, Cout, H, W] (+ the 1x1 bias)
+__device__ __forceinline__ void fused_store(const TmaConvParams& p, int head, const float (&acc2)[16], int n, int oy, int ox) {
+  const int co = p.fuse_cout[head];
+  const float* b2 = p.fuse_b[head];
+  float* o = p.fuse_out[head] + ((size_t)n * co * p.H + oy) * p.W + ox;
+  const size_t plane = (size_t)p.H * p.W;
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (j < co) o[j * plane] = acc2[j] + __ldg(b2 + j);
+}
+
 // PERSISTENT kernel: gridDim.x = min(#tiles, #SMs); CTA c processes tiles c, c + gridDim.x, ...  Every role keeps its
 // pipeline state across tiles, so the TMA / split / MMA of tile i+1 overlap the epilogue of tile i and the fixed cost
 // of a CTA (barrier init, TMEM allocation, descriptor fetch, pipeline fill) is paid once per SM instead of per tile.
@@ -122,6 +139,10 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   const long long cluster_id = blockIdx.x / p.cluster;
   const long long num_clusters = gridDim.x / p.cluster;
   const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
+  // Tile order of this CTA: units of `tph` consecutive tiles (same positions, the N tiles of one head when the 1x1 is
+  // fused; tph = 1 otherwise), units strided over the CTAs.
+  const long long tph = p.fuse ? p.tph : 1;
+  auto tile_at = [&](long long it) { return (cluster_id + (it / tph) * num_clusters) * tph + (it % tph); };
 
   if (tid == 0) {
     for (int s = 0; s < p.SA; ++s) {
@@ -156,13 +177,13 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   // Warpgroup 0 (control warps) and 3 (splitters) hand registers to warpgroups 1-2 (epilogue) with setmaxnreg; the
   // role code sits inside the branch that executed it so that ptxas allocates per branch.
   if (warp < 4) {
-  if (X3) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (X3) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
   if (warp == 0) {
     // ===================== activation slabs via TMA =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      for (long long it = 0, tile = tile_at(0); tile < total_tiles; tile = tile_at(++it)) {
         bool live;
         const TileGeo g = decode_tile(p, tile, n_tiles, rank, &live);
         for (int s = 0; s < nslab; ++s) {
@@ -192,7 +213,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      for (long long it = 0, tile = tile_at(0); tile < total_tiles; tile = tile_at(++it)) {
         const int n_tile = (int)(tile % n_tiles);       // identical for all CTAs of the cluster
         const unsigned char* wsrc = p.wtiles + (size_t)n_tile * KB * btile_bytes;
         for (int kb = 0; kb < KB; ++kb) {
@@ -229,7 +250,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     const int group = p.group;
     int sa = 0, sb = 0, buf = 0;
     uint32_t pa = 0, pb = 0, pe = 0;                              // pe bit b: phase of p_empty[b]
-    for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+    for (long long it = 0, tile = tile_at(0); tile < total_tiles; tile = tile_at(++it)) {
       bool live;
       const TileGeo g = decode_tile(p, tile, n_tiles, rank, &live);
       const uint32_t tap0 = (p.k == 3) ? (uint32_t)(g.g0 - 1 - g.r_lo * p.Wt) * rowu : 0u;
@@ -305,7 +326,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t nchunk = p.slab_bytes >> 4;
-    for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+    for (long long it = 0, tile = tile_at(0); tile < total_tiles; tile = tile_at(++it)) {
       for (int s = 0; s < nslab; ++s) {
         mbar_wait(smem_u32(&ctl->a_full[stage]), phase);
         const uint32_t hi = slabs0 + (uint32_t)stage * a_stage;
@@ -337,7 +358,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
       }
     }
   } else if (warp >= 4 && warp < 4 + 4 * MS) {
-    if (X3) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+    if (X3) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     // ===================== epilogue: TMEM lane == flattened output position =====================
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
     const int sub = (warp - 4) >> 2;              // M sub-tile (x3 only: 0 / 1)
@@ -360,7 +381,10 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     ep.W = p.W;
     int buf = 0;
     uint32_t pf = 0;                     // bit b: phase of p_full[b]
-    for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+    float acc2[16];                      // fused 1x1: the 16 (padded) outputs of this position's head
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc2[j] = 0.f;
+    for (long long it = 0, tile = tile_at(0); tile < total_tiles; tile = tile_at(++it)) {
       bool live;
         const TileGeo g = decode_tile(p, tile, n_tiles, rank, &live);
       bool valid;
@@ -408,14 +432,50 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
           pf ^= 1u << buf;
           buf ^= 1;
         }
+        if (p.fuse) {
+          // hidden = relu(conv3x3 + bias) never leaves the SM: multiply it with this head's 1x1 weights right here
+          const int head = g.n_tile / p.tph, part = g.n_tile - head * p.tph;
+          if (part == 0) {
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c0 = cc * 32;
-          if (c0 < p.BN) {
-            float vv[32];
+            for (int j = 0; j < 16; ++j) acc2[j] = 0.f;
+          }
+          const float* b1 = p.bias + (size_t)g.n_tile * p.BN;
+          const float4* w2 = reinterpret_cast<const float4*>(p.fuse_w[head]) + (size_t)part * p.BN * 4;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) vv[j] = sums[(X3 ? cc * 32 + j : 0)];
-            epilogue_sub_tile(ep, stage, vv, lane, valid, m, n, oy, ox, g.n_tile * p.BN + c0, col_end);
+          for (int c = 0; c < (X3 ? 128 : 1); ++c) {
+            if (c < p.BN) {
+              const float v = fmaxf(sums[(X3 ? c : 0)] + __ldg(b1 + c), 0.f);
+              const float4 wa = __ldg(w2 + c * 4), wb = __ldg(w2 + c * 4 + 1), wc = __ldg(w2 + c * 4 + 2),
+                           wd = __ldg(w2 + c * 4 + 3);
+              acc2[0] = fmaf(v, wa.x, acc2[0]);
+              acc2[1] = fmaf(v, wa.y, acc2[1]);
+              acc2[2] = fmaf(v, wa.z, acc2[2]);
+              acc2[3] = fmaf(v, wa.w, acc2[3]);
+              acc2[4] = fmaf(v, wb.x, acc2[4]);
+              acc2[5] = fmaf(v, wb.y, acc2[5]);
+              acc2[6] = fmaf(v, wb.z, acc2[6]);
+              acc2[7] = fmaf(v, wb.w, acc2[7]);
+              acc2[8] = fmaf(v, wc.x, acc2[8]);
+              acc2[9] = fmaf(v, wc.y, acc2[9]);
+              acc2[10] = fmaf(v, wc.z, acc2[10]);
+              acc2[11] = fmaf(v, wc.w, acc2[11]);
+              acc2[12] = fmaf(v, wd.x, acc2[12]);
+              acc2[13] = fmaf(v, wd.y, acc2[13]);
+              acc2[14] = fmaf(v, wd.z, acc2[14]);
+              acc2[15] = fmaf(v, wd.w, acc2[15]);
+            }
+          }
+          if (part == p.tph - 1 && valid) fused_store(p, head, acc2, n, oy, ox);
+        } else {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const int c0 = cc * 32;
+            if (c0 < p.BN) {
+              float vv[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) vv[j] = sums[(X3 ? cc * 32 + j : 0)];
+              epilogue_sub_tile(ep, stage, vv, lane, valid, m, n, oy, ox, g.n_tile * p.BN + c0, col_end);
+            }
           }
         }
       } else {
@@ -438,7 +498,40 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
           float vv[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(rr[j]);
-          epilogue_sub_tile(ep, stage, vv, lane, valid, m, n, oy, ox, g.n_tile * p.BN + c0, col_end);
+          if (p.fuse) {
+            const int head = g.n_tile / p.tph, part = g.n_tile - head * p.tph;
+            if (part == 0 && c0 == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc2[j] = 0.f;
+            }
+            const float* b1 = p.bias + (size_t)g.n_tile * p.BN + c0;
+            const float4* w2 = reinterpret_cast<const float4*>(p.fuse_w[head]) + ((size_t)part * p.BN + c0) * 4;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float v = fmaxf(vv[c] + __ldg(b1 + c), 0.f);
+              const float4 wa = __ldg(w2 + c * 4), wb = __ldg(w2 + c * 4 + 1), wc = __ldg(w2 + c * 4 + 2),
+                           wd = __ldg(w2 + c * 4 + 3);
+              acc2[0] = fmaf(v, wa.x, acc2[0]);
+              acc2[1] = fmaf(v, wa.y, acc2[1]);
+              acc2[2] = fmaf(v, wa.z, acc2[2]);
+              acc2[3] = fmaf(v, wa.w, acc2[3]);
+              acc2[4] = fmaf(v, wb.x, acc2[4]);
+              acc2[5] = fmaf(v, wb.y, acc2[5]);
+              acc2[6] = fmaf(v, wb.z, acc2[6]);
+              acc2[7] = fmaf(v, wb.w, acc2[7]);
+              acc2[8] = fmaf(v, wc.x, acc2[8]);
+              acc2[9] = fmaf(v, wc.y, acc2[9]);
+              acc2[10] = fmaf(v, wc.z, acc2[10]);
+              acc2[11] = fmaf(v, wc.w, acc2[11]);
+              acc2[12] = fmaf(v, wd.x, acc2[12]);
+              acc2[13] = fmaf(v, wd.y, acc2[13]);
+              acc2[14] = fmaf(v, wd.z, acc2[14]);
+              acc2[15] = fmaf(v, wd.w, acc2[15]);
+            }
+            if (part == p.tph - 1 && c0 + 32 >= p.BN && valid) fused_store(p, head, acc2, n, oy, ox);
+          } else {
+            epilogue_sub_tile(ep, stage, vv, lane, valid, m, n, oy, ox, g.n_tile * p.BN + c0, col_end);
+          }
         }
         pf ^= 1u << buf;
         buf ^= 1;
@@ -678,6 +771,18 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.out_nchw = p.out_nchw;
   q.round_tf32 = round_out_tf32;
   q.wtiles = (const unsigned char*)p.wgt_umma;
+  if (p.fuse_n > 0) {
+    if (p.fuse_hidden % q.BN || p.CoutPad != p.fuse_n * p.fuse_hidden || !p.relu || p.residual)
+      return fail(CP_ERR_INVALID, "conv_tma: fused 1x1 needs relu, no residual and head_conv a multiple of the N tile");
+    q.fuse = 1;
+    q.tph = p.fuse_hidden / q.BN;
+    for (int h = 0; h < p.fuse_n; ++h) {
+      q.fuse_w[h] = p.fuse_w[h];
+      q.fuse_b[h] = p.fuse_b[h];
+      q.fuse_out[h] = p.fuse_out[h];
+      q.fuse_cout[h] = p.fuse_cout[h];
+    }
+  }
   const size_t smem = 512 + 2048 + (size_t)q.SA * a_stage + (size_t)q.SB * btile;
   static thread_local bool configured[2] = {false, false};
   if (!configured[x3 ? 1 : 0]) {

@@ -56,6 +56,9 @@ struct Op {
   bool use_umma = false;   // run on the tcgen05 gather kernel
   bool use_tma = false;    // run on the TMA-fed tcgen05 kernel (conv_tma.cu)
   bool use_dcn_tma = false;   // deformable conv on the TMA-staged tcgen05 kernel (dcn_tma.cu)
+  std::vector<int> head_children;   // merged heads 3x3 conv: indices of the per-head 1x1 ops that read its slices
+  bool fuse_heads = false;          // ... which run inside its epilogue (conv_tma.cu), never touching HBM
+  bool fused_away = false;          // this 1x1 op is computed by its parent's epilogue
   int tma_cslab = 32;
   std::vector<unsigned char> tma_maps;   // 4 CUtensorMap, encoded once the arena exists
   size_t umma_off = 0;     // bytes into the plan's tensor-core weight-tile buffer
@@ -114,6 +117,7 @@ struct cp_plan {
   double* gn_stats = nullptr;
   int prec = -1;                 // -1 fp32 CUDA cores, 0 bf16 tcgen05, 1 tf32x3 tcgen05, 2 tf32 (TMA) + tf32x3 elsewhere
   int min_tc_cin = 32;           // ops with fewer input channels stay on the CUDA-core kernels (CP_MIN_TC_CIN overrides)
+  bool no_fuse_heads = false;    // CP_NO_FUSE_HEADS=1: keep the per-head 1x1 convs as separate launches
   bool no_dcn_tma = false;       // CP_NO_DCN_TMA=1: deformable convs on the global-gather kernel (A/B measurements)
   unsigned char* umma_wts = nullptr;
   size_t umma_bytes = 0;
@@ -497,6 +501,8 @@ int build_graph(cp_plan* P) {
       b.add_pack(n + ".0.weight", n + ".0.bias", "", HCV, f.C, 3, HCV, 9 * f.C, N, (int)gi * HCV, wm, bm);
     }
     b.conv({f}, "", "", "", N, 3, 1, 1, !gru, nullptr, false, &mid, 0, 0, wm, bm);
+    const size_t merged_idx = P->ops.size() - 1;
+    std::vector<int> children;
     for (size_t gi = 0; gi < grp.size(); ++gi) {
       int h = grp[gi];
       const std::string& n = P->head_names[h];
@@ -529,7 +535,9 @@ int build_graph(cp_plan* P) {
       }
       b.conv({slice}, last + ".weight", last + ".bias", "", c.head_channels[h], 1, 1, 0, false, nullptr, false,
              nullptr, 0, 0, (size_t)-1, (size_t)-1, h);
+      children.push_back((int)P->ops.size() - 1);
     }
+    if (!gru) P->ops[merged_idx].head_children = children;     // GroupNorm sits between the two convs in dlav1
   }
   // plan-owned head buffers (NCHW) for cp_infer
   P->head_bufs.clear();
@@ -579,6 +587,27 @@ int build_graph(cp_plan* P) {
       }
     }
   }
+  // The per-head 1x1 convs move into the epilogue of the merged heads conv when that one runs on conv_tma.  Single-pass
+  // tf32 only: there the epilogue has a whole tile of MMA time to hide 4096 FMAs per position (heads 3.8 -> 3.4 ms and
+  // the seven 1x1 launches disappear).  In tf32x3 the same epilogue threads also promote the accumulation groups of the
+  // NEXT tile, and the extra work stalls the MMA warp (measured 6.5 -> 9.9 ms), so the fusion is off unless
+  // CP_FUSE_HEADS_X3=1.
+  const bool fuse_x3 = getenv("CP_FUSE_HEADS_X3") && atoi(getenv("CP_FUSE_HEADS_X3"));
+  if (P->prec == 2 || (P->prec == 1 && fuse_x3)) {
+    for (auto& op : P->ops) {
+      if (op.head_children.empty() || !op.use_tma || P->no_fuse_heads) continue;
+      const int bn = tma_tile_n(op.CoutPad, P->prec == 1);
+      bool ok = op.relu && !op.has_res && (c.head_conv % bn == 0) && (int)op.head_children.size() <= 16 &&
+                op.CoutPad == (int)op.head_children.size() * c.head_conv;
+      for (int ci : op.head_children) {
+        const Op& ch = P->ops[ci];
+        ok = ok && ch.CoutPad == 16 && ch.w_ld == 16 && ch.Cin == c.head_conv && ch.out_head >= 0 && !ch.relu && !ch.has_res;
+      }
+      if (!ok) continue;
+      op.fuse_heads = true;
+      for (int ci : op.head_children) P->ops[ci].fused_away = true;
+    }
+  }
   return CP_OK;
 }
 
@@ -621,6 +650,7 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
   P->W = cfg->width;
   P->prec = cfg->precision == CP_PREC_BF16 ? 0 : (cfg->precision == CP_PREC_TF32X3 ? 1 : (cfg->precision == CP_PREC_TF32 ? 2 : -1));
   if (const char* e = getenv("CP_MIN_TC_CIN")) P->min_tc_cin = atoi(e);
+  if (const char* e = getenv("CP_NO_FUSE_HEADS")) P->no_fuse_heads = atoi(e) != 0;
   if (const char* e = getenv("CP_NO_DCN_TMA")) P->no_dcn_tma = atoi(e) != 0;
   CP_CUDA_CHECK(cudaSetDevice(cfg->device));
   int rc = build_graph(P.get());
@@ -666,7 +696,7 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
     if (rc2) return rc2;
   }
   int n = 0;
-  for (auto& op : P->ops) n += (op.type == OP_GN_RELU) ? 2 : 1;
+  for (auto& op : P->ops) n += op.fused_away ? 0 : ((op.type == OP_GN_RELU) ? 2 : 1);
   P->launches = n;
   *out = P.release();
   return CP_OK;
@@ -778,6 +808,7 @@ static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* 
       CP_CUDA_CHECK(cudaEventRecord(e, s));
       prof->ev.push_back(e);
     }
+    if (op.fused_away) continue;          // computed inside the epilogue of the merged heads conv
     switch (op.type) {
       case OP_IGEMM: {
         IgemmParams p{};
@@ -826,6 +857,17 @@ static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* 
           p.mask_is_logit = 1;
         }
         p.mode = op.mode;
+        if (op.fuse_heads) {
+          p.fuse_n = (int)op.head_children.size();
+          p.fuse_hidden = P->cfg.head_conv;
+          for (int i = 0; i < p.fuse_n; ++i) {
+            const Op& ch = P->ops[op.head_children[i]];
+            p.fuse_w[i] = P->wts + ch.w_off;
+            p.fuse_b[i] = P->wts + ch.b_off;
+            p.fuse_out[i] = head_out[ch.out_head];
+            p.fuse_cout[i] = ch.Cout;
+          }
+        }
         if (op.use_dcn_tma) {
           p.wgt_umma = P->umma_wts + op.umma_off;
           const unsigned char* mp = (const unsigned char*)(((uintptr_t)op.tma_maps.data() + 63) & ~(uintptr_t)63);
@@ -891,8 +933,12 @@ static void op_work(const Op& op, int batch, double* flops, double* bytes) {
       int Ho = (Hin + 2 * op.pad - op.kh) / op.stride + 1, Wo = (Win + 2 * op.pad - op.kw) / op.stride + 1;
       double M = B * Ho * Wo;
       *flops = 2.0 * M * op.kh * op.kw * op.Cin * op.Cout;
-      *bytes = 4.0 * (B * Hin * Win * op.Cin + (double)op.kh * op.kw * op.Cin * op.Cout + M * op.Cout +
+      *bytes = 4.0 * (B * Hin * Win * op.Cin + (double)op.kh * op.kw * op.Cin * op.Cout + (op.fuse_heads ? 0.0 : M * op.Cout) +
                       (op.has_res ? M * op.Cout : 0.0) + (op.mode == IGEMM_DCN ? M * 27 : 0.0));
+      if (op.fused_away) {      // accounted to the parent below
+        *flops = 0;
+        *bytes = 0;
+      }
       break;
     }
     case OP_MAXPOOL:

@@ -102,20 +102,21 @@ __device__ __forceinline__ TileGeo decode_tile(const TmaConvParams& p, long long
 }
 
 // fused 1x1 epilogue: outputs of one position of one head -> NCHW [B, Cout, H, W] (+ the 1x1 bias)
-__device__ __forceinline__ void fused_store(const TmaConvParams& p, int head, const float (&acc2)[16], int n, int oy, int ox) {
+template <int NA>
+__device__ __forceinline__ void fused_store(const TmaConvParams& p, int head, const float (&acc2)[NA], int n, int oy, int ox) {
   const int co = p.fuse_cout[head];
   const float* b2 = p.fuse_b[head];
   float* o = p.fuse_out[head] + ((size_t)n * co * p.H + oy) * p.W + ox;
   const size_t plane = (size_t)p.H * p.W;
 #pragma unroll
   for (int j = 0; j < 16; ++j)
-    if (j < co) o[j * plane] = acc2[j] + __ldg(b2 + j);
+    if (j < co && j < NA) o[j * plane] = acc2[j < NA ? j : 0] + __ldg(b2 + j);
 }
 
 // PERSISTENT kernel: gridDim.x = min(#tiles, #SMs); CTA c processes tiles c, c + gridDim.x, ...  Every role keeps its
 // pipeline state across tiles, so the TMA / split / MMA of tile i+1 overlap the epilogue of tile i and the fixed cost
 // of a CTA (barrier init, TMEM allocation, descriptor fetch, pipeline fill) is paid once per SM instead of per tile.
-template <bool X3>
+template <bool X3, bool FUSE>
 __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmaConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   TmaCtl* ctl = reinterpret_cast<TmaCtl*>(smem);
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
   // Tile order of this CTA: units of `tph` consecutive tiles (same positions, the N tiles of one head when the 1x1 is
   // fused; tph = 1 otherwise), units strided over the CTAs.
-  const long long tph = p.fuse ? p.tph : 1;
+  const long long tph = FUSE ? p.tph : 1;
   auto tile_at = [&](long long it) { return (cluster_id + (it / tph) * num_clusters) * tph + (it % tph); };
 
   if (tid == 0) {
@@ -177,7 +178,12 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   // Warpgroup 0 (control warps) and 3 (splitters) hand registers to warpgroups 1-2 (epilogue) with setmaxnreg; the
   // role code sits inside the branch that executed it so that ptxas allocates per branch.
   if (warp < 4) {
-  if (X3) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+  if (X3) {
+    if (FUSE)
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    else
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  }
   if (warp == 0) {
     // ===================== activation slabs via TMA =====================
     if (lane == 0) {
@@ -358,7 +364,12 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
       }
     }
   } else if (warp >= 4 && warp < 4 + 4 * MS) {
-    if (X3) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    if (X3) {
+      if (FUSE)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+      else
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+    }
     // ===================== epilogue: TMEM lane == flattened output position =====================
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
     const int sub = (warp - 4) >> 2;              // M sub-tile (x3 only: 0 / 1)
@@ -381,9 +392,9 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     ep.W = p.W;
     int buf = 0;
     uint32_t pf = 0;                     // bit b: phase of p_full[b]
-    float acc2[16];                      // fused 1x1: the 16 (padded) outputs of this position's head
+    float acc2[FUSE ? 16 : 1];           // fused 1x1: the 16 (padded) outputs of this position's head
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc2[j] = 0.f;
+    for (int j = 0; j < (FUSE ? 16 : 1); ++j) acc2[j] = 0.f;
     for (long long it = 0, tile = tile_at(0); tile < total_tiles; tile = tile_at(++it)) {
       bool live;
         const TileGeo g = decode_tile(p, tile, n_tiles, rank, &live);
@@ -432,12 +443,12 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
           pf ^= 1u << buf;
           buf ^= 1;
         }
-        if (p.fuse) {
+        if (FUSE) {
           // hidden = relu(conv3x3 + bias) never leaves the SM: multiply it with this head's 1x1 weights right here
           const int head = g.n_tile / p.tph, part = g.n_tile - head * p.tph;
           if (part == 0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc2[j] = 0.f;
+            for (int j = 0; j < (FUSE ? 16 : 1); ++j) acc2[j] = 0.f;
           }
           const float* b1 = p.bias + (size_t)g.n_tile * p.BN;
           const float4* w2 = reinterpret_cast<const float4*>(p.fuse_w[head]) + (size_t)part * p.BN * 4;
@@ -447,22 +458,22 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
               const float v = fmaxf(sums[(X3 ? c : 0)] + __ldg(b1 + c), 0.f);
               const float4 wa = __ldg(w2 + c * 4), wb = __ldg(w2 + c * 4 + 1), wc = __ldg(w2 + c * 4 + 2),
                            wd = __ldg(w2 + c * 4 + 3);
-              acc2[0] = fmaf(v, wa.x, acc2[0]);
-              acc2[1] = fmaf(v, wa.y, acc2[1]);
-              acc2[2] = fmaf(v, wa.z, acc2[2]);
-              acc2[3] = fmaf(v, wa.w, acc2[3]);
-              acc2[4] = fmaf(v, wb.x, acc2[4]);
-              acc2[5] = fmaf(v, wb.y, acc2[5]);
-              acc2[6] = fmaf(v, wb.z, acc2[6]);
-              acc2[7] = fmaf(v, wb.w, acc2[7]);
-              acc2[8] = fmaf(v, wc.x, acc2[8]);
-              acc2[9] = fmaf(v, wc.y, acc2[9]);
-              acc2[10] = fmaf(v, wc.z, acc2[10]);
-              acc2[11] = fmaf(v, wc.w, acc2[11]);
-              acc2[12] = fmaf(v, wd.x, acc2[12]);
-              acc2[13] = fmaf(v, wd.y, acc2[13]);
-              acc2[14] = fmaf(v, wd.z, acc2[14]);
-              acc2[15] = fmaf(v, wd.w, acc2[15]);
+              acc2[FUSE ? 0 : 0] = fmaf(v, wa.x, acc2[FUSE ? 0 : 0]);
+              acc2[FUSE ? 1 : 0] = fmaf(v, wa.y, acc2[FUSE ? 1 : 0]);
+              acc2[FUSE ? 2 : 0] = fmaf(v, wa.z, acc2[FUSE ? 2 : 0]);
+              acc2[FUSE ? 3 : 0] = fmaf(v, wa.w, acc2[FUSE ? 3 : 0]);
+              acc2[FUSE ? 4 : 0] = fmaf(v, wb.x, acc2[FUSE ? 4 : 0]);
+              acc2[FUSE ? 5 : 0] = fmaf(v, wb.y, acc2[FUSE ? 5 : 0]);
+              acc2[FUSE ? 6 : 0] = fmaf(v, wb.z, acc2[FUSE ? 6 : 0]);
+              acc2[FUSE ? 7 : 0] = fmaf(v, wb.w, acc2[FUSE ? 7 : 0]);
+              acc2[FUSE ? 8 : 0] = fmaf(v, wc.x, acc2[FUSE ? 8 : 0]);
+              acc2[FUSE ? 9 : 0] = fmaf(v, wc.y, acc2[FUSE ? 9 : 0]);
+              acc2[FUSE ? 10 : 0] = fmaf(v, wc.z, acc2[FUSE ? 10 : 0]);
+              acc2[FUSE ? 11 : 0] = fmaf(v, wc.w, acc2[FUSE ? 11 : 0]);
+              acc2[FUSE ? 12 : 0] = fmaf(v, wd.x, acc2[FUSE ? 12 : 0]);
+              acc2[FUSE ? 13 : 0] = fmaf(v, wd.y, acc2[FUSE ? 13 : 0]);
+              acc2[FUSE ? 14 : 0] = fmaf(v, wd.z, acc2[FUSE ? 14 : 0]);
+              acc2[FUSE ? 15 : 0] = fmaf(v, wd.w, acc2[FUSE ? 15 : 0]);
             }
           }
           if (part == p.tph - 1 && valid) fused_store(p, head, acc2, n, oy, ox);
@@ -498,11 +509,11 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
           float vv[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(rr[j]);
-          if (p.fuse) {
+          if (FUSE) {
             const int head = g.n_tile / p.tph, part = g.n_tile - head * p.tph;
             if (part == 0 && c0 == 0) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) acc2[j] = 0.f;
+              for (int j = 0; j < (FUSE ? 16 : 1); ++j) acc2[j] = 0.f;
             }
             const float* b1 = p.bias + (size_t)g.n_tile * p.BN + c0;
             const float4* w2 = reinterpret_cast<const float4*>(p.fuse_w[head]) + ((size_t)part * p.BN + c0) * 4;
@@ -511,22 +522,22 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
               const float v = fmaxf(vv[c] + __ldg(b1 + c), 0.f);
               const float4 wa = __ldg(w2 + c * 4), wb = __ldg(w2 + c * 4 + 1), wc = __ldg(w2 + c * 4 + 2),
                            wd = __ldg(w2 + c * 4 + 3);
-              acc2[0] = fmaf(v, wa.x, acc2[0]);
-              acc2[1] = fmaf(v, wa.y, acc2[1]);
-              acc2[2] = fmaf(v, wa.z, acc2[2]);
-              acc2[3] = fmaf(v, wa.w, acc2[3]);
-              acc2[4] = fmaf(v, wb.x, acc2[4]);
-              acc2[5] = fmaf(v, wb.y, acc2[5]);
-              acc2[6] = fmaf(v, wb.z, acc2[6]);
-              acc2[7] = fmaf(v, wb.w, acc2[7]);
-              acc2[8] = fmaf(v, wc.x, acc2[8]);
-              acc2[9] = fmaf(v, wc.y, acc2[9]);
-              acc2[10] = fmaf(v, wc.z, acc2[10]);
-              acc2[11] = fmaf(v, wc.w, acc2[11]);
-              acc2[12] = fmaf(v, wd.x, acc2[12]);
-              acc2[13] = fmaf(v, wd.y, acc2[13]);
-              acc2[14] = fmaf(v, wd.z, acc2[14]);
-              acc2[15] = fmaf(v, wd.w, acc2[15]);
+              acc2[FUSE ? 0 : 0] = fmaf(v, wa.x, acc2[FUSE ? 0 : 0]);
+              acc2[FUSE ? 1 : 0] = fmaf(v, wa.y, acc2[FUSE ? 1 : 0]);
+              acc2[FUSE ? 2 : 0] = fmaf(v, wa.z, acc2[FUSE ? 2 : 0]);
+              acc2[FUSE ? 3 : 0] = fmaf(v, wa.w, acc2[FUSE ? 3 : 0]);
+              acc2[FUSE ? 4 : 0] = fmaf(v, wb.x, acc2[FUSE ? 4 : 0]);
+              acc2[FUSE ? 5 : 0] = fmaf(v, wb.y, acc2[FUSE ? 5 : 0]);
+              acc2[FUSE ? 6 : 0] = fmaf(v, wb.z, acc2[FUSE ? 6 : 0]);
+              acc2[FUSE ? 7 : 0] = fmaf(v, wb.w, acc2[FUSE ? 7 : 0]);
+              acc2[FUSE ? 8 : 0] = fmaf(v, wc.x, acc2[FUSE ? 8 : 0]);
+              acc2[FUSE ? 9 : 0] = fmaf(v, wc.y, acc2[FUSE ? 9 : 0]);
+              acc2[FUSE ? 10 : 0] = fmaf(v, wc.z, acc2[FUSE ? 10 : 0]);
+              acc2[FUSE ? 11 : 0] = fmaf(v, wc.w, acc2[FUSE ? 11 : 0]);
+              acc2[FUSE ? 12 : 0] = fmaf(v, wd.x, acc2[FUSE ? 12 : 0]);
+              acc2[FUSE ? 13 : 0] = fmaf(v, wd.y, acc2[FUSE ? 13 : 0]);
+              acc2[FUSE ? 14 : 0] = fmaf(v, wd.z, acc2[FUSE ? 14 : 0]);
+              acc2[FUSE ? 15 : 0] = fmaf(v, wd.w, acc2[FUSE ? 15 : 0]);
             }
             if (part == p.tph - 1 && c0 + 32 >= p.BN && valid) fused_store(p, head, acc2, n, oy, ox);
           } else {
@@ -784,13 +795,13 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
     }
   }
   const size_t smem = 512 + 2048 + (size_t)q.SA * a_stage + (size_t)q.SB * btile;
-  static thread_local bool configured[2] = {false, false};
-  if (!configured[x3 ? 1 : 0]) {
-    if (x3)
-      CP_CUDA_CHECK(cudaFuncSetAttribute(conv_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    else
-      CP_CUDA_CHECK(cudaFuncSetAttribute(conv_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured[x3 ? 1 : 0] = true;
+  void (*kern)(TmaConvParams) = x3 ? (q.fuse ? conv_tma_kernel<true, true> : conv_tma_kernel<true, false>)
+                                   : (q.fuse ? conv_tma_kernel<false, true> : conv_tma_kernel<false, false>);
+  static thread_local bool configured[4] = {false, false, false, false};
+  const int slot = (x3 ? 2 : 0) + (q.fuse ? 1 : 0);
+  if (!configured[slot]) {
+    CP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured[slot] = true;
   }
   q.m_tiles = (long long)m_tiles;
   int cluster = 1;     // measured: multicast at cluster sizes 2/4 does not cut L2 traffic on this part and couples the CTAs
@@ -820,10 +831,7 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (x3)
-    CP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tma_kernel<true>, q));
-  else
-    CP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tma_kernel<false>, q));
+  CP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, q));
   CP_LAUNCH_CHECK("conv_tma_kernel");
   return CP_OK;
 }

@@ -260,6 +260,8 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
       bool live;
       const TileGeo g = decode_tile(p, tile, n_tiles, rank, &live);
       const uint32_t tap0 = (p.k == 3) ? (uint32_t)(g.g0 - 1 - g.r_lo * p.Wt) * rowu : 0u;
+      // x3: small feature maps end inside the first 128 rows of their last tile; the second accumulator is then skipped
+      const bool sub1_live = (p.k == 3) ? (g.g0 + TM_BM < p.H * p.Wt) : (g.pos0 + TM_BM < (long long)p.B * p.H * p.W);
       int kbi = 0, gk = 0;               // K-block index inside the tile (slab-major, tap-minor) / inside its group
       for (int s = 0; s < nslab; ++s) {
         mbar_wait(smem_u32(X3 ? &ctl->a_split[sa] : &ctl->a_full[sa]), pa);
@@ -286,6 +288,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
                   if (X3) {
 #pragma unroll
                     for (int sub = 0; sub < MS; ++sub) {          // rows [128 sub, 128 sub + 128) of the tile
+                      if (sub > 0 && !sub1_live) continue;        // no output position in the second half (image tail)
                       const uint64_t das = da + (uint64_t)(sub * (TM_BM * (int)rowu)) + 2 * ks;
                       const uint32_t dt = d_tmem + (uint32_t)(sub * p.BN);
                       umma_tf32(dt, das + a_lo_u, db + 2 * ks, idesc, acc);

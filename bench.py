@@ -34,7 +34,10 @@ import torch  # noqa: E402
 
 # stdout carries exactly ONE JSON line: anything the host code prints while it sets up (the detector mirrors the
 # reference's "Creating model..." message) goes to stderr
-_REAL_STDOUT = sys.stdout
+# (at the file-descriptor level: NCCL writes its version banner to fd 1 from C)
+sys.stdout.flush()
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 sys.stdout = sys.stderr
 
 METRIC = "images/sec at 512x512 DLA-34 (dla_34 + DCNv2, 7 heads, decode + PnP)"

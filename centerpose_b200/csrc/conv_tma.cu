@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     // (the 14-bit address field cannot carry: shared addresses stay below 256 KB).
     const uint32_t idesc = make_idesc_tf32(p.BN);
     const uint64_t dtmpl = make_desc(0, 0, p.cslab);
+    const uint32_t dhi = (uint32_t)(dtmpl >> 32), dlo0 = (uint32_t)dtmpl;     // descriptors are handled as 32-bit low words
     const uint32_t rowu = rowb >> 4;                              // row pitch in descriptor units
     const uint32_t a_lo_u = p.slab_stride >> 4;                   // x3: lo slab behind the hi slab
     const uint32_t b_lo_u = ((uint32_t)p.BN * rowb) >> 4;         // x3: lo tile behind the hi tile
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
       for (int s = 0; s < nslab; ++s) {
         mbar_wait(smem_u32(X3 ? &ctl->a_split[sa] : &ctl->a_full[sa]), pa);
         tc_fence_after();
-        const uint64_t a_slab = dtmpl + (uint64_t)(((slabs0 + (uint32_t)sa * a_stage) >> 4) + tap0);
+        const uint32_t a_slab = dlo0 + ((slabs0 + (uint32_t)sa * a_stage) >> 4) + tap0;
         for (int ky = 0; ky < p.k; ++ky) {
           for (int kx = 0; kx < p.k; ++kx, ++kbi) {
             const bool first = X3 ? (gk == 0) : (kbi == 0);
@@ -275,8 +276,8 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
             }
             mbar_wait(smem_u32(&ctl->b_full[sb]), pb);
             tc_fence_after();
-            const uint64_t da = a_slab + (uint64_t)((uint32_t)(ky * p.Wt + kx) * rowu);
-            const uint64_t db = dtmpl + (uint64_t)((btiles0 + (uint32_t)sb * btile_bytes) >> 4);
+            const uint32_t da = a_slab + (uint32_t)(ky * p.Wt + kx) * rowu;
+            const uint32_t db = dlo0 + ((btiles0 + (uint32_t)sb * btile_bytes) >> 4);
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN * MS);
             const bool last = X3 ? (gk == group - 1 || kbi == KB - 1) : (kbi == KB - 1);
             const bool slab_done = (ky == p.k - 1) && (kx == p.k - 1);
@@ -289,14 +290,14 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
 #pragma unroll
                     for (int sub = 0; sub < MS; ++sub) {          // rows [128 sub, 128 sub + 128) of the tile
                       if (sub > 0 && !sub1_live) continue;        // no output position in the second half (image tail)
-                      const uint64_t das = da + (uint64_t)(sub * (TM_BM * (int)rowu)) + 2 * ks;
+                      const uint32_t das = da + (uint32_t)(sub * TM_BM) * rowu + 2u * ks;
                       const uint32_t dt = d_tmem + (uint32_t)(sub * p.BN);
-                      umma_tf32(dt, das + a_lo_u, db + 2 * ks, idesc, acc);
-                      umma_tf32(dt, das, db + b_lo_u + 2 * ks, idesc, 1u);
-                      umma_tf32(dt, das, db + 2 * ks, idesc, 1u);
+                      umma_tf32_lohi(dt, das + a_lo_u, db + 2u * ks, dhi, idesc, acc);
+                      umma_tf32_lohi(dt, das, db + b_lo_u + 2u * ks, dhi, idesc, 1u);
+                      umma_tf32_lohi(dt, das, db + 2u * ks, dhi, idesc, 1u);
                     }
                   } else {
-                    umma_tf32(d_tmem, da + 2 * ks, db + 2 * ks, idesc, acc);
+                    umma_tf32_lohi(d_tmem, da + 2u * ks, db + 2u * ks, dhi, idesc, acc);
                   }
                 }
               }

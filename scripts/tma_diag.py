@@ -1,6 +1,7 @@
 """Addressing diagnostics for the TMA shifted-window conv (conv_tma.cu): one-hot weights that pick a single
 (tap, channel) make every output equal to one input element, so any slab / descriptor / base-offset mistake shows
-up as an exact, locatable mismatch.  Run with CP_TMA_BASE_OFFSET=0 and =1."""
+up as an exact, locatable mismatch.  (This is the test that showed the descriptor base-offset field must stay 0: UMMA
+swizzles on absolute shared-memory address bits)"""
 import os
 import sys
 
@@ -13,7 +14,6 @@ import centerpose_b200 as cpb  # noqa: E402
 
 torch.manual_seed(0)
 for bo in ("tf32", "tf32x3"):
-    os.environ["CP_TMA_BASE_OFFSET"] = "0"
     for (B, H, W, Cin, Cout, k) in ((1, 8, 16, 32, 32, 1), (1, 16, 16, 16, 16, 3), (2, 64, 64, 16, 16, 3), (1, 8, 16, 16, 32, 1), (1, 16, 16, 32, 64, 3), (2, 12, 30, 64, 32, 3),
                                     (1, 128, 128, 64, 256, 3), (1, 16, 16, 512, 128, 3)):
         x = (torch.arange(B * H * W * Cin, dtype=torch.float32).reshape(B, H, W, Cin) * 7 % 251) - 125
@@ -38,7 +38,6 @@ for bo in ("tf32", "tf32x3"):
             print("%s B%d %dx%d Cin%d Cout%d k%d: FAILED %s" % (bo, B, H, W, Cin, Cout, k, str(e)[:200]))
             sys.exit(0)          # a trap kills the context; stop here
 # random-data accuracy (tf32 single pass): expect ~1e-3 of max
-os.environ["CP_TMA_BASE_OFFSET"] = os.environ.get("CP_TMA_BEST", "0")
 for (B, H, W, Cin, Cout, k) in ((2, 32, 32, 64, 64, 3), (2, 64, 64, 16, 16, 3), (1, 64, 64, 128, 256, 1), (4, 128, 128, 64, 1792, 3), (1, 8, 8, 512, 256, 3)):
     x = torch.randn(B, H, W, Cin)
     w = torch.randn(Cout, Cin, k, k) / np.sqrt(Cin * k * k)

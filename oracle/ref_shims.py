@@ -108,8 +108,44 @@ def install():
     fpc = types.ModuleType("filterpy.common")
 
     class KalmanFilter(object):
-        def __init__(self, *a, **k):
-            raise NotImplementedError("filterpy is not installed; tracker is out of scope")
+        """Functional stand-in for filterpy.kalman.KalmanFilter (third party, `requirements.txt:14` pins
+        filterpy>=1.4.5; not installed here).  Published algorithm of 1.4.5: predict  x = F x, P = a^2 F P F^T + Q;
+        update  y = z - H x, S = H P H^T + R, K = P H^T S^-1, x += K y, P = (I-KH) P (I-KH)^T + K R K^T (Joseph form).
+        Only what utils/tracker.py uses: attributes x, P, Q, F, H, R and predict() / update(z, R=...)."""
+
+        def __init__(self, dim_x, dim_z, dim_u=0):
+            import numpy as _np
+            self.dim_x, self.dim_z = dim_x, dim_z
+            self.x = _np.zeros((dim_x, 1))
+            self.P = _np.eye(dim_x)
+            self.Q = _np.eye(dim_x)
+            self.F = _np.eye(dim_x)
+            self.H = _np.zeros((dim_z, dim_x))
+            self.R = _np.eye(dim_z)
+            self._alpha_sq = 1.0
+            self._I = _np.eye(dim_x)
+
+        def predict(self):
+            import numpy as _np
+            self.x = _np.dot(self.F, self.x)
+            self.P = self._alpha_sq * _np.dot(_np.dot(self.F, self.P), self.F.T) + self.Q
+
+        def update(self, z, R=None, H=None):
+            import numpy as _np
+            if z is None:
+                return
+            R = self.R if R is None else R
+            H = self.H if H is None else H
+            z = _np.atleast_2d(_np.asarray(z, dtype=float))
+            if z.shape[1] == self.dim_z and z.shape[0] == 1:
+                z = z.T
+            y = z - _np.dot(H, self.x)
+            PHT = _np.dot(self.P, H.T)
+            S = _np.dot(H, PHT) + R
+            K = _np.dot(PHT, _np.linalg.inv(S))
+            self.x = self.x + _np.dot(K, y)
+            I_KH = self._I - _np.dot(K, H)
+            self.P = _np.dot(_np.dot(I_KH, self.P), I_KH.T) + _np.dot(_np.dot(K, R), K.T)
     fpk.KalmanFilter = KalmanFilter
     fpc.Q_discrete_white_noise = _not_impl
     fp.kalman = fpk
@@ -121,7 +157,13 @@ def install():
     try:
         import sklearn.utils as sku
         la = types.ModuleType("sklearn.utils.linear_assignment_")
-        la.linear_assignment = _not_impl
+        def _linear_assignment(cost):
+            # sklearn <= 0.22 API: array of (row, col) pairs of the optimal assignment, sorted by row
+            import numpy as _np
+            from scipy.optimize import linear_sum_assignment
+            r, c = linear_sum_assignment(cost)
+            return _np.stack([r, c], axis=1)
+        la.linear_assignment = _linear_assignment
         sys.modules.setdefault("sklearn.utils.linear_assignment_", la)
         sku.linear_assignment_ = la
     except Exception:

@@ -116,21 +116,9 @@ class ClockSampler(threading.Thread):
 
 
 def calibrate_head_bias(model, eng, x, target=TARGET_OBJECTS):
-    """Random-init weights put every (or no) heat-map peak above the thresholds, which would make the decode /
-    PnP stage do 100 (or 0) solves per frame.  Shift the two heat-map biases -- setup only, outside any timed
-    region -- so that about `target` centre peaks per frame pass vis_thresh = 0.3 and about `target` peaks per
-    keypoint channel pass the 0.1 gate, i.e. a realistic scene density for the post-network stage."""
-    import math
-    import torch.nn.functional as F
-    out = eng.forward(x)
-    with torch.no_grad():
-        for head, thr in (("hm", math.log(0.3 / 0.7)), ("hm_hp", math.log(0.1 / 0.9))):
-            hm = out[head]
-            pk = F.max_pool2d(hm, 3, 1, 1)
-            peaks = torch.where(pk == hm, hm, torch.full_like(hm, -1e9)).flatten(2)      # [B, C, HW]
-            kth = peaks.topk(target + 1, dim=2).values
-            mid = (0.5 * (kth[..., target - 1] + kth[..., target])).median()
-            getattr(model, head)[2].bias += (thr - mid)
+    """Setup only, outside any timed region: see centerpose_b200.synth.calibrate_head_bias."""
+    from centerpose_b200 import synth
+    synth.calibrate_head_bias(model, eng.forward(x), target)
     return model
 
 

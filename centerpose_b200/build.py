@@ -13,7 +13,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcenterpose_b200.so")
 SOURCES = ["plan.cu", "igemm_fp32.cu", "elementwise.cu", "decode.cu", "ext_ops.cu", "igemm_umma.cu", "stem_conv.cu", "conv_tma.cu", "dcn_tma.cu"]
-HEADERS = ["common.cuh", "pose_core.h", os.path.join("..", "..", "include", "centerpose_b200.h")]
+def _headers():
+    """Every header a .cu may include: editing shared code (umma_common.cuh, pose_core.h ...) must rebuild the objects."""
+    hs = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    return hs + [os.path.join("..", "..", "include", "centerpose_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -42,7 +45,7 @@ def build(force=False, verbose=False):
     """Compile every .cu to an object (parallelisable, incremental) and link the .so."""
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
-    hdrs = [os.path.join(CSRC, h) for h in HEADERS]
+    hdrs = [os.path.join(CSRC, h) for h in _headers()]
     objs = []
     procs = []
     for src in SOURCES:

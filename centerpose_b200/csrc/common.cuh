@@ -114,6 +114,7 @@ bool tma_conv_supported(const IgemmParams& p, int x3);
 size_t tma_weight_bytes(int Cin, int taps, int CoutPad, int x3);
 int tma_tile_n(int CoutPad, int x3);             // N tile of conv_tma for this output width
 int tma_cslab(const IgemmParams& p, int x3);     // channels per activation slab (32 or 16); needs Cin, kh, Win, CoutPad
+int x3_group_blocks();                           // tf32x3: 32-channel K blocks per TMEM accumulation group
 int launch_pack_tma_weight(const float* src_k_by_ld, int ld, int Cin, int taps, int Cout, int CoutPad, int round_tf32,
                            int x3, int cslab, void* dst, cudaStream_t s, int bn_override = 0);
 int tma_encode_nhwc_box(const float* base, int C, int W, int H, int B, int strideFloats, int boxC, int boxW, int boxH,
@@ -129,5 +130,32 @@ int tma_conv_encode(const IgemmParams& p, int Bmax, int x3, void* maps_out /* 4 
 int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, int x3, cudaStream_t stream);
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Launch attributes (cudaFuncSetAttribute) and the SM count are properties of the CURRENT DEVICE, not of the calling
+// thread: the caches below are indexed by cudaGetDevice() so that a process which runs plans on cuda:0 and cuda:1
+// configures the > 48 KB shared-memory kernels on both.  (Two threads racing on the same slot set the same attribute
+// twice, which is harmless.)
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
+template <typename T, int N = 1>
+struct PerDevice {
+  T v[kMaxDevices][N] = {};
+  T& here(int slot = 0) { return v[current_device_slot()][slot]; }
+};
+inline int device_sm_count(int* out) {
+  static PerDevice<int> cache;
+  int& n = cache.here();
+  if (!n) {
+    int dev = 0;
+    CP_CUDA_CHECK(cudaGetDevice(&dev));
+    CP_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  *out = n;
+  return CP_OK;
+}
 
 }  // namespace cp

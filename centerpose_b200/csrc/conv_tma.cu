@@ -28,7 +28,22 @@ namespace {
 
 constexpr int TM_BM = 128;
 constexpr int TM_THREADS = 256;
-constexpr int TM_GROUP_X3 = 3;
+constexpr int TM_GROUP_X3 = 1;
+}  // namespace
+
+// tf32x3: 32-channel K blocks (12 MMAs each) per TMEM accumulation group.  The tensor core's fp32 accumulator TRUNCATES
+// every add (measured; the error is biased towards zero and grows with the chain length), so a group is promoted into
+// round-to-nearest fp32 sums after this many blocks.  CP_X3_GROUP overrides (diagnostics).
+int x3_group_blocks() {
+  int g = TM_GROUP_X3;
+  if (const char* e = getenv("CP_X3_GROUP")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 16) g = v;
+  }
+  return g;
+}
+
+namespace {
 
 struct TmaConvParams {
   CUtensorMap amap[4];
@@ -69,8 +84,13 @@ struct TmaCtl {
   unsigned long long b_full[8], b_empty[8];
   unsigned long long accum_full;
   unsigned long long p_full[2], p_empty[2];
+  unsigned long long w2_full, w2_empty;      // x3 fused heads: 1x1 weights + 3x3 bias of the current tile in shared memory
   uint32_t tmem_base;
 };
+
+// x3 fused heads: [128 hidden][16] fp32 1x1 weights of the tile's (head, part) followed by the 128 biases of the 3x3 conv
+constexpr uint32_t TM_W2_BYTES = 128u * 16u * 4u;
+constexpr uint32_t TM_W2_BUF = TM_W2_BYTES + 128u * 4u;
 
 constexpr int TM_THREADS_X3 = 512;    // x3: warps 4-11 epilogue (two 128-row sub-tiles), warps 12-15 hi/lo splitters
 
@@ -113,6 +133,31 @@ __device__ __forceinline__ void fused_store(const TmaConvParams& p, int head, co
     if (j < co && j < NA) o[j * plane] = acc2[j < NA ? j : 0] + __ldg(b2 + j);
 }
 
+// x3 fused heads: hidden[c] = relu(sums[c] + b1[c]) is multiplied with the [128][16] weight block in shared memory.
+// Every lane reads the SAME address (broadcast, one wavefront); only V = ceil(cout / 4) float4 groups are touched, so the
+// narrow heads (hm 1, wh / reg / hp_offset 2, scale 3 outputs) cost 4 FMAs per hidden channel instead of 16.
+template <int V>
+__device__ __forceinline__ void fused_part_smem(const float (&sums)[128], float (&acc2)[16], uint32_t w2s, uint32_t b1s) {
+#pragma unroll
+  for (int c4 = 0; c4 < 32; ++c4) {
+    const float4 bb = ld_shared_v4f(b1s + (uint32_t)c4 * 16u);
+    const float bq[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c4 * 4 + u;
+      const float v = fmaxf(sums[c] + bq[u], 0.f);
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        const float4 w = ld_shared_v4f(w2s + (uint32_t)(c * 64 + q * 16));
+        acc2[q * 4 + 0] = fmaf(v, w.x, acc2[q * 4 + 0]);
+        acc2[q * 4 + 1] = fmaf(v, w.y, acc2[q * 4 + 1]);
+        acc2[q * 4 + 2] = fmaf(v, w.z, acc2[q * 4 + 2]);
+        acc2[q * 4 + 3] = fmaf(v, w.w, acc2[q * 4 + 3]);
+      }
+    }
+  }
+}
+
 // PERSISTENT kernel: gridDim.x = min(#tiles, #SMs); CTA c processes tiles c, c + gridDim.x, ...  Every role keeps its
 // pipeline state across tiles, so the TMA / split / MMA of tile i+1 overlap the epilogue of tile i and the fixed cost
 // of a CTA (barrier init, TMEM allocation, descriptor fetch, pipeline fill) is paid once per SM instead of per tile.
@@ -129,6 +174,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   const uint32_t btile_bytes = (uint32_t)p.BN * rowb * (X3 ? 2u : 1u);         // hi (+ lo) weight tile
   const uint32_t a_stage = p.slab_stride * (X3 ? 2u : 1u);                    // hi (+ lo) slab
   const uint32_t btiles0 = slabs0 + (uint32_t)p.SA * a_stage;
+  const uint32_t w2buf = btiles0 + (uint32_t)p.SB * btile_bytes;                // x3 fused heads only (TM_W2_BUF bytes)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = p.CoutPad / p.BN;
@@ -159,6 +205,8 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
       mbar_init(smem_u32(&ctl->p_full[s]), 1);       // x3: accumulation group ready / x1: tile accumulator ready
       mbar_init(smem_u32(&ctl->p_empty[s]), 128 * MS);   // drained by the epilogue threads
     }
+    mbar_init(smem_u32(&ctl->w2_full), 1);
+    mbar_init(smem_u32(&ctl->w2_empty), 4 * MS);         // one arrive per epilogue warp
     fence_mbar_init();
   }
   // two TMEM accumulator buffers of BN columns: x1 ping-pongs whole tiles, x3 ping-pongs accumulation groups
@@ -282,11 +330,13 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
             const bool last = X3 ? (gk == group - 1 || kbi == KB - 1) : (kbi == KB - 1);
             const bool slab_done = (ky == p.k - 1) && (kx == p.k - 1);
             if (elect_one()) {
+              if (X3) {
+                // The accumulator truncates every add (error ~ its magnitude x chain length): the two cross terms of
+                // all K slices go first, while the accumulator still holds small values, the hi x hi terms last.
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                if (ks < kslices) {
-                  const uint32_t acc = (first && ks == 0) ? 0u : 1u;
-                  if (X3) {
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (ks < kslices) {
+                    const uint32_t acc = (first && ks == 0) ? 0u : 1u;
 #pragma unroll
                     for (int sub = 0; sub < MS; ++sub) {          // rows [128 sub, 128 sub + 128) of the tile
                       if (sub > 0 && !sub1_live) continue;        // no output position in the second half (image tail)
@@ -294,9 +344,25 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
                       const uint32_t dt = d_tmem + (uint32_t)(sub * p.BN);
                       umma_tf32_lohi(dt, das + a_lo_u, db + 2u * ks, dhi, idesc, acc);
                       umma_tf32_lohi(dt, das, db + b_lo_u + 2u * ks, dhi, idesc, 1u);
-                      umma_tf32_lohi(dt, das, db + 2u * ks, dhi, idesc, 1u);
                     }
-                  } else {
+                  }
+                }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (ks < kslices) {
+#pragma unroll
+                    for (int sub = 0; sub < MS; ++sub) {
+                      if (sub > 0 && !sub1_live) continue;
+                      const uint32_t das = da + (uint32_t)(sub * TM_BM) * rowu + 2u * ks;
+                      umma_tf32_lohi(d_tmem + (uint32_t)(sub * p.BN), das, db + 2u * ks, dhi, idesc, 1u);
+                    }
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (ks < kslices) {
+                    const uint32_t acc = (first && ks == 0) ? 0u : 1u;
                     umma_tf32_lohi(d_tmem, da + 2u * ks, db + 2u * ks, dhi, idesc, acc);
                   }
                 }
@@ -328,6 +394,22 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
         }
       }
     }
+  } else if (X3 && FUSE) {
+    // ===================== warp 3: 1x1 weights + 3x3 bias of every tile -> shared memory (x3 fused heads) =====================
+    if (lane == 0) {
+      uint32_t phase = 0;
+      for (long long it = 0, tile = tile_at(0); tile < total_tiles; tile = tile_at(++it)) {
+        const int n_tile = (int)(tile % n_tiles);
+        const int head = n_tile / p.tph, part = n_tile - head * p.tph;
+        mbar_wait(smem_u32(&ctl->w2_empty), phase ^ 1u);
+        const uint32_t bar = smem_u32(&ctl->w2_full);
+        mbar_arrive_expect_tx(bar, TM_W2_BUF);
+        bulk_g2s(w2buf, p.fuse_w[head] + (size_t)part * 128 * 16, TM_W2_BYTES, bar);
+        bulk_g2s(w2buf + TM_W2_BYTES, p.bias + (size_t)n_tile * 128, 128u * 4u, bar);
+        phase ^= 1u;
+      }
+    }
+    __syncwarp();
   }
   } else if (X3 && warp >= 12) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -396,6 +478,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     ep.W = p.W;
     int buf = 0;
     uint32_t pf = 0;                     // bit b: phase of p_full[b]
+    uint32_t w2_phase = 0;               // x3 fused heads: phase of w2_full
     float acc2[FUSE ? 16 : 1];           // fused 1x1: the 16 (padded) outputs of this position's head
 #pragma unroll
     for (int j = 0; j < (FUSE ? 16 : 1); ++j) acc2[j] = 0.f;
@@ -448,37 +531,26 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
           buf ^= 1;
         }
         if (FUSE) {
-          // hidden = relu(conv3x3 + bias) never leaves the SM: multiply it with this head's 1x1 weights right here
+          // hidden = relu(conv3x3 + bias) never leaves the SM: multiply it with this head's 1x1 weights right here.
+          // The [128][16] weight block + the 128 biases of this (head, part) were staged in shared memory by warp 3;
+          // only the float4 groups that hold real output channels are read.
           const int head = g.n_tile / p.tph, part = g.n_tile - head * p.tph;
           if (part == 0) {
 #pragma unroll
             for (int j = 0; j < (FUSE ? 16 : 1); ++j) acc2[j] = 0.f;
           }
-          const float* b1 = p.bias + (size_t)g.n_tile * p.BN;
-          const float4* w2 = reinterpret_cast<const float4*>(p.fuse_w[head]) + (size_t)part * p.BN * 4;
-#pragma unroll
-          for (int c = 0; c < (X3 ? 128 : 1); ++c) {
-            if (c < p.BN) {
-              const float v = fmaxf(sums[(X3 ? c : 0)] + __ldg(b1 + c), 0.f);
-              const float4 wa = __ldg(w2 + c * 4), wb = __ldg(w2 + c * 4 + 1), wc = __ldg(w2 + c * 4 + 2),
-                           wd = __ldg(w2 + c * 4 + 3);
-              acc2[FUSE ? 0 : 0] = fmaf(v, wa.x, acc2[FUSE ? 0 : 0]);
-              acc2[FUSE ? 1 : 0] = fmaf(v, wa.y, acc2[FUSE ? 1 : 0]);
-              acc2[FUSE ? 2 : 0] = fmaf(v, wa.z, acc2[FUSE ? 2 : 0]);
-              acc2[FUSE ? 3 : 0] = fmaf(v, wa.w, acc2[FUSE ? 3 : 0]);
-              acc2[FUSE ? 4 : 0] = fmaf(v, wb.x, acc2[FUSE ? 4 : 0]);
-              acc2[FUSE ? 5 : 0] = fmaf(v, wb.y, acc2[FUSE ? 5 : 0]);
-              acc2[FUSE ? 6 : 0] = fmaf(v, wb.z, acc2[FUSE ? 6 : 0]);
-              acc2[FUSE ? 7 : 0] = fmaf(v, wb.w, acc2[FUSE ? 7 : 0]);
-              acc2[FUSE ? 8 : 0] = fmaf(v, wc.x, acc2[FUSE ? 8 : 0]);
-              acc2[FUSE ? 9 : 0] = fmaf(v, wc.y, acc2[FUSE ? 9 : 0]);
-              acc2[FUSE ? 10 : 0] = fmaf(v, wc.z, acc2[FUSE ? 10 : 0]);
-              acc2[FUSE ? 11 : 0] = fmaf(v, wc.w, acc2[FUSE ? 11 : 0]);
-              acc2[FUSE ? 12 : 0] = fmaf(v, wd.x, acc2[FUSE ? 12 : 0]);
-              acc2[FUSE ? 13 : 0] = fmaf(v, wd.y, acc2[FUSE ? 13 : 0]);
-              acc2[FUSE ? 14 : 0] = fmaf(v, wd.z, acc2[FUSE ? 14 : 0]);
-              acc2[FUSE ? 15 : 0] = fmaf(v, wd.w, acc2[FUSE ? 15 : 0]);
-            }
+          if constexpr (X3 && FUSE) {
+            mbar_wait(smem_u32(&ctl->w2_full), w2_phase);
+            w2_phase ^= 1u;
+            const int co = p.fuse_cout[head];
+            if (co <= 4)
+              fused_part_smem<1>(sums, acc2, w2buf, w2buf + TM_W2_BYTES);
+            else if (co <= 8)
+              fused_part_smem<2>(sums, acc2, w2buf, w2buf + TM_W2_BYTES);
+            else
+              fused_part_smem<4>(sums, acc2, w2buf, w2buf + TM_W2_BYTES);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&ctl->w2_empty));
           }
           if (part == p.tph - 1 && valid) fused_store(p, head, acc2, n, oy, ox);
         } else {
@@ -625,6 +697,29 @@ EncodeTiledFn get_encode() {
 static int tma_tile_m(int x3) { return x3 ? 256 : TM_BM; }
 static int tma_boxh(int Wt, int x3) { return (tma_tile_m(x3) + 1 + 2 * Wt + Wt - 1) / Wt + 1; }
 
+// Stage counts of the slab ring (SA) and the weight-tile ring (SB) inside the 227 KB of dynamic shared memory
+// (512 B control block + up to 1024 B alignment + 1536 B slack are reserved).
+static int tma_smem_layout(uint32_t a_stage, uint32_t btile, int k, bool fuse_x3, int* SA, int* SB, size_t* smem) {
+  const size_t extra = fuse_x3 ? TM_W2_BUF : 0;
+  const size_t budget = 222 * 1024 - (fuse_x3 ? 6 * 1024 : 0);      // fused x3: 227 KB - 2.5 KB control - 8.5 KB weights
+  int sa = 2;
+  if ((size_t)sa * a_stage + 2 * (size_t)btile > budget) sa = 1;
+  if ((size_t)sa * a_stage + 2 * (size_t)btile > budget) return fail(CP_ERR_INVALID, "conv_tma: slab does not fit shared memory");
+  int sb = (int)((budget - (size_t)sa * a_stage) / btile);
+  if (sb > 8) sb = 8;
+  if (sb < 2) return fail(CP_ERR_INVALID, "conv_tma: tile does not fit shared memory");
+  if (k == 1 && sa < 4) {
+    // 1x1: slabs are small (16 KB); use up to 4 stages of them
+    int s4 = (int)((budget - (size_t)sb * btile) / a_stage);
+    if (s4 > 4) s4 = 4;
+    if (s4 > sa) sa = s4;
+  }
+  *SA = sa;
+  *SB = sb;
+  *smem = 512 + 2048 + (size_t)sa * a_stage + (size_t)sb * btile + extra;
+  return CP_OK;
+}
+
 int tma_cslab(const IgemmParams& p, int x3) {
   if (p.Cin % 32) return 16;
   if (!x3 || p.kh != 3) return 32;
@@ -744,7 +839,7 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.BN = tma_tile_n(p.CoutPad, x3);
   q.x3 = x3;
   q.cslab = tma_cslab(p, x3);
-  q.group = TM_GROUP_X3 * (32 / q.cslab);       // same number of MMAs per TMEM accumulation group
+  q.group = x3_group_blocks() * (32 / q.cslab);       // same number of MMAs per TMEM accumulation group
   q.k = p.kh;
   q.Wt = p.Win + 2;
   q.tile_m = tma_tile_m(x3);
@@ -762,20 +857,9 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.slab_stride = (q.slab_bytes + 1023u) & ~1023u;
   const uint32_t btile = (uint32_t)q.BN * (uint32_t)q.cslab * 4u * (x3 ? 2u : 1u);
   const uint32_t a_stage = q.slab_stride * (x3 ? 2u : 1u);
-  const size_t budget = 222 * 1024;
-  q.SA = 2;
-  if ((size_t)q.SA * a_stage + 2 * btile > budget) q.SA = 1;
-  if ((size_t)q.SA * a_stage + 2 * btile > budget) return fail(CP_ERR_INVALID, "conv_tma: slab does not fit shared memory");
-  size_t left = budget - (size_t)q.SA * a_stage;
-  q.SB = (int)(left / btile);
-  if (q.SB > 8) q.SB = 8;
-  if (q.SB < 2) return fail(CP_ERR_INVALID, "conv_tma: tile does not fit shared memory");
-  if (q.k == 1 && q.SA < 4) {
-    // 1x1: slabs are small (16 KB); use up to 4 stages of them
-    int sa = (int)((budget - (size_t)q.SB * btile) / a_stage);
-    if (sa > 4) sa = 4;
-    if (sa > q.SA) q.SA = sa;
-  }
+  const bool fuse_x3 = x3 && p.fuse_n > 0;        // + the staged 1x1 weights / 3x3 bias of the current tile
+  size_t smem = 0;
+  if (int rc = tma_smem_layout(a_stage, btile, q.k, fuse_x3, &q.SA, &q.SB, &smem)) return rc;
   q.bias = p.bias;
   q.residual = p.residual;
   q.resStride = p.resStride;
@@ -787,7 +871,7 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.round_tf32 = round_out_tf32;
   q.wtiles = (const unsigned char*)p.wgt_umma;
   if (p.fuse_n > 0) {
-    if (p.fuse_hidden % q.BN || p.CoutPad != p.fuse_n * p.fuse_hidden || !p.relu || p.residual)
+    if (p.fuse_hidden % q.BN || p.CoutPad != p.fuse_n * p.fuse_hidden || !p.relu || p.residual || (x3 && q.BN != 128))
       return fail(CP_ERR_INVALID, "conv_tma: fused 1x1 needs relu, no residual and head_conv a multiple of the N tile");
     q.fuse = 1;
     q.tph = p.fuse_hidden / q.BN;
@@ -798,14 +882,13 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
       q.fuse_cout[h] = p.fuse_cout[h];
     }
   }
-  const size_t smem = 512 + 2048 + (size_t)q.SA * a_stage + (size_t)q.SB * btile;
   void (*kern)(TmaConvParams) = x3 ? (q.fuse ? conv_tma_kernel<true, true> : conv_tma_kernel<true, false>)
                                    : (q.fuse ? conv_tma_kernel<false, true> : conv_tma_kernel<false, false>);
-  static thread_local bool configured[4] = {false, false, false, false};
+  static PerDevice<bool, 4> configured;
   const int slot = (x3 ? 2 : 0) + (q.fuse ? 1 : 0);
-  if (!configured[slot]) {
+  if (!configured.here(slot)) {
     CP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured[slot] = true;
+    configured.here(slot) = true;
   }
   q.m_tiles = (long long)m_tiles;
   int cluster = 1;     // measured: multicast at cluster sizes 2/4 does not cut L2 traffic on this part and couples the CTAs
@@ -815,12 +898,8 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.cluster = cluster;
   const long long m_groups = ((long long)m_tiles + cluster - 1) / cluster;
   q.total_tiles = m_groups * (p.CoutPad / q.BN);
-  static thread_local int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    CP_CUDA_CHECK(cudaGetDevice(&dev));
-    CP_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int num_sms = 0;
+  if (int rc = device_sm_count(&num_sms)) return rc;
   long long nclusters = num_sms / cluster;
   if (q.total_tiles < nclusters) nclusters = q.total_tiles;
   cudaLaunchConfig_t cfg{};

@@ -43,7 +43,6 @@ constexpr int DT_PH = 8, DT_PW = 16;  // output patch (rows x columns) = 128 pos
 constexpr int DT_HALO = 8;           // slab margin around the patch, both directions
 constexpr int DT_SH = DT_PH + 2 * DT_HALO, DT_SW = DT_PW + 2 * DT_HALO;     // slab rows x columns (24 x 32)
 constexpr uint32_t DT_SLAB_BYTES = DT_SH * DT_SW * DT_CS * 4;               // 49152
-constexpr int DT_GROUP = 6;          // x3: K blocks per TMEM accumulation group (= 36 MMAs, as in conv_tma.cu)
 constexpr uint32_t DT_COEF_BYTES = DT_BM * 9 * 16;
 
 struct DcnTmaParams {
@@ -56,6 +55,7 @@ struct DcnTmaParams {
   int tiles_x, tiles_per_image;      // patches per image row / per image
   long long total_tiles;             // m tiles x n tiles (n fastest)
   int SB;
+  int group;                         // x3: K blocks (16 channels) per TMEM accumulation group
   int AH;                            // A stages per gather half (1 or 2)
   const float* bias;
   const float* residual;
@@ -232,18 +232,20 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
         const uint64_t da = dtmpl + (uint64_t)((atiles0 + (uint32_t)((kbi & 1) * p.AH + (sa & 1)) * a_stage) >> 4);
         const uint64_t db = dtmpl + (uint64_t)((btiles0 + (uint32_t)sb * btile_bytes) >> 4);
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
-        const bool last = X3 ? (gk == DT_GROUP - 1 || kbi == KB - 1) : (kbi == KB - 1);
+        const bool last = X3 ? (gk == p.group - 1 || kbi == KB - 1) : (kbi == KB - 1);
         if (elect_one()) {
+          if (X3) {        // cross terms first, hi x hi last (see conv_tma.cu)
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint32_t acc = (first && ks == 0) ? 0u : 1u;
-            if (X3) {
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint32_t acc = (first && ks == 0) ? 0u : 1u;
               umma_tf32(d_tmem, da + a_lo_u + 2 * ks, db + 2 * ks, idesc, acc);
               umma_tf32(d_tmem, da + 2 * ks, db + b_lo_u + 2 * ks, idesc, 1u);
-              umma_tf32(d_tmem, da + 2 * ks, db + 2 * ks, idesc, 1u);
-            } else {
-              umma_tf32(d_tmem, da + 2 * ks, db + 2 * ks, idesc, acc);
             }
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) umma_tf32(d_tmem, da + 2 * ks, db + 2 * ks, idesc, 1u);
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) umma_tf32(d_tmem, da + 2 * ks, db + 2 * ks, idesc, (first && ks == 0) ? 0u : 1u);
           }
           umma_commit(smem_u32(&ctl->b_empty[sb]));
           umma_commit(smem_u32(&ctl->a_empty[sa]));
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
         // into running sums.  The sums live in a third TMEM region (columns [2 BN, 3 BN)) instead of registers, so the
         // tile can be 128 columns wide with 128 epilogue threads: ld group + ld sum -> add -> st sum, 16 columns at a time.
         const uint32_t sum_base = lane_base + (uint32_t)(2 * p.BN);
-        const int ngroups = (KB + DT_GROUP - 1) / DT_GROUP;
+        const int ngroups = (KB + p.group - 1) / p.group;
         for (int gi = 0; gi < ngroups; ++gi) {
           mbar_wait(smem_u32(&ctl->p_full[buf]), (pf >> buf) & 1u);
           tc_fence_after();
@@ -555,6 +557,7 @@ int launch_dcn_tma(const IgemmParams& p, const void* map, int x3, int round_out_
   q.tiles_per_image = q.tiles_x * (p.Hin / DT_PH);
   q.total_tiles = (long long)q.tiles_per_image * p.B * (p.CoutPad / q.BN);
   const uint32_t a_stage = x3 ? 16384u : 8192u;
+  q.group = x3_group_blocks() * 2;      // 16-channel K blocks: same MMA count per group as conv_tma.cu
   q.AH = x3 ? 1 : 2;                  // shared memory: x3 tiles are twice as large
   const uint32_t btile = (uint32_t)q.BN * 64u * (x3 ? 2u : 1u);
   const size_t fixed = 1024 + 2 * (size_t)DT_COEF_BYTES + 1024 + 2 * (size_t)DT_SLAB_BYTES + 2 * (size_t)q.AH * a_stage;
@@ -573,20 +576,16 @@ int launch_dcn_tma(const IgemmParams& p, const void* map, int x3, int round_out_
   q.round_tf32 = round_out_tf32;
   q.wtiles = (const unsigned char*)p.wgt_umma;
   const size_t smem = fixed + (size_t)q.SB * btile;
-  static thread_local bool configured[2] = {false, false};
-  if (!configured[x3 ? 1 : 0]) {
+  static PerDevice<bool, 2> configured;
+  if (!configured.here(x3 ? 1 : 0)) {
     if (x3)
       CP_CUDA_CHECK(cudaFuncSetAttribute(dcn_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     else
       CP_CUDA_CHECK(cudaFuncSetAttribute(dcn_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured[x3 ? 1 : 0] = true;
+    configured.here(x3 ? 1 : 0) = true;
   }
-  static thread_local int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    CP_CUDA_CHECK(cudaGetDevice(&dev));
-    CP_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int num_sms = 0;
+  if (int rc = device_sm_count(&num_sms)) return rc;
   const unsigned grid = (unsigned)(q.total_tiles < num_sms ? q.total_tiles : num_sms);
   if (x3)
     dcn_tma_kernel<true><<<grid, DT_THREADS, smem, stream>>>(q);

@@ -20,6 +20,7 @@
 // semantics (uint8 adds, `== 7` means all gates hold) -- see DESIGN.md.
 #include "common.cuh"
 #include "pose_core.h"
+#include "pnp_warp.cuh"
 
 namespace cp {
 namespace {
@@ -49,9 +50,12 @@ peaks_topk_kernel(const float* __restrict__ hm, const float* __restrict__ hm_hp,
   const int CH = C_hm + J;
   const float* src = (ch < C_hm) ? hm + ((size_t)b * C_hm + ch) * HW : hm_hp + ((size_t)b * J + (ch - C_hm)) * HW;
 
+  // apply_sigmoid: 0 = both maps are probabilities already, 1 = both are logits, 2 = only hm is a logit
+  // (opt.mse_loss: the reference skips the hm_hp sigmoid, object_pose.py:136-138)
+  const bool sig = (ch < C_hm) ? (apply_sigmoid != 0) : (apply_sigmoid == 1);
   for (int i = tid; i < HW; i += TOPK_THREADS) {
     float v = __ldg(src + i);
-    raw[i] = apply_sigmoid ? sigmoid_acc(v) : v;
+    raw[i] = sig ? sigmoid_acc(v) : v;
   }
   __syncthreads();
   // 3x3 max-pool (stride 1, -inf padding) equality NMS: keep = (hmax == heat)
@@ -68,7 +72,7 @@ peaks_topk_kernel(const float* __restrict__ hm, const float* __restrict__ hm_hp,
         m = fmaxf(m, raw[yy * W + xx]);
       }
     }
-    nv[i] = (m == v) ? v : v * 0.0f;
+    nv[i] = (m == v) ? v + 0.0f : 0.0f;      // heat * keep; -0 is canonicalised (torch.topk compares it equal to +0)
   }
   if (tid == 0) {
     s_prefix = 0;
@@ -77,14 +81,21 @@ peaks_topk_kernel(const float* __restrict__ hm, const float* __restrict__ hm_hp,
   }
   __syncthreads();
 
-  // radix select of the K-th largest value (values are >= 0 so the uint order is the float order)
+  // radix select of the K-th largest value on order-preserving keys: positive floats get the sign bit set, negative
+  // floats are bit-inverted, so the unsigned order of the keys is the float order for raw (un-sigmoided, possibly
+  // negative) maps too
+  auto ord = [](float f) -> unsigned int {
+    const unsigned int b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  };
+  auto unord = [](unsigned int k) -> float { return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k); };
   unsigned int mask = 0;
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int i = tid; i < 256; i += TOPK_THREADS) hist[i] = 0;
     __syncthreads();
     const unsigned int prefix = s_prefix;
     for (int i = tid; i < HW; i += TOPK_THREADS) {
-      unsigned int bits = __float_as_uint(nv[i]);
+      unsigned int bits = ord(nv[i]);
       if ((bits & mask) == prefix) atomicAdd(&hist[(bits >> shift) & 255u], 1u);
     }
     __syncthreads();
@@ -109,7 +120,7 @@ peaks_topk_kernel(const float* __restrict__ hm, const float* __restrict__ hm_hp,
   __syncthreads();
   // strictly greater: unordered compaction
   for (int i = tid; i < HW; i += TOPK_THREADS) {
-    unsigned int bits = __float_as_uint(nv[i]);
+    unsigned int bits = ord(nv[i]);
     if (bits > T) {
       unsigned int pos = atomicAdd(&s_cnt, 1u);
       keys[pos] = ((unsigned long long)bits << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)i);
@@ -119,7 +130,7 @@ peaks_topk_kernel(const float* __restrict__ hm, const float* __restrict__ hm_hp,
   const int per = (HW + TOPK_THREADS - 1) / TOPK_THREADS;
   const int i0 = tid * per, i1 = min(HW, i0 + per);
   int mine = 0;
-  for (int i = i0; i < i1; ++i) mine += (__float_as_uint(nv[i]) == T);
+  for (int i = i0; i < i1; ++i) mine += (ord(nv[i]) == T);
   int incl = mine;
   const int lane = tid & 31, wid = tid >> 5;
   for (int o = 1; o < 32; o <<= 1) {
@@ -140,7 +151,7 @@ peaks_topk_kernel(const float* __restrict__ hm, const float* __restrict__ hm_hp,
   __syncthreads();
   int rank = warp_tot[wid] + incl - mine;
   for (int i = i0; i < i1 && rank < (int)need; ++i) {
-    if (__float_as_uint(nv[i]) == T) {
+    if (ord(nv[i]) == T) {
       keys[n_gt + rank] = ((unsigned long long)T << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)i);
       ++rank;
     }
@@ -165,7 +176,7 @@ peaks_topk_kernel(const float* __restrict__ hm, const float* __restrict__ hm_hp,
   }
   if (tid < K) {
     unsigned long long kk = keys[tid];
-    peak_val[((size_t)b * CH + ch) * K + tid] = __uint_as_float((unsigned int)(kk >> 32));
+    peak_val[((size_t)b * CH + ch) * K + tid] = unord((unsigned int)(kk >> 32));
     peak_idx[((size_t)b * CH + ch) * K + tid] = (int)(0xFFFFFFFFu - (unsigned int)(kk & 0xFFFFFFFFull));
   }
 }
@@ -196,201 +207,6 @@ __device__ __forceinline__ void py_slice(int start, int stop, int n, int* s0, in
   stop = max(0, min(stop, n));
   *s0 = start;
   *s1 = max(start, stop);
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Warp-cooperative PnP.  One thread per detection (the first version) left ~4 ms of serial double-precision latency on
-// a handful of lanes: a 12x12 Jacobi eigen-solve and the LM loop with their matrices in local memory.  Here a WARP
-// owns a detection: the matrices live in shared memory, the Jacobi rotations are applied by 12 + 12 lanes, the LM
-// Jacobian is one point per lane, and the small dependent pieces (rotation angles, 6x6 Cholesky, Rodrigues) are
-// computed redundantly by every lane from identical inputs (bitwise identical results, so control flow stays uniform).
-// Same algorithm and iteration order as pose::dlt_init / pose::refine_lm (pose_core.h), which remain the host-tested
-// statement of the math.
-constexpr int PNP_SCRATCH = 320;      // doubles per warp: [0,288) Jacobi A|V or LM workspace, [288,320) image points
-
-__device__ void dlt_init_warp(const double* X, const double* uv, int n, double fx, double fy, double cx, double cy,
-                              double* R, double* t, double* sm, int lane) {
-  double* A = sm;
-  double* V = sm + 144;
-  for (int e = lane; e < 144; e += 32) {
-    const int a = e / 12, b = e - a * 12;
-    double acc = 0.0;
-    for (int i = 0; i < n; ++i) {
-      const double x = (uv[2 * i] - cx) / fx, y = (uv[2 * i + 1] - cy) / fy;
-      const double h[4] = {X[3 * i], X[3 * i + 1], X[3 * i + 2], 1.0};
-      const double r1a = a < 4 ? h[a] : (a < 8 ? 0.0 : -x * h[a - 8]);
-      const double r1b = b < 4 ? h[b] : (b < 8 ? 0.0 : -x * h[b - 8]);
-      const double r2a = a < 4 ? 0.0 : (a < 8 ? h[a - 4] : -y * h[a - 8]);
-      const double r2b = b < 4 ? 0.0 : (b < 8 ? h[b - 4] : -y * h[b - 8]);
-      acc += r1a * r1b + r2a * r2b;
-    }
-    A[e] = acc;
-    V[e] = (a == b) ? 1.0 : 0.0;
-  }
-  __syncwarp();
-  const int k = lane < 12 ? lane : lane - 12;       // lanes 0-11 rotate A, lanes 12-23 rotate V
-  for (int sweep = 0; sweep < 60; ++sweep) {
-    double off = 0.0, diag = 0.0;
-    for (int i = 0; i < 12; ++i) {
-      diag += A[i * 12 + i] * A[i * 12 + i];
-      for (int j = i + 1; j < 12; ++j) off += A[i * 12 + j] * A[i * 12 + j];
-    }
-    if (off <= 1e-60 * diag || off == 0.0) break;
-    for (int p = 0; p < 11; ++p)
-      for (int q = p + 1; q < 12; ++q) {
-        const double apq = A[p * 12 + q];
-        if (apq == 0.0) continue;
-        const double app = A[p * 12 + p], aqq = A[q * 12 + q];
-        const double theta = (aqq - app) / (2.0 * apq);
-        const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
-        __syncwarp();                                 // everybody has read A[p][q], A[p][p], A[q][q]
-        if (lane < 12) {
-          const double akp = A[k * 12 + p], akq = A[k * 12 + q];
-          A[k * 12 + p] = c * akp - s * akq;
-          A[k * 12 + q] = s * akp + c * akq;
-        } else if (lane < 24) {
-          const double vkp = V[k * 12 + p], vkq = V[k * 12 + q];
-          V[k * 12 + p] = c * vkp - s * vkq;
-          V[k * 12 + q] = s * vkp + c * vkq;
-        }
-        __syncwarp();
-        if (lane < 12) {
-          const double apk = A[p * 12 + k], aqk = A[q * 12 + k];
-          A[p * 12 + k] = c * apk - s * aqk;
-          A[q * 12 + k] = s * apk + c * aqk;
-        }
-        __syncwarp();
-      }
-  }
-  int m = 0;
-  for (int i = 1; i < 12; ++i)
-    if (A[i * 12 + i] < A[m * 12 + m]) m = i;
-  double pv[12];
-  for (int i = 0; i < 12; ++i) pv[i] = V[i * 12 + m];
-  __syncwarp();
-  pose::dlt_finish(pv, R, t);
-}
-
-// sum_i |project(R X_i + t) - uv_i|^2: one point per lane, summed in point order by every lane
-__device__ double reproj_cost_warp(const double* X, const double* uv, int n, const double* R, const double* t, double fx,
-                                   double fy, double cx, double cy, double* part, int lane) {
-  __syncwarp();
-  if (lane < n) {
-    const double* x = X + 3 * lane;
-    const double px = R[0] * x[0] + R[1] * x[1] + R[2] * x[2] + t[0];
-    const double py = R[3] * x[0] + R[4] * x[1] + R[5] * x[2] + t[1];
-    const double pz = R[6] * x[0] + R[7] * x[1] + R[8] * x[2] + t[2];
-    const double du = fx * px / pz + cx - uv[2 * lane];
-    const double dv = fy * py / pz + cy - uv[2 * lane + 1];
-    part[lane] = du * du + dv * dv;
-  }
-  __syncwarp();
-  double c = 0.0;
-  for (int i = 0; i < n; ++i) c += part[i];
-  return c;
-}
-
-__device__ double refine_lm_warp(const double* X, const double* uv, int n, double fx, double fy, double cx, double cy,
-                                 double* R, double* t, double* sm, int lane) {
-  double* J = sm;            // [16][14]: Ju[6], Jv[6], ru, rv
-  double* AG = sm + 224;     // 21 lower-triangle entries of J^T J, then 6 of J^T r
-  double* part = sm + 256;   // [16]
-  double lam = 1e-3;
-  double cost = reproj_cost_warp(X, uv, n, R, t, fx, fy, cx, cy, part, lane);
-  for (int iter = 0; iter < 20; ++iter) {       // cv2 TermCriteria MAX_ITER, see pose::refine_lm
-    __syncwarp();
-    if (lane < n) {
-      const double* x = X + 3 * lane;
-      const double qx = R[0] * x[0] + R[1] * x[1] + R[2] * x[2];
-      const double qy = R[3] * x[0] + R[4] * x[1] + R[5] * x[2];
-      const double qz = R[6] * x[0] + R[7] * x[1] + R[8] * x[2];
-      const double px = qx + t[0], py = qy + t[1], pz = qz + t[2];
-      const double iz = 1.0 / pz;
-      const double du[3] = {fx * iz, 0.0, -fx * px * iz * iz};
-      const double dv[3] = {0.0, fy * iz, -fy * py * iz * iz};
-      double* Jr = J + lane * 14;
-      Jr[0] = du[1] * (-qz) + du[2] * qy;
-      Jr[1] = du[0] * qz + du[2] * (-qx);
-      Jr[2] = du[0] * (-qy) + du[1] * qx;
-      Jr[6] = dv[1] * (-qz) + dv[2] * qy;
-      Jr[7] = dv[0] * qz + dv[2] * (-qx);
-      Jr[8] = dv[0] * (-qy) + dv[1] * qx;
-      for (int kk = 0; kk < 3; ++kk) {
-        Jr[3 + kk] = du[kk];
-        Jr[9 + kk] = dv[kk];
-      }
-      Jr[12] = fx * px * iz + cx - uv[2 * lane];
-      Jr[13] = fy * py * iz + cy - uv[2 * lane + 1];
-    }
-    __syncwarp();
-    if (lane < 27) {
-      double val = 0.0;
-      if (lane < 21) {
-        int a = 0;
-        while ((a + 1) * (a + 2) / 2 <= lane) ++a;      // lower-triangle index -> (a, b), b <= a
-        const int b = lane - a * (a + 1) / 2;
-        for (int i = 0; i < n; ++i) val += J[i * 14 + a] * J[i * 14 + b] + J[i * 14 + 6 + a] * J[i * 14 + 6 + b];
-      } else {
-        const int a = lane - 21;
-        for (int i = 0; i < n; ++i) val += J[i * 14 + a] * J[i * 14 + 12] + J[i * 14 + 6 + a] * J[i * 14 + 13];
-      }
-      AG[lane] = val;
-    }
-    __syncwarp();
-    double A[36], g[6];
-    for (int a = 0; a < 6; ++a) {
-      g[a] = AG[21 + a];
-      for (int b = 0; b <= a; ++b) {
-        const double v = AG[a * (a + 1) / 2 + b];
-        A[a * 6 + b] = v;
-        A[b * 6 + a] = v;
-      }
-    }
-    bool improved = false;
-    double d[6], Rn[9], tn[3], cn = 0.0;
-    for (int tr = 0; tr < 30; ++tr) {
-      if (pose::solve6(A, g, lam, d)) {
-        double E[9];
-        pose::rodrigues(d, E);
-        pose::mat3_mul(E, R, Rn);
-        for (int kk = 0; kk < 3; ++kk) tn[kk] = t[kk] + d[3 + kk];
-        cn = reproj_cost_warp(X, uv, n, Rn, tn, fx, fy, cx, cy, part, lane);
-        if (cn == cn && cn <= cost && fabs(cn) < 1e300) {
-          improved = true;
-          break;
-        }
-      }
-      lam *= 10.0;
-    }
-    if (!improved) break;
-    double step = 0.0;
-    for (int kk = 0; kk < 6; ++kk) step += d[kk] * d[kk];
-    step = sqrt(step);
-    for (int kk = 0; kk < 9; ++kk) R[kk] = Rn[kk];
-    for (int kk = 0; kk < 3; ++kk) t[kk] = tn[kk];
-    const double dec = cost - cn;
-    cost = cn;
-    lam = lam * 0.1;
-    if (lam < 1e-12) lam = 1e-12;
-    if (step < 1e-10 || dec <= 1e-28 * (cost > 1e-300 ? cost : 1e-300)) break;
-  }
-  return cost;
-}
-
-// pose::solve_and_shell, executed by a whole warp; every lane ends with the same PnPOut
-__device__ void solve_and_shell_warp(const double* pts, int n_in, const float* obj_scale, const double* Kc, double width,
-                                     double height, int visible_thresh, int opencv_return, pose::PnPOut* o, double* sm,
-                                     int lane) {
-  double V[24], X[48], uv[32];
-  const int n = pose::pnp_collect(pts, n_in, obj_scale, V, X, uv);
-  o->n_pts = n;
-  o->status = CP_PNP_FEW_POINTS;
-  if (n < 6) return;
-  double R[9], t[3];
-  dlt_init_warp(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t, sm, lane);
-  const double cost = refine_lm_warp(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t, sm, lane);
-  pose::pnp_finish(V, R, t, cost, n, Kc, width, height, visible_thresh, opencv_return, o);
 }
 
 __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
@@ -527,7 +343,7 @@ __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
             double v = 0.0;
             if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
               float raw = __ldg(hp + yy * W + xx);
-              v = (double)(P.apply_sigmoid ? sigmoid_acc(raw) : raw);
+              v = (double)(P.apply_sigmoid == 1 ? sigmoid_acc(raw) : raw);
             }
             win[rr * nc + cc] = v;
           }
@@ -547,7 +363,7 @@ __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
         if (ix < 0) ix += W;
         if (iy >= 0 && iy < H && ix >= 0 && ix < W) {   // the reference raises IndexError outside
           float raw = __ldg(hp + iy * W + ix);
-          height = P.apply_sigmoid ? sigmoid_acc(raw) : raw;
+          height = P.apply_sigmoid == 1 ? sigmoid_acc(raw) : raw;
           mean_x = sx;
           mean_y = sy;
           std_x = 1.0f;
@@ -763,10 +579,10 @@ int cp_decode_pnp(const cp_decode_params* prm, const cp_heads* heads, const doub
 
   const int HW = prm->out_h * prm->out_w;
   const size_t smem = (size_t)HW * 2 * sizeof(float);
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
+  static cp::PerDevice<size_t> configured;
+  if (smem > configured.here()) {
     CP_CUDA_CHECK(cudaFuncSetAttribute(peaks_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    configured.here() = smem;
   }
   dim3 g1(prm->num_classes + prm->num_joints, prm->batch);
   peaks_topk_kernel<<<g1, TOPK_THREADS, smem, s>>>(heads->hm, heads->hm_hp, prm->num_classes, prm->num_joints,
@@ -782,10 +598,10 @@ int cp_decode_pnp(const cp_decode_params* prm, const cp_heads* heads, const doub
   ga.dets = dets_buf;
   ga.poses = poses;
   ga.n_valid = n_valid;
-  static thread_local bool pose_configured = false;
-  if (!pose_configured) {      // static (~29 KB) + dynamic (20 KB) shared memory crosses the 48 KB default
+  static cp::PerDevice<bool> pose_configured;
+  if (!pose_configured.here()) {      // static (~29 KB) + dynamic (20 KB) shared memory crosses the 48 KB default
     CP_CUDA_CHECK(cudaFuncSetAttribute(group_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    pose_configured = true;
+    pose_configured.here() = true;
   }
   group_pose_kernel<<<prm->batch, 256, 8 * PNP_SCRATCH * sizeof(double), s>>>(ga);
   CP_LAUNCH_CHECK("group_pose_kernel");

@@ -26,7 +26,8 @@ namespace {
 
 constexpr int UM_BM = 128;
 constexpr int UM_PROD_WARPS = 8;            // A-gather warps: two threads per tile row, 4 chunks each
-constexpr int UM_THREADS = (UM_PROD_WARPS + 2) * 32;
+constexpr int UM_THREADS = (UM_PROD_WARPS + 2 + 4) * 32;   // + 4 promoter / epilogue warps (tf32x3 only; idle otherwise)
+constexpr int UM_PROMO_WARP0 = UM_PROD_WARPS + 2;
 constexpr uint32_t ROW_BYTES = 128;        // one K block = 128 bytes per row (64 bf16 / 32 tf32)
 constexpr uint32_t A_TILE_BYTES = UM_BM * ROW_BYTES;
 
@@ -64,6 +65,7 @@ struct UmmaSmem {   // control block at the head of dynamic smem (the tiles foll
   unsigned long long full[8];
   unsigned long long empty[8];
   unsigned long long accum_full;
+  unsigned long long p_full[2], p_empty[2];     // tf32x3: accumulation-group buffers (MMA issuer <-> promoter warps)
   uint32_t tmem_base;
 };
 
@@ -105,10 +107,15 @@ __global__ void __launch_bounds__(UM_THREADS) igemm_umma_kernel(const IgemmParam
       mbar_init(smem_u32(&ctl->empty[s]), 1);
     }
     mbar_init(smem_u32(&ctl->accum_full), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&ctl->p_full[s]), 1);
+      mbar_init(smem_u32(&ctl->p_empty[s]), 128);
+    }
     fence_mbar_init();
   }
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < BN * NACC) tmem_cols <<= 1;
+  // tf32x3: two accumulation-group buffers + BN columns of promoted sums (NACC = K blocks per group); else NACC accumulators
+  while ((int)tmem_cols < BN * (PREC == 1 ? 3 : NACC)) tmem_cols <<= 1;
   if (warp == UM_PROD_WARPS) {
     tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     tmem_relinquish();
@@ -271,8 +278,8 @@ __global__ void __launch_bounds__(UM_THREADS) igemm_umma_kernel(const IgemmParam
       }
     }
 
-    // =========================== epilogue (warps 0-3): TMEM lane == tile row ===========================
-    if (warp < 4) {
+    // =========================== epilogue (warps 0-3): TMEM lane == tile row (bf16; tf32x3: promoter warps) =====
+    if (PREC != 1 && warp < 4) {
     const int m = m0 + tid;
     const bool valid = m < M;
     int ox = 0, oy = 0, n = 0;
@@ -328,35 +335,123 @@ __global__ void __launch_bounds__(UM_THREADS) igemm_umma_kernel(const IgemmParam
       const uint32_t idesc = make_idesc(BN, T::kFmt);
       int stage = 0;
       uint32_t phase = 0;
+      int gk = 0, buf = 0;                   // tf32x3: K block inside its accumulation group / group buffer
+      uint32_t pe = 0;                       // bit b: phase of p_empty[b]
       for (int kb = 0; kb < KB; ++kb) {
+        if (PREC == 1 && gk == 0) mbar_wait(smem_u32(&ctl->p_empty[buf]), ((pe >> buf) & 1u) ^ 1u);
         mbar_wait(smem_u32(&ctl->full[stage]), phase);
         tc_fence_after();
         const uint32_t a_hi = tiles0 + (uint32_t)stage * stage_bytes;
         const uint32_t b_hi = a_hi + a_bytes;
         const uint64_t da_hi = make_desc(a_hi), db_hi = make_desc(b_hi);
-        const uint32_t d_tmem = tmem_base + (uint32_t)((kb % NACC) * BN);
-        const bool fresh = kb < NACC;        // first K block of this accumulator overwrites it
+        // tf32x3: the accumulator truncates, so only NACC K blocks are chained in TMEM; every finished group is promoted
+        // into round-to-nearest fp32 sums by the promoter warps (same two-level scheme as conv_tma.cu / dcn_tma.cu)
+        const uint32_t d_tmem = tmem_base + (uint32_t)((PREC == 1 ? buf : (kb % NACC)) * BN);
+        const bool fresh = PREC == 1 ? (gk == 0) : (kb < NACC);        // first K block of this accumulator overwrites it
+        if (PREC == 0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {       // 4 x 32-byte K slices per 128-byte row
-          const uint64_t adv = (uint64_t)(k * 2);
-          if (PREC == 0) {
-            umma<0>(d_tmem, da_hi + adv, db_hi + adv, idesc, (!fresh || k > 0) ? 1u : 0u);
-          } else {
-            const uint64_t da_lo = make_desc(a_hi + A_TILE_BYTES), db_lo = make_desc(b_hi + (uint32_t)BN * ROW_BYTES);
+          for (int k = 0; k < 4; ++k)        // 4 x 32-byte K slices per 128-byte row
+            umma<0>(d_tmem, da_hi + (uint64_t)(k * 2), db_hi + (uint64_t)(k * 2), idesc, (!fresh || k > 0) ? 1u : 0u);
+        } else {                            // cross terms first, hi x hi last (see conv_tma.cu)
+          const uint64_t da_lo = make_desc(a_hi + A_TILE_BYTES), db_lo = make_desc(b_hi + (uint32_t)BN * ROW_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);
             umma<1>(d_tmem, da_lo + adv, db_hi + adv, idesc, (!fresh || k > 0) ? 1u : 0u);
             umma<1>(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
-            umma<1>(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
           }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma<1>(d_tmem, da_hi + (uint64_t)(k * 2), db_hi + (uint64_t)(k * 2), idesc, 1u);
         }
         umma_commit(smem_u32(&ctl->empty[stage]));     // frees the stage when these MMAs have read it
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
         }
+        if (PREC == 1) {
+          if (gk == NACC - 1 || kb == KB - 1) {
+            umma_commit(smem_u32(&ctl->p_full[buf]));
+            pe ^= 1u << buf;
+            buf ^= 1;
+            gk = 0;
+          } else {
+            ++gk;
+          }
+        }
       }
-      umma_commit(smem_u32(&ctl->accum_full));
+      if (PREC != 1) umma_commit(smem_u32(&ctl->accum_full));
     }
     __syncwarp();
+  } else if (warp >= UM_PROMO_WARP0) {
+    // =========================== tf32x3: promoter + epilogue warps, TMEM lane == tile row ===========================
+    if (PREC == 1) {
+      const int q = warp & 3;                    // TMEM lane quadrant this warp may access
+      const int row = q * 32 + lane;
+      const int m = m0 + row;
+      const bool valid = m < M;
+      int ox = 0, oy = 0, n = 0;
+      if (valid) {
+        ox = m % p.Wout;
+        int t = m / p.Wout;
+        oy = t % p.Hout;
+        n = t / p.Hout;
+      }
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+      const uint32_t sum_base = lane_base + (uint32_t)(2 * BN);
+      const int ngroups = (KB + NACC - 1) / NACC;
+      int buf = 0;
+      uint32_t pf = 0;
+      for (int gi = 0; gi < ngroups; ++gi) {
+        mbar_wait(smem_u32(&ctl->p_full[buf]), (pf >> buf) & 1u);
+        tc_fence_after();
+        for (int c = 0; c * 16 < BN; ++c) {
+          uint32_t rr[16], ss[16];
+          tmem_ld16(lane_base + (uint32_t)(buf * BN + c * 16), rr);
+          if (gi > 0) tmem_ld16(sum_base + (uint32_t)(c * 16), ss);
+          tmem_ld_wait();
+          if (gi > 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(__uint_as_float(ss[j]) + __uint_as_float(rr[j]));
+          }
+          tmem_st16(sum_base + (uint32_t)(c * 16), rr);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&ctl->p_empty[buf]));
+        pf ^= 1u << buf;
+        buf ^= 1;
+      }
+      EpiParams ep;
+      ep.bias = p.bias;
+      ep.residual = p.residual;
+      ep.resStride = p.resStride;
+      ep.relu = p.relu;
+      ep.res_after_relu = p.res_after_relu;
+      ep.round_tf32 = 0;
+      ep.out = p.out;
+      ep.outStride = p.outStride;
+      ep.out_nchw = p.out_nchw;
+      ep.Cout = p.Cout;
+      ep.CoutPad = p.CoutPad;
+      ep.H = p.Hout;
+      ep.W = p.Wout;
+      const int col_end = min(p.Cout, (n_tile + 1) * BN);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t rr[32];
+        tmem_ld16(sum_base + (uint32_t)c0, rr);
+        if (c0 + 16 < BN) {
+          tmem_ld16(sum_base + (uint32_t)(c0 + 16), rr + 16);
+        } else {
+#pragma unroll
+          for (int j = 16; j < 32; ++j) rr[j] = 0u;
+        }
+        tmem_ld_wait();
+        float vv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(rr[j]);
+        epilogue_sub_tile(ep, nullptr, vv, lane, valid, m, n, oy, ox, n_tile * BN + c0, col_end);
+      }
+    }
   } else {
     // =========================== weight-tile loader (one lane) ===========================
     if (lane == 0) {
@@ -428,7 +523,11 @@ __global__ void pack_umma_weight_kernel(const float* __restrict__ src, int ld, i
 }  // namespace
 
 // ---- host side -----------------------------------------------------------------------------------------------
-int umma_tile_n(int CoutPad) { return CoutPad <= 256 ? CoutPad : 256; }
+// tf32x3 keeps two accumulation-group buffers and the promoted sums in TMEM: 3 BN <= 512 columns
+int umma_tile_n(int CoutPad, int prec) {
+  const int cap = prec == 1 ? 128 : 256;
+  return CoutPad <= cap ? CoutPad : cap;
+}
 
 bool umma_supported(const IgemmParams& p, int prec) {
   if (p.mode != IGEMM_NHWC_VEC && p.mode != IGEMM_DCN) return false;
@@ -436,7 +535,7 @@ bool umma_supported(const IgemmParams& p, int prec) {
   if (p.Cin % ch) return false;
   for (int s = 0; s < p.nsrc; ++s)
     if (p.srcC[s] % ch || p.srcStride[s] % 4) return false;
-  const int bn = umma_tile_n(p.CoutPad);
+  const int bn = umma_tile_n(p.CoutPad, prec);
   if (bn % 16 || p.CoutPad % bn) return false;
   return true;
 }
@@ -444,7 +543,7 @@ bool umma_supported(const IgemmParams& p, int prec) {
 size_t umma_weight_bytes(int Kreal, int CoutPad, int prec) {
   const int elems = prec == 0 ? 64 : 32;
   const int KB = (Kreal + elems - 1) / elems;
-  const int bn = umma_tile_n(CoutPad);
+  const int bn = umma_tile_n(CoutPad, prec);
   return (size_t)(CoutPad / bn) * KB * bn * ROW_BYTES * (prec == 0 ? 1 : 2);
 }
 
@@ -452,7 +551,7 @@ int launch_pack_umma_weight(const float* src, int ld, int Kreal, int Cout, int C
                             cudaStream_t s) {
   const int elems = prec == 0 ? 64 : 32;
   const int KB = (Kreal + elems - 1) / elems;
-  const int bn = umma_tile_n(CoutPad);
+  const int bn = umma_tile_n(CoutPad, prec);
   const int nt = CoutPad / bn;
   size_t total = (size_t)nt * KB * bn * 8;
   int blocks = (int)((total + 255) / 256);
@@ -468,7 +567,7 @@ int launch_pack_umma_weight(const float* src, int ld, int Kreal, int Cout, int C
 int launch_igemm_umma(const IgemmParams& p, int prec, cudaStream_t stream) {
   if (!umma_supported(p, prec)) return fail(CP_ERR_INVALID, "igemm_umma: unsupported shape");
   if (!p.wgt_umma) return fail(CP_ERR_INVALID, "igemm_umma: weight tiles missing");
-  const int bn = umma_tile_n(p.CoutPad);
+  const int bn = umma_tile_n(p.CoutPad, prec);
   const int tilesA = prec == 0 ? 1 : 2;
   const size_t stage_bytes = (size_t)A_TILE_BYTES * tilesA + (size_t)bn * ROW_BYTES * tilesA;
   int stages = (int)((204 * 1024) / stage_bytes);
@@ -485,21 +584,14 @@ int launch_igemm_umma(const IgemmParams& p, int prec, cudaStream_t stream) {
     kern = (p.mode == IGEMM_DCN) ? igemm_umma_kernel<0, IGEMM_DCN> : igemm_umma_kernel<0, IGEMM_NHWC_VEC>;
   else
     kern = (p.mode == IGEMM_DCN) ? igemm_umma_kernel<1, IGEMM_DCN> : igemm_umma_kernel<1, IGEMM_NHWC_VEC>;
-  static thread_local bool configured[4] = {false, false, false, false};
+  static PerDevice<bool, 4> configured;
   const int slot = prec * 2 + (p.mode == IGEMM_DCN ? 1 : 0);
-  if (!configured[slot]) {
+  if (!configured.here(slot)) {
     CP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured[slot] = true;
+    configured.here(slot) = true;
   }
-  int nacc = 1;                                   // tf32x3: split the K chain over up to 4 TMEM accumulators
-  if (prec == 1) {
-    nacc = 512 / bn;
-    if (nacc > 4) nacc = 4;
-    const int elems = 32;
-    const int KBn = (p.kh * p.kw * p.Cin + elems - 1) / elems;
-    if (nacc > KBn) nacc = KBn;
-    if (nacc < 1) nacc = 1;
-  }
+  // tf32x3: K blocks (12 MMAs each) per TMEM accumulation group, promoted into fp32 sums by the promoter warps
+  const int nacc = prec == 1 ? x3_group_blocks() : 1;
   kern<<<grid, UM_THREADS, smem, stream>>>(p, bn, stages, nacc);
   CP_LAUNCH_CHECK("igemm_umma_kernel");
   return CP_OK;

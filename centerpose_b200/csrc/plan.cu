@@ -119,6 +119,7 @@ struct cp_plan {
   int min_tc_cin = 32;           // ops with fewer input channels stay on the CUDA-core kernels (CP_MIN_TC_CIN overrides)
   bool no_fuse_heads = false;    // CP_NO_FUSE_HEADS=1: keep the per-head 1x1 convs as separate launches
   bool no_dcn_tma = false;       // CP_NO_DCN_TMA=1: deformable convs on the global-gather kernel (A/B measurements)
+  bool no_umma = false;          // CP_NO_UMMA=1: ops the TMA kernels do not take stay on the fp32 CUDA-core kernel (diagnostics)
   unsigned char* umma_wts = nullptr;
   size_t umma_bytes = 0;
 };
@@ -580,25 +581,25 @@ int build_graph(cp_plan* P) {
         op.use_tma = true;
         op.umma_off = P->umma_bytes;
         P->umma_bytes += (tma_weight_bytes(op.Cin, op.kh * op.kw, op.CoutPad, P->prec == 1) + 1023) / 1024 * 1024;
-      } else if (umma_supported(q, gather_prec)) {
+      } else if (!P->no_umma && umma_supported(q, gather_prec)) {
         op.use_umma = true;
         op.umma_off = P->umma_bytes;
         P->umma_bytes += (umma_weight_bytes(op.kh * op.kw * op.Cin, op.CoutPad, gather_prec) + 1023) / 1024 * 1024;
       }
     }
   }
-  // The per-head 1x1 convs move into the epilogue of the merged heads conv when that one runs on conv_tma.  Single-pass
-  // tf32 only: there the epilogue has a whole tile of MMA time to hide 4096 FMAs per position (heads 3.8 -> 3.4 ms and
-  // the seven 1x1 launches disappear).  In tf32x3 the same epilogue threads also promote the accumulation groups of the
-  // NEXT tile, and the extra work stalls the MMA warp (measured 6.5 -> 9.9 ms), so the fusion is off unless
-  // CP_FUSE_HEADS_X3=1.
-  const bool fuse_x3 = getenv("CP_FUSE_HEADS_X3") && atoi(getenv("CP_FUSE_HEADS_X3"));
-  if (P->prec == 2 || (P->prec == 1 && fuse_x3)) {
+  // The per-head 1x1 convs move into the epilogue of the merged heads conv when that one runs on conv_tma: hidden =
+  // relu(conv3x3) never reaches HBM (3.7 GB of writes + 3.7 GB of reads and seven launches at batch 32).  Single-pass
+  // tf32: the epilogue thread that owns a position multiplies it with the head's [256][16] weights (3.8 -> 3.4 ms).
+  // tf32x3: the same threads also promote the accumulation groups of the NEXT tile, so the 1x1 weights + 3x3 bias of
+  // the tile are staged in shared memory by a dedicated warp and only the float4 groups holding real output channels are
+  // multiplied (heads 7.7 -> 5.2 ms; the first version, 16 padded outputs through __ldg, stalled the promotion: 9.9 ms).
+  if (P->prec == 2 || P->prec == 1) {
     for (auto& op : P->ops) {
       if (op.head_children.empty() || !op.use_tma || P->no_fuse_heads) continue;
       const int bn = tma_tile_n(op.CoutPad, P->prec == 1);
       bool ok = op.relu && !op.has_res && (c.head_conv % bn == 0) && (int)op.head_children.size() <= 16 &&
-                op.CoutPad == (int)op.head_children.size() * c.head_conv;
+                op.CoutPad == (int)op.head_children.size() * c.head_conv && (P->prec != 1 || bn == 128);
       for (int ci : op.head_children) {
         const Op& ch = P->ops[ci];
         ok = ok && ch.CoutPad == 16 && ch.w_ld == 16 && ch.Cin == c.head_conv && ch.out_head >= 0 && !ch.relu && !ch.has_res;
@@ -652,6 +653,15 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
   if (const char* e = getenv("CP_MIN_TC_CIN")) P->min_tc_cin = atoi(e);
   if (const char* e = getenv("CP_NO_FUSE_HEADS")) P->no_fuse_heads = atoi(e) != 0;
   if (const char* e = getenv("CP_NO_DCN_TMA")) P->no_dcn_tma = atoi(e) != 0;
+  if (const char* e = getenv("CP_NO_UMMA")) P->no_umma = atoi(e) != 0;
+  // the plan lives on cfg->device; the caller's current device is restored on every exit path
+  struct DeviceGuard {
+    int prev = -1;
+    ~DeviceGuard() {
+      if (prev >= 0) cudaSetDevice(prev);
+    }
+  } guard;
+  CP_CUDA_CHECK(cudaGetDevice(&guard.prev));
   CP_CUDA_CHECK(cudaSetDevice(cfg->device));
   int rc = build_graph(P.get());
   if (rc) return rc;
@@ -1028,7 +1038,7 @@ int cp_infer(cp_plan* P, int32_t batch, const float* images, const float* pre_im
   q.batch = batch;
   q.out_h = P->H / 4;
   q.out_w = P->W / 4;
-  q.apply_sigmoid = 1;
+  q.apply_sigmoid = prm->apply_sigmoid == 2 ? 2 : 1;     // the plan's heads are logits; 2 = opt.mse_loss (raw hm_hp)
   size_t need = cp_decode_workspace_bytes(&q);
   if (need > P->decode_ws_bytes) {
     // grows only on the first call for a given K / batch (not steady state)

@@ -218,10 +218,10 @@ bool conv3_c16_supported(const IgemmParams& p) {
 int launch_conv3_c16(const IgemmParams& p, cudaStream_t s) {
   if (!conv3_c16_supported(p)) return fail(CP_ERR_INVALID, "conv3_c16: unsupported shape");
   const size_t smem = ((size_t)9 * 16 * 16 + (size_t)16 * C3_PLANE) * sizeof(float);
-  static thread_local bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured;
+  if (!configured.here()) {
     CP_CUDA_CHECK(cudaFuncSetAttribute(conv3_c16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configured.here() = true;
   }
   dim3 grid((p.Win + C3_W - 1) / C3_W, (p.Hin + C3_TY - 1) / C3_TY, p.B);
   dim3 block(C3_TX, C3_TY);
@@ -240,10 +240,10 @@ bool stem_supported(const IgemmParams& p) {
 int launch_stem_conv(const IgemmParams& p, cudaStream_t s) {
   if (!stem_supported(p)) return fail(CP_ERR_INVALID, "stem_conv: unsupported shape");
   const size_t smem = ((size_t)p.Cin * ST_HALO_H * ST_HALO_W + (size_t)49 * p.Cin * 16) * sizeof(float);
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static PerDevice<size_t> configured;
+  if (smem > 48 * 1024 && smem > configured.here()) {
     CP_CUDA_CHECK(cudaFuncSetAttribute(stem_conv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    configured.here() = smem;
   }
   dim3 grid((p.Win + ST_W - 1) / ST_W, (p.Hin + ST_TY - 1) / ST_TY, p.B);
   dim3 block(ST_TX, ST_TY);

@@ -39,7 +39,8 @@ def decode_params(opt=None, **over):
         raise ValueError("unknown category '%s' (cuboid_pnp_shell.py:59-66)" % cat)
     p.visible_thresh = _VISIBLE[cat]
     p.opencv_return = int(bool(g("show_axes", False)))
-    p.apply_sigmoid = int(over.get("apply_sigmoid", 1))
+    # object_pose.py:136-138: hm always goes through sigmoid_, hm_hp only when not opt.mse_loss
+    p.apply_sigmoid = int(over.get("apply_sigmoid", 2 if bool(g("mse_loss", False)) else 1))
     p.use_pnp = int(bool(g("use_pnp", True)))
     p.vis_thresh = float(g("vis_thresh", 0.3))
     bal = g("balance_coefficient", None)
@@ -131,7 +132,8 @@ class Engine(object):
             cfg.head_channels[i] = int(self.heads[self.head_names[i]])
         self._cfg = cfg
         plan = ctypes.c_void_p()
-        _lib.check(self.L.cp_plan_create(ctypes.byref(cfg), ctypes.byref(plan)), "cp_plan_create")
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.cp_plan_create(ctypes.byref(cfg), ctypes.byref(plan)), "cp_plan_create")
         self.plan = plan
         self.weights_sig = None
         self.forward_launches = int(self.L.cp_plan_forward_launches(plan))
@@ -167,19 +169,38 @@ class Engine(object):
             _lib.check(rc, "cp_plan_load_weights")
             torch.cuda.current_stream().synchronize()   # borrowed tensors may be freed after this
 
+    def _dev(self, t, name, shape):
+        """Every tensor handed to the kernels by data_ptr() must be a contiguous fp32 tensor ON THE PLAN'S DEVICE: a
+        CPU tensor or one on another GPU would become a wild device pointer (sticky illegal-address error).  Like the
+        reference (`images.to(opt.device)`, base_detector.py:436-441) tensors that live elsewhere are moved."""
+        if not torch.is_tensor(t):
+            raise TypeError("%s must be a torch tensor" % name)
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError("%s %s does not fit the plan: expected %s" % (name, tuple(t.shape), tuple(shape)))
+        if t.device != self.device or t.dtype != torch.float32:
+            t = t.to(self.device, torch.float32)
+        return t.contiguous()
+
     def _check_inputs(self, x, pre_img, pre_hm, pre_hm_hp):
         B = x.shape[0]
-        if tuple(x.shape[1:]) != (3, self.height, self.width) or B > self.max_batch:
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, self.height, self.width) or B > self.max_batch or B < 1:
             raise ValueError("input %s does not fit the plan (%d,3,%d,%d)" % (tuple(x.shape), self.max_batch,
                                                                             self.height, self.width))
-        xs = [x.contiguous().float()]
+        xs = [self._dev(x, "images", (B, 3, self.height, self.width))]
         if self.tracking:
             if pre_img is None or pre_hm is None or pre_hm_hp is None:
                 raise ValueError("a tracking plan needs pre_img, pre_hm and pre_hm_hp")
-            xs += [pre_img.contiguous().float(), pre_hm.contiguous().float(), pre_hm_hp.contiguous().float()]
+            xs += [self._dev(pre_img, "pre_img", (B, 3, self.height, self.width)),
+                   self._dev(pre_hm, "pre_hm", (B, 1, self.height, self.width)),
+                   self._dev(pre_hm_hp, "pre_hm_hp", (B, 8, self.height, self.width))]
         else:
             xs += [None, None, None]
         return B, xs
+
+    def _out_tensor(self, t, name, shape, dtype):
+        if t.device != self.device or t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+            raise ValueError("%s must be a contiguous %s tensor of shape %s on %s" % (name, dtype, tuple(shape), self.device))
+        return t
 
     def forward(self, x, pre_img=None, pre_hm=None, pre_hm_hp=None, out=None):
         """Head logits {name: [B,C,H/4,W/4] fp32 CUDA}."""
@@ -187,6 +208,9 @@ class Engine(object):
         if out is None:
             out = {n: torch.empty((B, c, self.height // 4, self.width // 4), dtype=torch.float32, device=self.device)
                    for n, c in self.heads.items()}
+        else:
+            for n, c in self.heads.items():
+                self._out_tensor(out[n], "out[%s]" % n, (B, c, self.height // 4, self.width // 4), torch.float32)
         hp = (ctypes.c_void_p * len(self.head_names))(*[out[n].data_ptr() for n in self.head_names])
         with torch.cuda.device(self.device):
             rc = self.L.cp_forward(self.plan, B, _ptr(xs[0]), _ptr(xs[1]), _ptr(xs[2]), _ptr(xs[3]), hp, _stream())
@@ -213,14 +237,26 @@ class Engine(object):
               poses=None, n_valid=None, dets=None):
         """forward + decode + PnP in one native call.  Returns (dets|None, poses, n_valid)."""
         B, xs = self._check_inputs(x, pre_img, pre_hm, pre_hm_hp)
+        if not torch.is_tensor(meta) or tuple(meta.shape) != (B, _lib.CP_META_DOUBLES):
+            raise ValueError("meta must be a [%d,%d] tensor (make_meta)" % (B, _lib.CP_META_DOUBLES))
+        if meta.device != self.device or meta.dtype != torch.float64 or not meta.is_contiguous():
+            meta = meta.to(self.device, torch.float64).contiguous()
         if poses is None:
             poses = torch.empty((B, prm.K, _lib.CP_POSE_RECORD), dtype=torch.float32, device=self.device)
+        else:
+            self._out_tensor(poses, "poses", (B, prm.K, _lib.CP_POSE_RECORD), torch.float32)
         if n_valid is None:
             n_valid = torch.empty((B,), dtype=torch.int32, device=self.device)
+        else:
+            self._out_tensor(n_valid, "n_valid", (B,), torch.int32)
         if want_dets and dets is None:
             dets = torch.empty((B, prm.K, _lib.CP_DETS_RECORD), dtype=torch.float32, device=self.device)
+        elif dets is not None:
+            self._out_tensor(dets, "dets", (B, prm.K, _lib.CP_DETS_RECORD), torch.float32)
         hp = None
         if heads_out is not None:
+            for n, c in self.heads.items():
+                self._out_tensor(heads_out[n], "heads_out[%s]" % n, (B, c, self.height // 4, self.width // 4), torch.float32)
             hp = (ctypes.c_void_p * len(self.head_names))(*[heads_out[n].data_ptr() for n in self.head_names])
         with torch.cuda.device(self.device):
             rc = self.L.cp_infer(self.plan, B, _ptr(xs[0]), _ptr(xs[1]), _ptr(xs[2]), _ptr(xs[3]), ctypes.byref(prm),

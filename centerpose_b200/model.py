@@ -262,11 +262,28 @@ def create_model(arch, heads, head_conv, opt=None):
     return _model_factory[name](num_layers=num_layers, heads=heads, head_conv=head_conv, opt=opt)
 
 
+def _load_checkpoint(model_path):
+    """Checkpoints are downloaded files: unpickle with `weights_only=True` (reference checkpoints hold only
+    `epoch`, `state_dict` and `optimizer` tensors/ints).  A checkpoint that needs arbitrary pickled classes is only
+    loaded when CENTERPOSE_B200_UNSAFE_LOAD=1 is set explicitly."""
+    import os
+    import warnings
+    try:
+        return torch.load(model_path, map_location="cpu", weights_only=True)
+    except Exception as e:            # pickle.UnpicklingError and friends
+        if os.environ.get("CENTERPOSE_B200_UNSAFE_LOAD", "") != "1":
+            raise RuntimeError("load_model: %s cannot be read with weights_only=True (%s); set "
+                               "CENTERPOSE_B200_UNSAFE_LOAD=1 to unpickle it anyway if you trust the file"
+                               % (model_path, e))
+        warnings.warn("load_model: unpickling %s with weights_only=False (arbitrary code execution risk)" % model_path)
+        return torch.load(model_path, map_location="cpu", weights_only=False)
+
+
 def load_model(model, model_path, optimizer=None, resume=False, lr=None, lr_step=None):
     """models/model.py:34-87: strips `module.`, tolerates shape mismatches and
     missing keys with the same messages, restores the optimizer on resume."""
     start_epoch = 0
-    checkpoint = torch.load(model_path, map_location=lambda storage, loc: storage, weights_only=False)
+    checkpoint = _load_checkpoint(model_path)
     print("loaded {}, epoch {}".format(model_path, checkpoint["epoch"]))
     state_dict = {}
     for k, v in checkpoint["state_dict"].items():

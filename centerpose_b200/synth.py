@@ -210,3 +210,25 @@ def planted_batch(batch, n_obj=3, seed=0, heads=None, **kw):
         hs.append(h)
         truths.append(t)
     return {k: np.stack([h[k] for h in hs]) for k in hs[0]}, truths
+
+
+def calibrate_head_bias(model, heads_out, target=4):
+    """Random-init weights put every (or no) heat-map peak above the decode thresholds, which would make the
+    decode / PnP stage do 100 (or 0) solves per frame.  Given the head logits `heads_out` of a calibration batch
+    ({'hm': [B,1,h,w], 'hm_hp': [B,8,h,w]} torch tensors, any device), shift the two heat-map biases of `model` so
+    that about `target` centre peaks per frame pass vis_thresh = 0.3 and about `target` peaks per keypoint channel
+    pass the 0.1 gate -- a realistic scene density for the post-network stage.  Setup only (bench / tests), never
+    inside a timed region.  Returns the two shifts."""
+    import torch.nn.functional as F
+    shifts = {}
+    with torch.no_grad():
+        for head, thr in (("hm", math.log(0.3 / 0.7)), ("hm_hp", math.log(0.1 / 0.9))):
+            hm = heads_out[head].float()
+            pk = F.max_pool2d(hm, 3, 1, 1)
+            peaks = torch.where(pk == hm, hm, torch.full_like(hm, -1e9)).flatten(2)      # [B, C, HW]
+            kth = peaks.topk(target + 1, dim=2).values
+            mid = (0.5 * (kth[..., target - 1] + kth[..., target])).median()
+            delta = float(thr - mid)
+            getattr(model, head)[-1].bias += delta
+            shifts[head] = delta
+    return shifts

@@ -169,7 +169,8 @@ typedef struct cp_decode_params {
   int32_t nms;             /* opt.nms (demo.py:114 sets True)                              */
   int32_t visible_thresh;  /* cuboid_pnp_shell.py:59-66: 6 book/chair/cereal_box, 3 camera/bottle/cup, 0 bike/laptop/shoe */
   int32_t opencv_return;   /* opt.show_axes: return the OpenCV pose instead of OpenGL      */
-  int32_t apply_sigmoid;   /* 1: hm / hm_hp are logits                                     */
+  int32_t apply_sigmoid;   /* 0: hm / hm_hp are probabilities; 1: both are logits; 2: only hm is a logit
+                            * (opt.mse_loss: hm_hp is decoded raw, object_pose.py:136-138)  */
   int32_t use_pnp;         /* opt.use_pnp                                                  */
   float vis_thresh;        /* opt.vis_thresh (0.3)                                         */
   float balance;           /* opt.balance_coefficient[opt.c] (2)                           */

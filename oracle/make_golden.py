@@ -37,6 +37,8 @@ NET_CASES = [
     ("net_dla34_b2_96x128", "dla_34", False, 2, 96, 128, 3, 101),
     ("net_dlav1_b1_64x64", "dlav1_34", False, 1, 64, 64, 4, 102),
     ("net_dla34track_b1_64x96", "dla_34", True, 1, 64, 96, 5, 103),
+    # the benched shape (BASELINE.json configs[1]/[2]: 512 x 512, dla_34): feature maps 128 / 64 / 32 / 16 wide
+    ("net_dla34_b1_512", "dla_34", False, 1, 512, 512, 12, 104),
 ]
 
 DECODE_CASES = [
@@ -60,10 +62,12 @@ def net_inputs(batch, H, W, seed, tracking):
     return x, extra
 
 
-def make_net():
+def make_net(only=None):
     import centerpose_b200 as cpb
     from lib.models.model import create_model as ref_create
     for name, arch, trk, B, H, W, wseed, iseed in NET_CASES:
+        if only and name not in only:
+            continue
         opt = ref_shims.make_opt(arch, tracking_task=trk)
         ours = cpb.create_model(opt.arch, opt.heads, opt.head_conv, cpb.default_opt(arch, tracking_task=trk))
         sd = synth.seeded_state_dict(ours, seed=wseed, offset_std=0.3)
@@ -200,6 +204,9 @@ if __name__ == "__main__":
     ref_shims.install()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
-    make_dcn()
-    make_net()
-    make_decode()
+    only = set(sys.argv[1:])
+    if not only:
+        make_dcn()
+    make_net(only)
+    if not only:
+        make_decode()

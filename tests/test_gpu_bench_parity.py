@@ -1,0 +1,198 @@
+"""Parity on the configuration bench.py measures: 512 x 512, dla_34, the tensor-core plans
+(`tf32x3` = the headline parity mode, `tf32` = the fast mode with its own bound), batch 1 and batch 32, and the
+whole image -> pose chain against the CPU oracle chain `net_ref -> decode_ref -> pnp_ref` on the same uint8 frames.
+
+At 512 x 512 the feature maps are 128 / 64 / 32 / 16 wide, i.e. the layers take the code paths the small fixtures
+never reach: 32-channel slabs with 256-position tiles crossing image rows and images, `dcn_tma` 8 x 16 patches on
+every DLAUp / IDAUp level, the fused heads epilogue, > 148 tiles per launch.
+"""
+import functools
+
+import numpy as np
+import pytest
+import torch
+
+import centerpose_b200 as cpb
+from centerpose_b200 import _lib as L
+from centerpose_b200 import synth
+from tests.util import TOL_HEAD_REL_512, golden, net_case_inputs, oracle_records
+
+pytestmark = pytest.mark.gpu
+
+# drift of the fast modes at 512 x 512 (max-abs / max|head|): measured 1.1e-2 (tf32), bounded with margin
+TOL_512 = {"fp32": TOL_HEAD_REL_512, "tf32x3": TOL_HEAD_REL_512, "tf32": 5e-2}
+
+
+def _model(wseed, precision, offset_std=0.3, head_gain=1.0):
+    opt = cpb.default_opt("dla_34")
+    m = cpb.create_model(opt.arch, opt.heads, opt.head_conv, opt)
+    m.precision = precision
+    sd = synth.seeded_state_dict(m, seed=wseed, offset_std=offset_std, head_gain=head_gain)
+    m.load_state_dict(sd)
+    return m.cuda().eval(), opt, sd
+
+
+@functools.lru_cache(maxsize=None)
+def _golden_512():
+    g = golden("net_dla34_b1_512")
+    x, _ = net_case_inputs(g)
+    return g, x
+
+
+@functools.lru_cache(maxsize=None)
+def _truth_512():
+    """fp64 CPU evaluation of the oracle graph on the golden's input (once per session, ~1 min)."""
+    import os
+    from oracle import net_ref
+    from tests.util import GOLD
+    g, x = _golden_512()
+    opt = cpb.default_opt("dla_34")
+    cache = os.path.join(GOLD, "_cache", "net_dla34_b1_512_truth64.npz")     # git-ignored, written in the build container
+    if os.path.exists(cache):
+        z = np.load(cache)
+        return {h: z[h] for h in opt.heads}
+    m = cpb.create_model(opt.arch, opt.heads, opt.head_conv, opt)
+    sd = synth.seeded_state_dict(m, seed=int(g["wseed"]), offset_std=float(g["offset_std"]))
+    sd64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in sd.items()}
+    out = net_ref.forward(torch.from_numpy(x).double(), sd64, opt.heads, "dla_34")
+    return {h: v.numpy() for h, v in out.items()}
+
+
+@pytest.mark.parametrize("prec", ["tf32x3", "tf32", "fp32"])
+def test_512_b1_matches_reference_golden(prec, cplib):
+    """(i) batch 1, 512 x 512 vs the golden heads of the UNMODIFIED reference (oracle/make_golden.py) and, for the
+    parity modes, vs the fp64 truth: the CUDA heads may be no further from fp64 than 4x the reference's own fp32 path."""
+    g, x = _golden_512()
+    m, opt, _ = _model(int(g["wseed"]), prec, float(g["offset_std"]))
+    out = m(torch.from_numpy(x).cuda())[-1]
+    truth = _truth_512() if prec != "tf32" else None
+    for h in opt.heads:
+        want = g["head_" + h]
+        got = out[h].cpu().numpy()
+        assert np.isfinite(got).all(), h
+        mag = np.abs(want).max()
+        e = np.abs(got - want).max() / mag
+        msg = "512x512 b1 %-7s %-10s gpu-vs-ref %.2e" % (prec, h, e)
+        if truth is not None:
+            e_ref = np.abs(want.astype(np.float64) - truth[h]).max() / mag
+            e_gpu = np.abs(got.astype(np.float64) - truth[h]).max() / mag
+            msg += "  gpu-vs-fp64 %.2e  ref-fp32-vs-fp64 %.2e" % (e_gpu, e_ref)
+            assert e_gpu <= 4.0 * e_ref + 3e-5, msg
+        print(msg)
+        assert e <= TOL_512[prec], msg
+
+
+@pytest.mark.parametrize("prec", ["tf32x3", "tf32"])
+def test_512_frame17_of_b32(prec, cplib):
+    """(ii) frame 17 of a 32-frame batch (the benched batch) == the same frame alone (bit-identical: frames are
+    independent) and matches the CPU oracle on that frame."""
+    from oracle import net_ref
+    m, opt, sd = _model(12, prec)
+    frames = synth.synthetic_frames(32, 512, 512, seed=4242)
+    x = torch.from_numpy(synth.normalize_frames(frames))
+    full = m(x.cuda())[-1]
+    one = m(x[17:18].contiguous().cuda())[-1]
+    last = m(x[31:32].contiguous().cuda())[-1]
+    for h in opt.heads:
+        assert torch.equal(full[h][17:18], one[h]), "frame 17 of the batch differs from the frame alone: " + h
+        assert torch.equal(full[h][31:32], last[h]), "the last frame of the batch differs from the frame alone: " + h
+    want = net_ref.forward(x[17:18], sd, opt.heads, "dla_34")
+    for h in opt.heads:
+        w = want[h].numpy()
+        e = np.abs(one[h].cpu().numpy() - w).max() / np.abs(w).max()
+        print("512x512 b32[17] %-7s %-10s gpu-vs-oracle %.2e" % (prec, h, e))
+        assert e <= TOL_512[prec], (h, e)
+
+
+# ------------------------------------------------------------------------------------------- image -> pose
+def _match(got, want):
+    """Pairs (i_got, i_want) of records whose box centres agree to < 1 px (the top-K order may swap on score ties)."""
+    pairs, used = [], set()
+    for j in range(want.shape[0]):
+        d = np.abs(got[:, L.P_CT:L.P_CT + 2] - want[j, L.P_CT:L.P_CT + 2]).max(axis=1) if got.shape[0] else np.zeros(0)
+        cand = [i for i in np.argsort(d) if i not in used and d[i] < 1.0]
+        if cand:
+            used.add(cand[0])
+            pairs.append((cand[0], j))
+    return pairs
+
+
+E2E_FRAMES = 6
+
+
+@functools.lru_cache(maxsize=None)
+def _e2e_oracle():
+    """Calibrated weights + the oracle chain on E2E_FRAMES uint8 frames (CPU, once per session)."""
+    from oracle import decode_ref, net_ref
+    m, opt, _ = _model(0, "fp32", offset_std=0.3)
+    frames = synth.synthetic_frames(E2E_FRAMES, 512, 512, seed=977)
+    x = torch.from_numpy(synth.normalize_frames(frames))
+    synth.calibrate_head_bias(m, m(x.cuda())[-1], target=4)       # setup: ~4 centre peaks per frame pass vis_thresh
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    cam = synth.default_camera(512, 512)
+    prm = decode_ref.DecodeParams(rep_mode=opt.rep_mode, vis_thresh=opt.vis_thresh, category=opt.c)
+    c = np.array([256., 256.], np.float32)
+    recs = []
+    for b in range(E2E_FRAMES):
+        heads = net_ref.forward(x[b:b + 1], sd, opt.heads, "dla_34")
+        _, r = oracle_records({k: v[0].numpy() for k, v in heads.items()}, prm, cam, 512, 512, c, 512.0, L)
+        recs.append(r)
+    return sd, frames, cam, recs
+
+
+# stated end-to-end bounds (image pixels / sign-normalised quaternion) for records that keep the same keypoint
+# source (regressed vs heat-map peak) in both pipelines.  The network heads carry the fp32 floor of stage B
+# (<= 1e-3 * max|head| at 512 x 512, i.e. up to ~0.03 map px = 0.12 image px on `hps`), so the stage-A bar of 1e-3 px
+# does not transfer to image -> pose; the measured numbers are printed and recorded in DESIGN.md section 5.
+E2E_BOUNDS = {"tf32x3": dict(score=2e-3, px=0.25, quat=5e-2, stable_frac=0.9),
+              "tf32": dict(score=5e-2, px=8.0, quat=1.0, stable_frac=0.5)}
+
+
+@pytest.mark.parametrize("prec", ["tf32x3", "tf32"])
+def test_image_to_pose_vs_oracle_chain(prec, cplib):
+    """Same uint8 frames + calibrated weights: `run_batch()` records vs `net_ref -> decode_ref -> pnp_ref` records."""
+    sd, frames, cam, want = _e2e_oracle()
+    opt = cpb.default_opt("dla_34")
+    m = cpb.create_model(opt.arch, opt.heads, opt.head_conv, opt)
+    m.precision = prec
+    m.load_state_dict(sd)
+    det = cpb.ObjectPoseDetector(opt, model=m)
+    poses, n_valid = det.run_batch(frames, cam)
+    bnd = E2E_BOUNDS[prec]
+    n_want = n_got = n_pair = n_stable = 0
+    worst = dict(score=0.0, px=0.0, quat=0.0, loc_rel=0.0)
+    for b in range(E2E_FRAMES):
+        got = poses[b, :n_valid[b]].astype(np.float64)
+        w = want[b]
+        # detections within 2e-3 of vis_thresh may legitimately fall on either side
+        margin = np.abs(w[:, L.P_SCORE] - opt.vis_thresh) > 2e-3 if w.shape[0] else np.zeros(0, bool)
+        n_want += int(margin.sum())
+        n_got += got.shape[0]
+        pairs = _match(got, w)
+        n_pair += sum(1 for i, j in pairs if margin[j])
+        for i, j in pairs:
+            worst["score"] = max(worst["score"], abs(got[i, L.P_SCORE] - w[j, L.P_SCORE]))
+            dk = np.abs(got[i, L.P_KPS:L.P_KPS + 16] - w[j, L.P_KPS:L.P_KPS + 16]).max()
+            dh = np.abs(got[i, L.P_KPS_HM_MEAN:L.P_KPS_HM_MEAN + 16] - w[j, L.P_KPS_HM_MEAN:L.P_KPS_HM_MEAN + 16]).max()
+            if max(dk, dh) > 2.0:          # a grouping gate flipped (regressed <-> heat-map peak): not a drift sample
+                continue
+            n_stable += 1
+            dd = np.abs(got[i, L.P_KPS_DISP_MEAN:L.P_KPS_DISP_MEAN + 16] -
+                        w[j, L.P_KPS_DISP_MEAN:L.P_KPS_DISP_MEAN + 16]).max()
+            worst["px"] = max(worst["px"], dk, dh, dd, np.abs(got[i, L.P_BBOX:L.P_BBOX + 4] - w[j, L.P_BBOX:L.P_BBOX + 4]).max())
+            if int(got[i, L.P_STATUS]) in (L.PNP_OK, L.PNP_INVISIBLE) and int(w[j, L.P_STATUS]) in (L.PNP_OK, L.PNP_INVISIBLE):
+                q1, q2 = w[j, L.P_QUAT:L.P_QUAT + 4], got[i, L.P_QUAT:L.P_QUAT + 4]
+                if np.dot(q1, q2) < 0:
+                    q2 = -q2
+                worst["quat"] = max(worst["quat"], np.abs(q1 - q2).max())
+                t1, t2 = w[j, L.P_LOCATION:L.P_LOCATION + 3], got[i, L.P_LOCATION:L.P_LOCATION + 3]
+                worst["loc_rel"] = max(worst["loc_rel"], np.abs(t1 - t2).max() / np.linalg.norm(t1))
+    print("image->pose %s: oracle dets %d (away from the threshold), gpu dets %d, matched %d, same keypoint source %d; "
+          "max drift: score %.2e, keypoints/boxes %.3e px, quaternion %.2e, location %.2e (relative)"
+          % (prec, n_want, n_got, n_pair, n_stable, worst["score"], worst["px"], worst["quat"], worst["loc_rel"]))
+    assert n_want > 0
+    assert n_pair == n_want, "a detection away from the score threshold is missing on the GPU path"
+    assert n_stable >= bnd["stable_frac"] * n_pair
+    assert worst["score"] <= bnd["score"]
+    assert worst["px"] <= bnd["px"]
+    assert worst["quat"] <= bnd["quat"]

@@ -17,6 +17,11 @@ TOL_LOC_REL = 1e-4      # location, relative to |t|
 # fp32 implementations is only meaningful relative to that floor.)  tests/test_gpu_net.py additionally requires
 # the CUDA heads to be no further from the fp64 truth than 4x the reference's fp32 path + 3e-5.
 TOL_HEAD_REL = 3e-4
+# At 512 x 512 (the benched shape) the fp32 floor is higher: the reference's own fp32 CPU heads are 1.2e-4 .. 2.6e-4
+# of max|head| away from the fp64 evaluation (64x more positions, 128-wide deformable sampling), so the bar between
+# two fp32-equivalent implementations is 1e-3 there -- always together with the fp64-truth criterion
+# (gpu-vs-fp64 <= 4 x reference-fp32-vs-fp64 + 3e-5).
+TOL_HEAD_REL_512 = 1e-3
 
 
 def golden(name):

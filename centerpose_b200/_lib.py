@@ -32,6 +32,11 @@ P_LOCATION, P_QUAT, P_REPROJ, P_PROJ_CUBOID, P_KPS_3D_CAM, P_KPS_PNP, P_SRC_INDE
 # cp_dets_field
 D_BBOX, D_SCORE, D_CLS, D_KPS, D_OBJ_SCALE, D_OBJ_SCALE_UNC, D_TRACKING, D_TRACKING_HP = 0, 4, 5, 6, 22, 25, 28, 30
 D_KPS_DISP_MEAN, D_KPS_DISP_STD, D_KPS_HM_MEAN, D_KPS_HM_STD, D_KPS_HM_HEIGHT, D_IND = 46, 62, 78, 94, 110, 118
+# cp_track_field
+CP_TRACK_RECORD = 320
+T_ID, T_AGE, T_ACTIVE, T_IN_BOXES, T_PNP2_STATUS, T_CONF_AVG = 192, 193, 194, 195, 196, 197
+T_KPS_FUSION_MEAN, T_KPS_FUSION_STD, T_KPS_MEAN_KF, T_KPS_STD_KF = 200, 216, 232, 248
+T_OBJ_SCALE_KF, T_OBJ_SCALE_UNC_KF, T_KPS_PNP_KF, T_KPS_3D_CAM_KF = 264, 267, 270, 288
 # cp_pnp_status
 PNP_NOT_RUN, PNP_OK, PNP_INVISIBLE, PNP_BEHIND, PNP_FEW_POINTS, PNP_SOLVER_FAIL = 0, 1, 2, 3, 4, 5
 
@@ -40,6 +45,7 @@ EXPORTS = [
     "cp_forward", "cp_plan_bytes", "cp_plan_forward_launches", "cp_decode_workspace_bytes",
     "cp_decode_pnp", "cp_infer", "cp_dcn_v2_forward", "cp_preprocess", "cp_plan_num_ops", "cp_plan_profile",
     "cp_dcn_v2_forward_ex", "cp_conv2d",
+    "cp_tracker_create", "cp_tracker_destroy", "cp_tracker_reset", "cp_tracker_step", "cp_tracker_render",
 ]
 
 
@@ -74,6 +80,13 @@ class CpDecodeParams(ctypes.Structure):
         ("apply_sigmoid", ctypes.c_int32), ("use_pnp", ctypes.c_int32),
         ("vis_thresh", ctypes.c_float), ("balance", ctypes.c_float), ("reserved", ctypes.c_float),
     ]
+
+
+class CpTrackerConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "streams", "max_tracks", "kalman", "scale_pool", "use_pnp", "hps_uncertainty", "max_age", "visible_thresh",
+        "opencv_return", "render_hm_mode", "render_hmhp_mode", "device")] + [
+        (n, ctypes.c_float) for n in ("new_thresh", "pre_thresh", "R", "conf_lo", "conf_hi")]
 
 
 _lib = None
@@ -119,6 +132,11 @@ def load():
     L.cp_conv2d.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     L.cp_preprocess.argtypes = [vp, vp, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_float),
                                 ctypes.POINTER(ctypes.c_float), vp]
+    L.cp_tracker_create.argtypes = [ctypes.POINTER(CpTrackerConfig), ctypes.POINTER(vp)]
+    L.cp_tracker_destroy.argtypes = [vp]
+    L.cp_tracker_reset.argtypes = [vp, i32, vp]
+    L.cp_tracker_step.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp]
+    L.cp_tracker_render.argtypes = [vp, i32, vp, vp, i32, i32, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("cp_version", "cp_last_error", "cp_plan_bytes", "cp_plan_forward_launches",

@@ -202,6 +202,20 @@ __device__ void solve_and_shell_warp(const double* pts, int n_in, const float* o
   pose::pnp_finish(V, R, t, cost, n, Kc, width, height, visible_thresh, opencv_return, o);
 }
 
+// same with the cuboid vertices given (tracker: second PnP with the pooled float64 scale)
+__device__ void solve_and_shell_warp_v(const double* pts, int n_in, const double* V, const double* Kc, double width,
+                                       double height, int visible_thresh, int opencv_return, pose::PnPOut* o, double* sm,
+                                       int lane) {
+  double X[48], uv[32];
+  const int n = pose::pnp_collect_v(pts, n_in, V, X, uv);
+  o->n_pts = n;
+  o->status = CP_PNP_FEW_POINTS;
+  if (n < 6) return;
+  double R[9], t[3];
+  dlt_init_warp(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t, sm, lane);
+  const double cost = refine_lm_warp(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t, sm, lane);
+  pose::pnp_finish(V, R, t, cost, n, Kc, width, height, visible_thresh, opencv_return, o);
+}
 
 }  // namespace
 }  // namespace cp

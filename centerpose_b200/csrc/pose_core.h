@@ -18,7 +18,7 @@
 
 #if defined(__CUDACC__)
 #define CP_HD __host__ __device__ __forceinline__
-#define CP_HDN __host__ __device__
+#define CP_HDN inline __host__ __device__
 #else
 #define CP_HD inline
 #define CP_HDN inline
@@ -348,6 +348,37 @@ CP_HDN double refine_lm(const double* X, const double* uv, int n, double fx, dou
 //   Kc:  camera matrix row-major; width/height: image size for kps_pnp normalisation
 //   visible_thresh: 6 / 3 / 0 (see cp_decode_params)
 // pnp_collect: cuboid vertices + the points that are not the -10000 sentinel; returns their number.
+// same with the vertices given (tracker: the pooled scale is float64, so are its vertices -- tracker.py:263-273)
+CP_HDN int pnp_collect_v(const double* pts, int n_in, const double* V /*24*/, double* X /*48*/, double* uv /*32*/) {
+  int n = 0;
+  const int per = n_in / 8;
+  for (int i = 0; i < n_in; ++i) {
+    if (pts[2 * i] < -5000.0 || pts[2 * i + 1] < -5000.0) continue;
+    uv[2 * n] = pts[2 * i];
+    uv[2 * n + 1] = pts[2 * i + 1];
+    const double* v = V + 3 * (i / per);
+    X[3 * n] = v[0];
+    X[3 * n + 1] = v[1];
+    X[3 * n + 2] = v[2];
+    ++n;
+  }
+  return n;
+}
+
+// Cuboid3d(scale / scale[1]).get_vertices() in float64 (scale is a float64 array there)
+CP_HD void cuboid_vertices_d(const double* scale, double* V /*[8][3]*/) {
+  const double hx = (scale[0] / scale[1]) / 2.0, hy = (scale[1] / scale[1]) / 2.0, hz = (scale[2] / scale[1]) / 2.0;
+  int t = 0;
+  for (int ix = 0; ix < 2; ++ix)
+    for (int iy = 0; iy < 2; ++iy)
+      for (int iz = 0; iz < 2; ++iz) {
+        V[t * 3 + 0] = ix ? hx : -hx;
+        V[t * 3 + 1] = iy ? hy : -hy;
+        V[t * 3 + 2] = iz ? hz : -hz;
+        ++t;
+      }
+}
+
 CP_HDN int pnp_collect(const double* pts, int n_in, const float* obj_scale, double* V /*24*/, double* X /*48*/,
                        double* uv /*32*/) {
   cuboid_vertices(obj_scale, V);
@@ -447,6 +478,20 @@ CP_HDN void solve_and_shell(const double* pts, int n_in, const float* obj_scale,
                             double height, int visible_thresh, int opencv_return, PnPOut* o) {
   double V[24], X[48], uv[32];
   const int n = pnp_collect(pts, n_in, obj_scale, V, X, uv);
+  o->n_pts = n;
+  o->status = 4;  // CP_PNP_FEW_POINTS
+  if (n < 6) return;
+  double R[9], t[3];
+  dlt_init(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t);
+  const double cost = refine_lm(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t);
+  pnp_finish(V, R, t, cost, n, Kc, width, height, visible_thresh, opencv_return, o);
+}
+
+// solve_and_shell with the cuboid vertices given
+CP_HDN void solve_and_shell_v(const double* pts, int n_in, const double* V, const double* Kc, double width, double height,
+                              int visible_thresh, int opencv_return, PnPOut* o) {
+  double X[48], uv[32];
+  const int n = pnp_collect_v(pts, n_in, V, X, uv);
   o->n_pts = n;
   o->status = 4;  // CP_PNP_FEW_POINTS
   if (n < 6) return;

@@ -20,6 +20,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "../../include/centerpose_b200.h"
 #include "pose_core.h"
 
 namespace cp {
@@ -227,6 +228,213 @@ CP_HDN void greedy_associate(const float* det_c, const float* det_size, const in
       det_of_trk[best] = i;
     }
   }
+}
+
+
+// ---- one track ------------------------------------------------------------------------------------------------------
+struct Slot {
+  float rec[CP_POSE_RECORD];     // the detection the track carries (cp_pose_field layout, image pixels)
+  int id, age, active, has_kf;
+  int has_pnp_kf;                // the second PnP of the latest step returned a tuple ('kps_pnp_kf' in the track dict)
+  float kps_pnp_kf[18];          // its 9 normalised projected points (centre first)
+  double fus_mean[16], fus_std[16];
+  Filter f;
+};
+
+CP_HD void slot_fusion(const Cfg& c, Slot* s) {
+  gaussian_fusion(s->rec + CP_P_KPS_DISP_MEAN, s->rec + CP_P_KPS_DISP_STD, s->rec + CP_P_KPS_HM_MEAN, s->rec + CP_P_KPS_HM_STD,
+                  c.hps_uncertainty, s->fus_mean, s->fus_std);
+}
+
+// tracker.py:103-116 as running sums (the reference re-adds the whole history in the same order every frame)
+CP_HD void scale_pool_add(Slot* s, bool first) {
+  for (int k = 0; k < 3; ++k) {
+    const double u = (double)s->rec[CP_P_OBJ_SCALE_UNC + k];
+    const double w = 1.0 / (u * u);
+    s->f.sp_w[k] = (first ? 0.0 : s->f.sp_w[k]) + w;
+    s->f.sp_m[k] = (first ? 0.0 : s->f.sp_m[k]) + w * (double)s->rec[CP_P_OBJ_SCALE + k];
+  }
+}
+
+// Step 2 (tracker.py:167-186): detection `rec` continues track `old`
+CP_HDN void entry_matched(const Cfg& c, Slot* dst, const Slot* old, const float* rec) {
+  for (int i = 0; i < CP_POSE_RECORD; ++i) dst->rec[i] = rec[i];
+  dst->id = old->id;
+  dst->age = 1;
+  dst->active = old->active + 1;
+  dst->has_kf = old->has_kf;
+  dst->has_pnp_kf = 0;
+  dst->f = old->f;
+  slot_fusion(c, dst);
+  if (c.kalman) {
+    for (int i = 0; i < 8; ++i) kf_predict_update_kp(&dst->f, i, dst->fus_mean, dst->fus_std, dst->rec + CP_P_TRACKING_HP, c.R);
+    dst->has_kf = 1;
+  }
+  if (c.scale_pool) scale_pool_add(dst, false);
+}
+
+// Step 3 (tracker.py:188-204): an unmatched detection above new_thresh starts a track
+CP_HDN void entry_new(const Cfg& c, Slot* dst, const float* rec, int id) {
+  for (int i = 0; i < CP_POSE_RECORD; ++i) dst->rec[i] = rec[i];
+  dst->id = id;
+  dst->age = 1;
+  dst->active = 1;
+  dst->has_kf = 0;
+  dst->has_pnp_kf = 0;
+  slot_fusion(c, dst);
+  for (int i = 0; i < 32; ++i) dst->f.x[i] = 0.0;
+  for (int i = 0; i < 8; ++i)
+    for (int e = 0; e < 16; ++e) dst->f.P[i][e] = 0.0;
+  for (int k = 0; k < 3; ++k) dst->f.sp_w[k] = dst->f.sp_m[k] = 0.0;
+  if (c.kalman) {
+    for (int i = 0; i < 8; ++i) kf_init_kp(&dst->f, i, dst->fus_mean, dst->fus_std, dst->rec + CP_P_TRACKING_HP, c.R);
+    dst->has_kf = 1;
+  }
+  if (c.scale_pool) scale_pool_add(dst, true);
+}
+
+// Step 4 (tracker.py:206-236): a track without a detection is kept, unmoved, while age < max_age
+CP_HD void entry_lost(Slot* dst, const Slot* old) {
+  *dst = *old;
+  dst->age = old->age + 1;
+  dst->active = 0;
+}
+
+// Step 5 (tracker.py:238-270): filter read-out.  kps_mean_kf gets the -10000 sentinel where the confidence is < 0.15
+// (in the returned copy only -- the state keeps the estimate); conf_avg = sum(conf) / 8 (0 without the filter).
+CP_HDN void entry_readout(const Cfg& c, const Slot* s, double* kps_mean_kf /*16*/, double* kps_std_kf /*16*/, double* conf_avg,
+                          double* scale_new /*3*/, double* scale_unc /*3*/) {
+  double csum = 0.0;
+  for (int i = 0; i < 8; ++i) {
+    if (c.kalman) {
+      const double pxx = s->f.P[i][0], pyy = s->f.P[i][5];
+      kps_mean_kf[2 * i] = s->f.x[4 * i];
+      kps_mean_kf[2 * i + 1] = s->f.x[4 * i + 1];
+      kps_std_kf[2 * i] = sqrt(pxx);
+      kps_std_kf[2 * i + 1] = sqrt(pyy);
+      const double conf = kp_confidence(pxx, pyy, c.conf_lo, c.conf_hi);
+      csum += conf;
+      if (conf < 0.15) kps_mean_kf[2 * i] = kps_mean_kf[2 * i + 1] = -10000.0;
+    } else {
+      kps_mean_kf[2 * i] = (double)s->rec[CP_P_KPS + 2 * i];
+      kps_mean_kf[2 * i + 1] = (double)s->rec[CP_P_KPS + 2 * i + 1];
+      kps_std_kf[2 * i] = kps_std_kf[2 * i + 1] = 0.0;
+    }
+  }
+  *conf_avg = csum / 8.0;
+  for (int k = 0; k < 3; ++k) {
+    if (c.scale_pool) {
+      const double sd = 1.0 / sqrt(s->f.sp_w[k]);
+      scale_unc[k] = sd;
+      scale_new[k] = s->f.sp_m[k] * (sd * sd);
+    } else {
+      scale_new[k] = (double)s->rec[CP_P_OBJ_SCALE + k];
+      scale_unc[k] = (double)s->rec[CP_P_OBJ_SCALE_UNC + k];
+    }
+  }
+}
+
+// The second PnP wrote a pose: pnp_shell mutates the track dict (cuboid_pnp_shell.py:27-54), so the record's pose fields
+// now hold the filtered result
+CP_HD void slot_store_pose(Slot* s, const pose::PnPOut& po) {
+  if (po.status != CP_PNP_OK && po.status != CP_PNP_INVISIBLE) return;
+  float* o = s->rec;
+  o[CP_P_STATUS] = (float)po.status;
+  o[CP_P_NPTS] = (float)po.n_pts;
+  for (int t = 0; t < 3; ++t) o[CP_P_LOCATION + t] = (float)po.loc[t];
+  for (int t = 0; t < 4; ++t) o[CP_P_QUAT + t] = (float)po.quat[t];
+  o[CP_P_REPROJ] = (float)po.reproj;
+  for (int t = 0; t < 16; ++t) o[CP_P_PROJ_CUBOID + t] = (float)po.proj[t];
+  for (int t = 0; t < 27; ++t) o[CP_P_KPS_3D_CAM + t] = (float)po.kps3d[t];
+  for (int t = 0; t < 18; ++t) o[CP_P_KPS_PNP + t] = (float)po.kpspnp[t];
+}
+
+// tracker.py:283-286: ret[idx]['kps_pnp_kf'] exists when the filtered PnP returned a tuple.  A matched / new track is a
+// fresh dict (no stale key); a lost track keeps its dict, and re-solving the unchanged state gives the same answer.
+CP_HD void slot_store_pnp_kf(Slot* s, const pose::PnPOut& po) {
+  s->has_pnp_kf = (po.status == CP_PNP_OK) ? 1 : 0;
+  for (int t = 0; t < 18; ++t) s->kps_pnp_kf[t] = s->has_pnp_kf ? (float)po.kpspnp[t] : 0.f;
+}
+
+// one output row (cp_track_field layout)
+CP_HDN void write_track_record(const Slot* s, const double* kps_mean_kf, const double* kps_std_kf, double conf_avg,
+                               const double* scale_new, const double* scale_unc, const pose::PnPOut* po, int in_boxes,
+                               float* o /*CP_TRACK_RECORD*/) {
+  for (int i = 0; i < CP_POSE_RECORD; ++i) o[i] = s->rec[i];
+  for (int i = CP_POSE_RECORD; i < CP_TRACK_RECORD; ++i) o[i] = 0.f;
+  o[CP_T_ID] = (float)s->id;
+  o[CP_T_AGE] = (float)s->age;
+  o[CP_T_ACTIVE] = (float)s->active;
+  o[CP_T_IN_BOXES] = (float)in_boxes;
+  o[CP_T_PNP2_STATUS] = (float)(po ? po->status : CP_PNP_NOT_RUN);
+  o[CP_T_CONF_AVG] = (float)conf_avg;
+  for (int i = 0; i < 16; ++i) {
+    o[CP_T_KPS_FUSION_MEAN + i] = (float)s->fus_mean[i];
+    o[CP_T_KPS_FUSION_STD + i] = (float)s->fus_std[i];
+    o[CP_T_KPS_MEAN_KF + i] = (float)kps_mean_kf[i];
+    o[CP_T_KPS_STD_KF + i] = (float)kps_std_kf[i];
+  }
+  for (int k = 0; k < 3; ++k) {
+    o[CP_T_OBJ_SCALE_KF + k] = (float)scale_new[k];
+    o[CP_T_OBJ_SCALE_UNC_KF + k] = (float)scale_unc[k];
+  }
+  if (po && po->status == CP_PNP_OK) {
+    for (int t = 0; t < 18; ++t) o[CP_T_KPS_PNP_KF + t] = (float)po->kpspnp[t];
+    for (int t = 0; t < 27; ++t) o[CP_T_KPS_3D_CAM_KF + t] = (float)po->kps3d[t];
+  }
+}
+
+// ---- Steps 0-4 as a plan (serial; tiny): which detections enter, who continues which track, the order of `ret` -----------
+enum { ENTRY_MATCHED = 0, ENTRY_NEW = 1, ENTRY_LOST = 2 };
+struct Entry {
+  int kind, det, trk, id;
+};
+
+// poses: n_valid records of this frame; old: M tracks.  Scratch: det_idx[K], fbuf[3 * (K + M)] floats, ibuf[2 * K + 2 * M]
+// ints, taken[M].  Returns the number of entries written (<= max_entries); *id_count is advanced for every new track.
+CP_HDN int plan_step(const Cfg& c, const float* poses, int n_valid, const Slot* old, int M, int* id_count, Entry* entries,
+                     int max_entries, int* det_idx, float* fbuf, int* ibuf, unsigned char* taken) {
+  // Step 0 (tracker.py:121-130): with PnP on and at least one solved box, only the solved detections are tracked
+  int N = 0;
+  bool any_box = false;
+  if (c.use_pnp)
+    for (int i = 0; i < n_valid; ++i) any_box = any_box || ((int)poses[(size_t)i * CP_POSE_RECORD + CP_P_STATUS] == CP_PNP_OK);
+  for (int i = 0; i < n_valid; ++i)
+    if (!any_box || (int)poses[(size_t)i * CP_POSE_RECORD + CP_P_STATUS] == CP_PNP_OK) det_idx[N++] = i;
+  float* det_c = fbuf;
+  float* det_size = det_c + 2 * N;
+  float* trk_c = det_size + N;
+  float* trk_size = trk_c + 2 * M;
+  int* det_cls = ibuf;
+  int* trk_cls = det_cls + N;
+  int* match_of_det = trk_cls + M;
+  int* det_of_trk = match_of_det + N;
+  for (int i = 0; i < N; ++i) {
+    const float* r = poses + (size_t)det_idx[i] * CP_POSE_RECORD;
+    det_c[2 * i] = (float)((double)r[CP_P_CT] + (double)r[CP_P_TRACKING]);
+    det_c[2 * i + 1] = (float)((double)r[CP_P_CT + 1] + (double)r[CP_P_TRACKING + 1]);
+    det_size[i] = (float)(((double)r[CP_P_BBOX + 2] - (double)r[CP_P_BBOX]) * ((double)r[CP_P_BBOX + 3] - (double)r[CP_P_BBOX + 1]));
+    det_cls[i] = (int)r[CP_P_CLS];
+  }
+  for (int j = 0; j < M; ++j) {
+    const float* r = old[j].rec;
+    trk_c[2 * j] = r[CP_P_CT];
+    trk_c[2 * j + 1] = r[CP_P_CT + 1];
+    trk_size[j] = (float)(((double)r[CP_P_BBOX + 2] - (double)r[CP_P_BBOX]) * ((double)r[CP_P_BBOX + 3] - (double)r[CP_P_BBOX + 1]));
+    trk_cls[j] = (int)r[CP_P_CLS];
+  }
+  greedy_associate(det_c, det_size, det_cls, N, trk_c, trk_size, trk_cls, M, match_of_det, det_of_trk, taken);
+  int n = 0;
+  for (int i = 0; i < N && n < max_entries; ++i)
+    if (match_of_det[i] >= 0) entries[n++] = Entry{ENTRY_MATCHED, det_idx[i], match_of_det[i], 0};
+  for (int i = 0; i < N && n < max_entries; ++i)
+    if (match_of_det[i] < 0 && (double)poses[(size_t)det_idx[i] * CP_POSE_RECORD + CP_P_SCORE] > c.new_thresh) {
+      *id_count += 1;
+      entries[n++] = Entry{ENTRY_NEW, det_idx[i], -1, *id_count};
+    }
+  for (int j = 0; j < M && n < max_entries; ++j)
+    if (det_of_trk[j] < 0 && old[j].age < c.max_age) entries[n++] = Entry{ENTRY_LOST, -1, j, 0};
+  return n;
 }
 
 // ---- previous-frame heat maps (base_detector.py:150-388) -----------------------------------------------------------------

@@ -9,6 +9,8 @@ rebuilding the reference's Python result structures from the fixed-shape pose
 records (`records_to_results`).  `run_batch()` is the batched entry point the
 reference does not have (B = 32 / 256 configurations of BASELINE.json).
 """
+import json
+import os
 import time
 
 import numpy as np
@@ -17,6 +19,7 @@ import torch
 from . import _lib
 from .engine import decode_params, decode_pnp, make_meta, preprocess
 from .model import create_model, load_model
+from .tracker import Tracker, tracks_to_results
 
 
 # ----------------------------------------------------------------------------- records -> reference structures
@@ -122,33 +125,51 @@ class ObjectPoseDetector(object):
         self.pre_images = None
         self.tracker = None
         self.flip_idx = getattr(opt, "flip_idx", None)
-        if getattr(opt, "tracking_task", False) or getattr(opt, "refined_Kalman", False):
-            # Tracker state (utils/tracker.py) is CPU, per-video and needs filterpy: SURVEY.md row f-2.
-            self.tracker = None
+        if getattr(opt, "refined_Kalman", False):
+            raise NotImplementedError("opt.refined_Kalman (utils/tracker_baseline.py, CenterPose + Kalman baseline) is not "
+                                      "on the accelerated path; use --tracking_task (CenterPoseTrack)")
+        if getattr(opt, "tracking_task", False):
+            # base_detector.py:53-54: the tracker state lives on the device (centerpose_b200/tracker.py)
+            self.tracker = Tracker(opt, streams=1, device=opt.device)
+        self._batch_tracker = None
+        self._batch_pre = None
 
-    # base_detector.py:91-148 -- unchanged cv2 pre-processing (host side)
+    # base_detector.py:91-148 -- the reference's cv2 pre-processing (host side), all three modes
     def pre_process(self, image, scale, input_meta={}):
         import cv2
         height, width = image.shape[0:2]
         new_height = int(height * scale)
         new_width = int(width * scale)
         if self.opt.fix_short > 0:
-            raise NotImplementedError("fix_short pre-processing is not on the supported path")
-        if not self.opt.fix_res:
-            raise NotImplementedError("keep_res pre-processing is not on the supported path")
-        inp_height, inp_width = self.opt.input_h, self.opt.input_w
-        c = np.array([new_width / 2., new_height / 2.], dtype=np.float32)
-        s = max(height, width) * 1.0
-        trans_input = affine_from_center_scale(c, s, inp_width, inp_height)
+            if height < width:
+                inp_height = self.opt.fix_short
+                inp_width = (int(width / height * self.opt.fix_short) + 63) // 64 * 64
+            else:
+                inp_height = (int(height / width * self.opt.fix_short) + 63) // 64 * 64
+                inp_width = self.opt.fix_short
+            c = np.array([width / 2, height / 2], dtype=np.float32)
+            s = np.array([width, height], dtype=np.float32)
+        elif self.opt.fix_res:
+            inp_height, inp_width = self.opt.input_h, self.opt.input_w
+            c = np.array([new_width / 2., new_height / 2.], dtype=np.float32)
+            s = max(height, width) * 1.0
+        else:
+            inp_height = (new_height | self.opt.pad) + 1
+            inp_width = (new_width | self.opt.pad) + 1
+            c = np.array([new_width // 2, new_height // 2], dtype=np.float32)
+            s = np.array([inp_width, inp_height], dtype=np.float32)
+        s0 = float(s[0]) if isinstance(s, np.ndarray) else float(s)      # the affine only uses the width (image.py:44)
+        trans_input = affine_from_center_scale(c, s0, inp_width, inp_height)
         out_height = inp_height // self.opt.down_ratio
         out_width = inp_width // self.opt.down_ratio
+        trans_output = affine_from_center_scale(c, s0, out_width, out_height)
         resized = cv2.resize(image, (new_width, new_height))
         inp = cv2.warpAffine(resized, trans_input, (inp_width, inp_height), flags=cv2.INTER_LINEAR)
         inp = ((inp / 255. - self.mean) / self.std).astype(np.float32)
         images = torch.from_numpy(inp.transpose(2, 0, 1).reshape(1, 3, inp_height, inp_width))
         meta = {"c": c, "s": s, "height": height, "width": width, "out_height": out_height,
                 "out_width": out_width, "inp_height": inp_height, "inp_width": inp_width,
-                "trans_input": trans_input}
+                "trans_input": trans_input, "trans_output": trans_output}
         for k in ("pre_dets", "camera_matrix", "id"):
             if k in input_meta:
                 meta[k] = input_meta[k]
@@ -166,18 +187,19 @@ class ObjectPoseDetector(object):
                 meta=None):
         """object_pose.py:131-165: network + sigmoid + decode.  Returns
         (output, dets[, forward_time]); the pose records of the fused stage are
-        kept on `self._last` for post_process / merge / PnP."""
+        kept on `self._last` (host) / `self._last_dev` (device) for post_process / merge / PnP / tracking."""
         torch.cuda.synchronize()
         output = self.model(images, pre_images, pre_hms, pre_hm_hp)[-1]
         torch.cuda.synchronize()
         forward_time = time.time()
         prm = decode_params(self.opt)
-        metat = self._meta_tensor(meta if meta is not None else self._dummy_meta(images), images.shape[0])
-        dets, poses, n_valid = decode_pnp(output, metat.to(images.device), prm, want_dets=True)
+        metat = self._meta_tensor(meta if meta is not None else self._dummy_meta(images), images.shape[0]).to(images.device)
+        dets, poses, n_valid = decode_pnp(output, metat, prm, want_dets=True)
         output["hm"] = output["hm"].sigmoid_()
         if self.opt.hm_hp and not self.opt.mse_loss:
             output["hm_hp"] = output["hm_hp"].sigmoid_()
         output.update({"pre_inds": pre_inds})
+        self._last_dev = (poses, n_valid, metat)
         self._last = (poses.cpu().numpy(), n_valid.cpu().numpy())
         dets = dets_to_dict(dets.cpu().numpy())
         if return_time:
@@ -190,14 +212,15 @@ class ObjectPoseDetector(object):
                 "camera_matrix": np.eye(3)}
 
     def run(self, image_or_path_or_tensor, filename=None, meta_inp={}, preprocessed_flag=False):
+        """base_detector.py:390-772.  One image per call, the reference's 12-key return dict.  After pre_process
+        everything runs in libcenterpose_b200.so; post_process / merge_outputs / PnP are part of the fused decode call,
+        so their stamps are 0 and `dec` carries the whole post-network stage."""
         import cv2
         load_time, pre_time, net_time, dec_time, post_time = 0, 0, 0, 0, 0
         merge_time, track_time, pnp_time, tot_time = 0, 0, 0, 0
         if len(self.scales) != 1 or self.scales[0] != 1.0:
             raise NotImplementedError("multi-scale testing merges detections on the host; only test_scales=[1] is supported")
-        if getattr(self.opt, "tracking_task", False) or getattr(self.opt, "refined_Kalman", False):
-            raise NotImplementedError("tracker state (utils/tracker.py) is not on the accelerated path yet; "
-                                      "use run_batch(..., pre_images=, pre_hms=, pre_hm_hp=) for the two-frame network")
+        tracking = bool(getattr(self.opt, "tracking_task", False))
         start_time = time.time()
         pre_processed = preprocessed_flag
         if isinstance(image_or_path_or_tensor, np.ndarray):
@@ -219,11 +242,24 @@ class ObjectPoseDetector(object):
             images = torch.from_numpy(np.expand_dims(image, axis=0))
             meta = meta_inp
         images = images.to(self.opt.device)
+
+        pre_hms, pre_hm_hp, pre_inds = None, None, None
+        if tracking:
+            if self.pre_images is None:                       # base_detector.py:444-449
+                print("Initialize tracking!")
+                self.pre_images = images
+                self.tracker.init_track(meta)
+            if self.opt.pre_hm or self.opt.pre_hm_hp:         # :456-462, rendered on the device from the tracker state
+                if "trans_input" not in meta:
+                    raise ValueError("tracking needs meta['trans_input'] (pre_process provides it)")
+                metat = self._meta_tensor(meta).to(images.device)
+                pre_hms, pre_hm_hp = self.tracker.render(metat, meta["trans_input"], images.shape[2], images.shape[3])
         torch.cuda.synchronize()
         pre_process_time = time.time()
         pre_time += pre_process_time - loaded_time
 
-        output, dets, forward_time = self.process(images, None, None, None, None, return_time=True, meta=meta)
+        output, dets, forward_time = self.process(images, self.pre_images if tracking else None, pre_hms, pre_hm_hp,
+                                                  pre_inds, return_time=True, meta=meta)
         torch.cuda.synchronize()
         net_time += forward_time - pre_process_time
         decode_time = time.time()
@@ -236,36 +272,171 @@ class ObjectPoseDetector(object):
             boxes = []
         post_process_time = time.time()
         post_time += post_process_time - decode_time
-        merge_outputs_time = pnp_process_time = post_process_time
+        pnp_process_time = post_process_time
+
+        if tracking:                                          # :660-665 (gaussian_fusion :502-544 runs inside the step)
+            pd, nd, md = self._last_dev
+            self.tracker.step_records(pd, nd, md)
+            rows, nt = self.tracker._host()
+            results, boxes = tracks_to_results(rows[0], nt[0], meta["width"], meta["height"])
+            if not self.opt.use_pnp:
+                boxes = []
+            self.pre_images = images
         end_time = time.time()
         track_time += end_time - pnp_process_time
         tot_time += end_time - start_time
 
-        dict_out = {"camera_data": [], "objects": []}
-        if "camera_matrix" in meta:
-            dict_out["camera_data"] = np.asarray(meta["camera_matrix"]).tolist()
-        for box in boxes:
-            b = box[4]
-            obj = {
-                "class": self.opt.c, "ct": b["ct"], "bbox": np.array(b["bbox"]).tolist(), "confidence": b["score"],
-                "kps_displacement_mean": b["kps_displacement_mean"].tolist(),
-                "kps_heatmap_mean": b["kps_heatmap_mean"].tolist(),
-                "kps_heatmap_std": b["kps_heatmap_std"].tolist(),
-                "kps_heatmap_height": b["kps_heatmap_height"].tolist(),
-                "obj_scale": b["obj_scale"].tolist(),
-            }
-            if self.opt.use_pnp:
-                if "location" in b:
-                    obj["location"] = b["location"]
-                    obj["quaternion_xyzw"] = b["quaternion_xyzw"].tolist()
-                if "kps_pnp" in b:
-                    obj["kps_pnp"] = b["kps_pnp"].tolist()
-                    obj["kps_3d_cam"] = b["kps_3d_cam"].tolist()
-            dict_out["objects"].append(obj)
+        dict_out = self.build_dict_out(meta, results, boxes)
         self.last_dict_out = dict_out
+        debug = int(getattr(self.opt, "debug", 0) or 0)
+        if debug >= 1 and debug < 4:
+            self.show_results(None, image, results)
+        elif debug == 4:
+            self.save_results(None, image, results, image_or_path_or_tensor, dict_out)
+        elif debug == 6:
+            self.save_results_eval(None, image, results, image_or_path_or_tensor, dict_out)
         return {"results": results, "boxes": boxes, "output": output, "tot": tot_time, "load": load_time,
                 "pre": pre_time, "net": net_time, "dec": dec_time, "post": post_time, "merge": merge_time,
                 "pnp": pnp_time, "track": track_time}
+
+    # ------------------------------------------------------------------ result emitters
+    def build_dict_out(self, meta, results, boxes):
+        """The JSON payload of base_detector.py:672-754: camera matrix + one object per track (tracking) or per box."""
+        opt = self.opt
+        dict_out = {"camera_data": [], "objects": []}
+        if "camera_matrix" in meta:
+            dict_out["camera_data"] = np.asarray(meta["camera_matrix"]).tolist()
+        lst = lambda v: np.asarray(v).tolist()      # noqa: E731
+        if getattr(opt, "tracking_task", False):
+            for tr in results:
+                sc = np.asarray(tr["obj_scale"], np.float64)
+                obj = {"class": opt.c, "ct": tr["ct"], "bbox": lst(tr["bbox"]), "confidence": tr["score"],
+                       "kps_displacement_mean": lst(tr["kps_displacement_mean"]), "kps_heatmap_mean": lst(tr["kps_heatmap_mean"]),
+                       "kps_heatmap_std": lst(tr["kps_heatmap_std"]), "kps_heatmap_height": lst(tr["kps_heatmap_height"]),
+                       "obj_scale": (sc / sc[1]).tolist(), "tracking_id": tr["tracking_id"]}
+                if opt.use_pnp:
+                    if "location" in tr:
+                        obj["location"] = tr["location"]
+                        obj["quaternion_xyzw"] = lst(tr["quaternion_xyzw"])
+                    if "kps_pnp" in tr:
+                        obj["kps_pnp"] = lst(tr["kps_pnp"])
+                        obj["kps_3d_cam"] = lst(tr["kps_3d_cam"])
+                if getattr(opt, "obj_scale_uncertainty", False):
+                    obj["obj_scale_uncertainty"] = lst(tr["obj_scale_uncertainty"])
+                if getattr(opt, "kalman", False):
+                    obj["kps_mean_kf"] = lst(tr["kps_mean_kf"])
+                    obj["kps_std_kf"] = tr["kps_std_kf"]
+                    if opt.use_pnp and "kps_pnp_kf" in tr:
+                        obj["kps_pnp_kf"] = lst(tr["kps_pnp_kf"])
+                        obj["kps_3d_cam_kf"] = lst(tr["kps_3d_cam_kf"])
+                if getattr(opt, "scale_pool", False):
+                    sk = np.asarray(tr["obj_scale_kf"], np.float64)
+                    obj["obj_scale_kf"] = (sk / sk[1]).tolist()
+                    obj["obj_scale_uncertainty_kf"] = lst(tr["obj_scale_uncertainty_kf"])
+                if getattr(opt, "hps_uncertainty", False):
+                    obj["kps_displacement_std"] = lst(tr["kps_displacement_std"])
+                    obj["kps_fusion_mean"] = lst(tr["kps_fusion_mean"])
+                    obj["kps_fusion_std"] = lst(tr["kps_fusion_std"])
+                if getattr(opt, "tracking", False):
+                    obj["tracking"] = lst(tr["tracking"])
+                if getattr(opt, "tracking_hp", False):
+                    obj["tracking_hp"] = lst(tr["tracking_hp"])
+                dict_out["objects"].append(obj)
+        else:
+            for box in boxes:
+                b = box[4]
+                obj = {"class": opt.c, "ct": b["ct"], "bbox": lst(b["bbox"]), "confidence": b["score"],
+                       "kps_displacement_mean": lst(b["kps_displacement_mean"]), "kps_heatmap_mean": lst(b["kps_heatmap_mean"]),
+                       "kps_heatmap_std": lst(b["kps_heatmap_std"]), "kps_heatmap_height": lst(b["kps_heatmap_height"]),
+                       "obj_scale": lst(b["obj_scale"])}
+                if opt.use_pnp:
+                    if "location" in b:
+                        obj["location"] = b["location"]
+                        obj["quaternion_xyzw"] = lst(b["quaternion_xyzw"])
+                    if "kps_pnp" in b:
+                        obj["kps_pnp"] = lst(b["kps_pnp"])
+                        obj["kps_3d_cam"] = lst(b["kps_3d_cam"])
+                dict_out["objects"].append(obj)
+        return dict_out
+
+    def _debugger(self, debugger):
+        """The reference's Debugger (drawing) when its package is importable (drop-in use inside the reference tree);
+        visualisation itself is outside the accelerated path, so without it only the JSON is written."""
+        if debugger is not None:
+            return debugger
+        try:
+            from lib.utils.debugger import Debugger
+            return Debugger(dataset=self.opt.dataset, ipynb=(self.opt.debug == 3),
+                            theme=getattr(self.opt, "debugger_theme", "white"))
+        except Exception:
+            return None
+
+    def _draw(self, debugger, image, results, eval_mode=False):
+        opt = self.opt
+        debugger.add_img(image, img_id="out_img_pred")
+        for bbox in results:
+            if bbox["score"] > opt.vis_thresh and opt.reg_bbox:
+                if getattr(opt, "tracking_task", False) and not eval_mode:
+                    debugger.add_coco_bbox(bbox["bbox"], 0, bbox["score"], id=bbox["tracking_id"], img_id="out_img_pred")
+                else:
+                    debugger.add_coco_bbox(bbox["bbox"], 0, bbox["score"], img_id="out_img_pred")
+                if "projected_cuboid" in bbox:
+                    debugger.add_coco_hp(bbox["projected_cuboid"], img_id="out_img_pred", pred_flag="pnp")
+
+    def show_results(self, debugger, image, results):
+        """object_pose.py:280-317 (interactive display): needs the reference's Debugger."""
+        dbg = self._debugger(debugger)
+        if dbg is None:
+            return
+        self._draw(dbg, image, results)
+        dbg.show_all_imgs(pause=self.pause)
+
+    def save_results(self, debugger, image, results, image_or_path_or_tensor, dict_out=None):
+        """object_pose.py:357-414: <demo_save>/<source name>/<frame>.json (+ the rendered image when a Debugger exists)."""
+        opt = self.opt
+        if os.path.isdir(opt.demo):
+            target = os.path.join(opt.demo_save, os.path.basename(opt.demo))
+        else:
+            target = os.path.join(opt.demo_save, os.path.splitext(os.path.basename(opt.demo))[0])
+        os.makedirs(target, exist_ok=True)
+        dbg = self._debugger(debugger)
+        if dbg is not None:
+            self._draw(dbg, image, results)
+            dbg.save_all_imgs_demo(image_or_path_or_tensor, path=target)
+        if dict_out is not None:
+            name = os.path.splitext(os.path.basename(image_or_path_or_tensor))[0]
+            with open(os.path.join(target, name + ".json"), "w") as fp:
+                json.dump(dict_out, fp)
+            return os.path.join(target, name + ".json")
+
+    def save_results_eval(self, debugger, image, results, image_or_path_or_tensor, dict_out=None, video_layout=False):
+        """object_pose.py:319-355: demo/<checkpoint name>/[<video>/]<frame>.json, the layout the Objectron evaluator
+        (tools/objectron_eval/eval_video_official.py:307-311) reads."""
+        opt = self.opt
+        if getattr(opt, "tracking_task", False) or getattr(opt, "eval_max_num", None) == 100:
+            video_layout = True
+        root = os.path.join("demo", os.path.splitext(os.path.basename(opt.load_model))[0])
+        os.makedirs(root, exist_ok=True)
+        key = image_or_path_or_tensor
+        file_id = key[key.rfind("_") + 1:]
+        folder = key[:key.rfind("_")]
+        dbg = self._debugger(debugger)
+        if dbg is not None:
+            self._draw(dbg, image, results, eval_mode=True)
+        if video_layout:
+            vdir = os.path.join(root, folder)
+            os.makedirs(vdir, exist_ok=True)
+            if dbg is not None:
+                dbg.save_all_imgs_eval(key, path=vdir, video_layout=True)
+            path = os.path.join(vdir, file_id + ".json")
+        else:
+            if dbg is not None:
+                dbg.save_all_imgs_eval(key, path=root, video_layout=False)
+            path = os.path.join(root, "%s_%s.json" % (folder, file_id))
+        if dict_out is not None:
+            with open(path, "w") as fp:
+                json.dump(dict_out, fp)
+            return path
 
     # ------------------------------------------------------------------ batched API (not in the reference)
     def run_batch(self, frames, camera_matrix, pre_images=None, pre_hms=None, pre_hm_hp=None, to_host=True):
@@ -295,7 +466,13 @@ class ObjectPoseDetector(object):
         return poses, n_valid
 
     def reset_tracking(self):
+        """base_detector.py:774-776."""
+        if self.tracker is not None:
+            self.tracker.reset()
         self.pre_images = None
+        self._batch_pre = None
+        if self._batch_tracker is not None:
+            self._batch_tracker.reset()
 
 
 detector_factory = {"object_pose": ObjectPoseDetector}

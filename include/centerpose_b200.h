@@ -250,6 +250,67 @@ enum cp_dets_field {
   CP_D_IND = 118            /* flat index of the centre cell */
 };
 
+/* ---- CenterPoseTrack state on the device (SURVEY.md rows a-T / f-2) ----------- */
+/* Replaces utils/tracker.py:15-302 (Tracker: association, 32-state Kalman filter per object, scale pool, second PnP
+ * with the filtered keypoints), the gaussian_fusion closure of detectors/base_detector.py:502-544 and the rendering of
+ * the previous-frame heat maps, base_detector.py:150-388 (_get_additional_inputs, default options: use_pnp,
+ * render_hm_mode 1, render_hmhp_mode 0-3).  One tracker holds `streams` independent videos (the batch dimension);
+ * state lives in device memory, every call is enqueued on `stream`, calls on one tracker must be issued in frame order
+ * on one stream.  Not supported: --hungarian, meta['pre_dets'] seeding, gt_pre_hm_hmhp. */
+#define CP_TRACK_RECORD 320
+typedef struct cp_tracker cp_tracker;
+typedef struct cp_tracker_config {
+  int32_t streams;            /* independent videos = max batch of cp_tracker_step                         */
+  int32_t max_tracks;         /* per stream, <= CP_MAX_K                                                    */
+  int32_t kalman;             /* opt.kalman                                                                 */
+  int32_t scale_pool;         /* opt.scale_pool                                                             */
+  int32_t use_pnp;            /* opt.use_pnp                                                                */
+  int32_t hps_uncertainty;    /* opt.hps_uncertainty                                                        */
+  int32_t max_age;            /* opt.max_age (5)                                                            */
+  int32_t visible_thresh;     /* as in cp_decode_params                                                     */
+  int32_t opencv_return;      /* opt.show_axes                                                              */
+  int32_t render_hm_mode;     /* opt.render_hm_mode (1: centre heat = score)                                */
+  int32_t render_hmhp_mode;   /* opt.render_hmhp_mode (2: PnP keypoints, heat = filter confidence)          */
+  int32_t device;
+  float new_thresh;           /* opt.new_thresh                                                             */
+  float pre_thresh;           /* opt.pre_thresh                                                             */
+  float R;                    /* opt.R (20)                                                                 */
+  float conf_lo, conf_hi;     /* opt.conf_border[opt.c] (3, 9)                                              */
+} cp_tracker_config;
+
+int cp_tracker_create(const cp_tracker_config* cfg, cp_tracker** out);
+int cp_tracker_destroy(cp_tracker* trk);
+/* Tracker.reset(): forget every track of stream `index` (or of all streams when index < 0). */
+int cp_tracker_reset(cp_tracker* trk, int32_t index, void* stream);
+/* Tracker.step(results, boxes) for `batch` streams (stream b <- poses[b]).  poses / n_valid / meta as produced by
+ * cp_decode_pnp / cp_infer (K slots per image).  tracks_out: device fp32 [batch, max_tracks, CP_TRACK_RECORD], slots
+ * [0, n_tracks[b]) = the reference's self.tracker.tracks in order (layout: cp_track_field); n_tracks: device int32. */
+int cp_tracker_step(cp_tracker* trk, int32_t batch, const float* poses, const int32_t* n_valid, int32_t K,
+                    const double* meta, float* tracks_out, int32_t* n_tracks, void* stream);
+/* _get_additional_inputs(): render the tracks of every stream into pre_hm [batch,1,inp_h,inp_w] and pre_hm_hp
+ * [batch,8,inp_h,inp_w] (device fp32, overwritten).  trans_input: device fp64 [batch,6] = the row-major 2x3 affine
+ * meta['trans_input'] (original image -> network input). */
+int cp_tracker_render(cp_tracker* trk, int32_t batch, const double* meta, const double* trans_input, int32_t inp_h,
+                      int32_t inp_w, float* pre_hm, float* pre_hm_hp, void* stream);
+
+/* Offsets (in floats) inside one CP_TRACK_RECORD slot.  [0, CP_POSE_RECORD) is the pose record of the detection the
+ * track carries; its PnP fields hold the SECOND (filtered) solve whenever that produced a pose (pnp_shell mutates the
+ * track dict, cuboid_pnp_shell.py:27-54). */
+enum cp_track_field {
+  CP_T_ID = 192, CP_T_AGE = 193, CP_T_ACTIVE = 194,
+  CP_T_IN_BOXES = 195,         /* 1: the second PnP returned a tuple and conf_avg > 0.25 -> in `boxes` (tracker.py:278-281) */
+  CP_T_PNP2_STATUS = 196,      /* cp_pnp_status of the second PnP                                          */
+  CP_T_CONF_AVG = 197,
+  CP_T_KPS_FUSION_MEAN = 200,  /* 16 */
+  CP_T_KPS_FUSION_STD = 216,   /* 16 */
+  CP_T_KPS_MEAN_KF = 232,      /* 16, -10000 where the filter confidence is < 0.15                         */
+  CP_T_KPS_STD_KF = 248,       /* 16 */
+  CP_T_OBJ_SCALE_KF = 264,     /* 3  */
+  CP_T_OBJ_SCALE_UNC_KF = 267, /* 3  */
+  CP_T_KPS_PNP_KF = 270,       /* 18 */
+  CP_T_KPS_3D_CAM_KF = 288     /* 27 */
+};
+
 /* ---- stand-alone modulated deformable convolution (the `_ext` replacement) -- */
 /* input [B,C,H,W], weight [Co,C,3,3], bias [Co], offset [B,18,H,W]
  * (channel 2k = dy, 2k+1 = dx of tap k), mask [B,9,H,W] (already sigmoid'ed),

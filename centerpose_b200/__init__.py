@@ -12,5 +12,6 @@ from .model import create_model, load_model, save_model, DLASegB200          # n
 from .detector import ObjectPoseDetector, detector_factory                   # noqa: F401
 from .engine import Engine, decode_pnp, decode_params, make_meta, dcn_v2_forward, preprocess, conv2d_nhwc  # noqa: F401
 from .opts import default_opt                                                # noqa: F401
+from .tracker import Tracker, track_to_dict, tracks_to_results               # noqa: F401
 
 __version__ = "0.1.0"

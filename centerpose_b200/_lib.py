@@ -45,7 +45,7 @@ EXPORTS = [
     "cp_forward", "cp_plan_bytes", "cp_plan_forward_launches", "cp_decode_workspace_bytes",
     "cp_decode_pnp", "cp_infer", "cp_dcn_v2_forward", "cp_preprocess", "cp_plan_num_ops", "cp_plan_profile",
     "cp_dcn_v2_forward_ex", "cp_conv2d",
-    "cp_tracker_create", "cp_tracker_destroy", "cp_tracker_reset", "cp_tracker_step", "cp_tracker_render",
+    "cp_preprocess_affine", "cp_tracker_create", "cp_tracker_destroy", "cp_tracker_reset", "cp_tracker_step", "cp_tracker_render",
 ]
 
 
@@ -132,6 +132,8 @@ def load():
     L.cp_conv2d.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     L.cp_preprocess.argtypes = [vp, vp, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_float),
                                 ctypes.POINTER(ctypes.c_float), vp]
+    L.cp_preprocess_affine.argtypes = [vp, vp, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_double),
+                                       ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), vp]
     L.cp_tracker_create.argtypes = [ctypes.POINTER(CpTrackerConfig), ctypes.POINTER(vp)]
     L.cp_tracker_destroy.argtypes = [vp]
     L.cp_tracker_reset.argtypes = [vp, i32, vp]

@@ -11,44 +11,59 @@
 namespace cp {
 namespace {
 
-// cv2.warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) with the reference's isotropic
-// fix_res affine, followed by ((v / 255) - mean) / std evaluated in double and
-// rounded once to float32 like the numpy expression at base_detector.py:132.
-// Source coordinates are quantised to 1/32 pixel and the blended value is rounded
-// to an integer, mirroring OpenCV's fixed-point remap (INTER_BITS = 5).
+// cv2.warpAffine(src, M, dsize, flags=INTER_LINEAR) (BORDER_CONSTANT 0) for 8-bit 3-channel frames, restated bit for bit
+// (OpenCV imgwarp.cpp WarpAffineInvoker + remapBilinear, third party: opencv-python >= 4.5.3.56, 4.13.0 in this image,
+// checked by tests/test_preprocess_host.py against cv2 itself):
+//   * M is inverted on the host exactly like cv::warpAffine does (cp_preprocess_affine below);
+//   * AB_BITS = 10: X0 = cvRound((M[1] y + M[2]) * 1024) + 16, adelta[x] = cvRound(M[0] x * 1024) (cvRound = round
+//     half to even), X = (X0 + adelta[x]) >> 5 -> integer source pixel X >> 5 and a 1/32-pixel fraction X & 31;
+//   * the four bilinear weights are the integers (32 - fy)(32 - fx) * 32, ... (sum 32768, INTER_REMAP_COEF_BITS = 15);
+//   * pixel = (sum of weight * source + 16384) >> 15, neighbours outside the image contribute the border value 0;
+// followed by ((v / 255.) - mean) / std evaluated in double and rounded once to float32 like the numpy expression at
+// base_detector.py:132.  `Minv` = the inverted 2 x 3 matrix (dst -> src).
+struct WarpM {
+  double m[6];
+};
+
 __global__ void preprocess_kernel(const uint8_t* __restrict__ frames, float* __restrict__ out, int B, int sh,
-                                  int sw, int dh, int dw, float m0, float m1, float m2, float s0, float s1,
+                                  int sw, int dh, int dw, const WarpM W, float m0, float m1, float m2, float s0, float s1,
                                   float s2) {
-  const double cx = (double)(float)(sw / 2.0), cy = (double)(float)(sh / 2.0);
-  const double s = (double)(sh > sw ? sh : sw);
-  const double a = s / (double)dw;  // src pixels per dst pixel
   size_t total = (size_t)B * dh * dw;
   const float mean[3] = {m0, m1, m2};
   const float stdv[3] = {s0, s1, s2};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int x = i % dw;
-    size_t t = i / dw;
-    int y = t % dh;
-    int n = t / dh;
-    double sx = ((double)x - dw * 0.5) * a + cx;
-    double sy = ((double)y - dh * 0.5) * a + cy;
-    long qx = lrint(sx * 32.0), qy = lrint(sy * 32.0);
-    int ix = (int)(qx >> 5), iy = (int)(qy >> 5);
-    float fx = (float)(qx & 31) * (1.0f / 32.0f), fy = (float)(qy & 31) * (1.0f / 32.0f);
+    const int x = (int)(i % dw);
+    const size_t t = i / dw;
+    const int y = (int)(t % dh);
+    const int n = (int)(t / dh);
+    // unfused double arithmetic (the host code OpenCV runs here has no FMA contraction)
+    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(W.m[1], (double)y), W.m[2]), 1024.0)) + 16;
+    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(W.m[4], (double)y), W.m[5]), 1024.0)) + 16;
+    const int ad = __double2int_rn(__dmul_rn(__dmul_rn(W.m[0], (double)x), 1024.0));
+    const int bd = __double2int_rn(__dmul_rn(__dmul_rn(W.m[3], (double)x), 1024.0));
+    const int X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5;
+    int ix = X >> 5, iy = Y >> 5;
+    // saturate_cast<short> of the integer coordinates (only matters for absurd scales; keeps the restatement exact)
+    ix = max(-32768, min(32767, ix));
+    iy = max(-32768, min(32767, iy));
+    const int fx = X & 31, fy = Y & 31;
+    const int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
     const uint8_t* img = frames + (size_t)n * sh * sw * 3;
+    const bool y0 = iy >= 0 && iy < sh, y1 = iy + 1 >= 0 && iy + 1 < sh;
+    const bool x0 = ix >= 0 && ix < sw, x1 = ix + 1 >= 0 && ix + 1 < sw;
     for (int c = 0; c < 3; ++c) {
-      float v00 = 0, v01 = 0, v10 = 0, v11 = 0;
-      if (iy >= 0 && iy < sh) {
-        if (ix >= 0 && ix < sw) v00 = img[((size_t)iy * sw + ix) * 3 + c];
-        if (ix + 1 >= 0 && ix + 1 < sw) v01 = img[((size_t)iy * sw + ix + 1) * 3 + c];
+      int v00 = 0, v01 = 0, v10 = 0, v11 = 0;
+      if (y0) {
+        if (x0) v00 = img[((size_t)iy * sw + ix) * 3 + c];
+        if (x1) v01 = img[((size_t)iy * sw + ix + 1) * 3 + c];
       }
-      if (iy + 1 >= 0 && iy + 1 < sh) {
-        if (ix >= 0 && ix < sw) v10 = img[((size_t)(iy + 1) * sw + ix) * 3 + c];
-        if (ix + 1 >= 0 && ix + 1 < sw) v11 = img[((size_t)(iy + 1) * sw + ix + 1) * 3 + c];
+      if (y1) {
+        if (x0) v10 = img[((size_t)(iy + 1) * sw + ix) * 3 + c];
+        if (x1) v11 = img[((size_t)(iy + 1) * sw + ix + 1) * 3 + c];
       }
-      float v = (1.f - fy) * ((1.f - fx) * v00 + fx * v01) + fy * ((1.f - fx) * v10 + fx * v11);
-      double u8 = (double)(int)(v + 0.5f);
-      double r = (u8 / 255.0 - (double)mean[c]) / (double)stdv[c];
+      int u8 = (v00 * w00 + v01 * w01 + v10 * w10 + v11 * w11 + (1 << 14)) >> 15;
+      u8 = max(0, min(255, u8));
+      const double r = ((double)u8 / 255.0 - (double)mean[c]) / (double)stdv[c];
       out[(((size_t)n * 3 + c) * dh + y) * dw + x] = (float)r;
     }
   }
@@ -238,18 +253,50 @@ int cp_dcn_v2_forward_ex(const float* input, const float* weight, const float* b
   return rc;
 }
 
-int cp_preprocess(const uint8_t* frames, float* out, int32_t B, int32_t src_h, int32_t src_w, int32_t dst_h,
-                  int32_t dst_w, const float mean[3], const float stdv[3], void* stream_) {
-  if (!frames || !out || !mean || !stdv) return fail(CP_ERR_INVALID, "cp_preprocess: null argument");
+int cp_preprocess_affine(const uint8_t* frames, float* out, int32_t B, int32_t src_h, int32_t src_w, int32_t dst_h,
+                         int32_t dst_w, const double trans_input[6], const float mean[3], const float stdv[3], void* stream_) {
+  if (!frames || !out || !mean || !stdv || !trans_input) return fail(CP_ERR_INVALID, "cp_preprocess: null argument");
   if (B <= 0 || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0)
     return fail(CP_ERR_INVALID, "cp_preprocess: bad shape");
+  // cv::warpAffine inverts the forward matrix like this (imgwarp.cpp), in double, before the fixed-point walk
+  WarpM W;
+  double* M = W.m;
+  for (int i = 0; i < 6; ++i) M[i] = trans_input[i];
+  double D = M[0] * M[4] - M[1] * M[3];
+  D = D != 0 ? 1. / D : 0;
+  const double A11 = M[4] * D, A22 = M[0] * D;
+  M[0] = A11;
+  M[1] *= -D;
+  M[3] *= -D;
+  M[4] = A22;
+  const double b1 = -M[0] * M[2] - M[1] * M[5];
+  const double b2 = -M[3] * M[2] - M[4] * M[5];
+  M[2] = b1;
+  M[5] = b2;
   size_t total = (size_t)B * dst_h * dst_w;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  preprocess_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(frames, out, B, src_h, src_w, dst_h, dst_w, mean[0],
+  preprocess_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(frames, out, B, src_h, src_w, dst_h, dst_w, W, mean[0],
                                                               mean[1], mean[2], stdv[0], stdv[1], stdv[2]);
   CP_LAUNCH_CHECK("preprocess_kernel");
   return CP_OK;
+}
+
+// fix_res affine of base_detector.py:109-121 (c = frame centre, s = max side, rot 0) in closed form: the float32 control
+// points of utils/image.py:35-68 give an isotropic scale a = dst_w / s.  (cv2.getAffineTransform solves the same three
+// point pairs by LU; the two agree to <= 3e-14, which the fixed-point walk cannot see except on exact rounding ties.
+// Callers that hold the reference's own `trans_input` pass it to cp_preprocess_affine.)
+int cp_preprocess(const uint8_t* frames, float* out, int32_t B, int32_t src_h, int32_t src_w, int32_t dst_h,
+                  int32_t dst_w, const float mean[3], const float stdv[3], void* stream_) {
+  if (src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0) return fail(CP_ERR_INVALID, "cp_preprocess: bad shape");
+  const float cx = (float)(src_w / 2.0), cy = (float)(src_h / 2.0);
+  const float s = (float)(src_h > src_w ? src_h : src_w);
+  const float src1y = cy + s * -0.5f;                               // float32 control points
+  const float dst0x = (float)(dst_w * 0.5), dst0y = (float)(dst_h * 0.5);
+  const float dst1y = dst0y + (float)(dst_w * -0.5);
+  const double a = ((double)dst1y - (double)dst0y) / ((double)src1y - (double)cy);
+  const double T[6] = {a, 0.0, (double)dst0x - a * (double)cx, 0.0, a, (double)dst0y - a * (double)cy};
+  return cp_preprocess_affine(frames, out, B, src_h, src_w, dst_h, dst_w, T, mean, stdv, stream_);
 }
 
 }  // extern "C"

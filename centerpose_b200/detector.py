@@ -439,11 +439,15 @@ class ObjectPoseDetector(object):
             return path
 
     # ------------------------------------------------------------------ batched API (not in the reference)
-    def run_batch(self, frames, camera_matrix, pre_images=None, pre_hms=None, pre_hm_hp=None, to_host=True):
+    def run_batch(self, frames, camera_matrix, pre_images=None, pre_hms=None, pre_hm_hp=None, to_host=True, track=False):
         """frames: uint8 [B,H,W,3] (numpy / pinned CPU tensor / CUDA tensor) or a
         pre-processed fp32 [B,3,h,w] CUDA tensor.  One native cp_infer call for the
         whole batch.  Returns (poses [B,K,192], n_valid [B]) -- on the host when
-        `to_host`, else as CUDA tensors."""
+        `to_host`, else as CUDA tensors.
+
+        track=True (tracking models): the batch is B independent VIDEO STREAMS and every call is their next frame.
+        The previous frames, the tracker state and the rendered previous-frame heat maps stay on the device; returns
+        (tracks [B,T,320], n_tracks [B]) (layout: cp_track_field) instead."""
         dev = self.opt.device
         if isinstance(frames, np.ndarray):
             frames = torch.from_numpy(frames)
@@ -460,6 +464,23 @@ class ObjectPoseDetector(object):
         meta = make_meta(B, c, s, iw, ih, camera_matrix).to(dev, non_blocking=True)
         eng = self.model.engine(B, x.shape[2], x.shape[3], x.device)
         prm = decode_params(self.opt)
+        if track:
+            if not getattr(self.opt, "tracking_task", False):
+                raise ValueError("run_batch(track=True) needs a tracking model (opt.tracking_task)")
+            trk = self._batch_tracker
+            if trk is None or trk.streams != B:
+                trk = self._batch_tracker = Tracker(self.opt, streams=B, device=x.device)
+                self._batch_pre = None
+            if self._batch_pre is None or self._batch_pre.shape != x.shape:
+                self._batch_pre = x                                   # first frame: pre_images = images (base_detector.py:446)
+            trans = affine_from_center_scale(c, s, x.shape[3], x.shape[2])
+            pre_hms, pre_hm_hp = trk.render(meta, trans, x.shape[2], x.shape[3])
+            _, poses, n_valid = eng.infer(x, meta, prm, self._batch_pre, pre_hms, pre_hm_hp)
+            tracks, nt = trk.step_records(poses, n_valid, meta)
+            self._batch_pre = x
+            if to_host:
+                return tracks.cpu().numpy(), nt.cpu().numpy()
+            return tracks, nt
         _, poses, n_valid = eng.infer(x, meta, prm, pre_images, pre_hms, pre_hm_hp)
         if to_host:
             return poses.cpu().numpy(), n_valid.cpu().numpy()

@@ -265,8 +265,9 @@ class Engine(object):
         return dets, poses, n_valid
 
 
-def preprocess(frames_u8, dst_h, dst_w, mean, std, out=None):
-    """cp_preprocess: uint8 [B,H,W,3] CUDA -> fp32 [B,3,dst_h,dst_w] CUDA."""
+def preprocess(frames_u8, dst_h, dst_w, mean, std, out=None, trans_input=None):
+    """cp_preprocess: uint8 [B,H,W,3] CUDA -> fp32 [B,3,dst_h,dst_w] CUDA (bit-exact cv2.warpAffine + normalise).
+    trans_input: optional 2x3 forward affine (meta['trans_input']); default = the fix_res affine of the frame size."""
     L = _lib.load()
     if not frames_u8.is_cuda or frames_u8.dtype != torch.uint8:
         raise RuntimeError("preprocess needs a uint8 CUDA tensor")
@@ -276,7 +277,11 @@ def preprocess(frames_u8, dst_h, dst_w, mean, std, out=None):
     m = (ctypes.c_float * 3)(*[float(v) for v in mean])
     s = (ctypes.c_float * 3)(*[float(v) for v in std])
     with torch.cuda.device(frames_u8.device):
-        rc = L.cp_preprocess(_ptr(frames_u8.contiguous()), _ptr(out), B, sh, sw, dst_h, dst_w, m, s, _stream())
+        if trans_input is not None:
+            tm = (ctypes.c_double * 6)(*[float(v) for v in np.asarray(trans_input, np.float64).reshape(-1)])
+            rc = L.cp_preprocess_affine(_ptr(frames_u8.contiguous()), _ptr(out), B, sh, sw, dst_h, dst_w, tm, m, s, _stream())
+        else:
+            rc = L.cp_preprocess(_ptr(frames_u8.contiguous()), _ptr(out), B, sh, sw, dst_h, dst_w, m, s, _stream())
     _lib.check(rc, "cp_preprocess")
     return out
 

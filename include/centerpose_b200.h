@@ -336,10 +336,16 @@ int cp_conv2d(const float* x, const float* weight, const float* bias, const floa
 
 /* ---- batched pre-process (next-row f-1) ------------------------------------ */
 /* frames: device uint8 [B, src_h, src_w, 3] (BGR as cv2.imread gives);
- * out: device fp32 NCHW [B,3,dst_h,dst_w] = (bilinear-warped/255 - mean)/std with the
- * reference's fix_res affine (c = src centre, s = max(src_h, src_w)). */
+ * out: device fp32 NCHW [B,3,dst_h,dst_w] = (warpAffine(frame)/255 - mean)/std with the
+ * reference's fix_res affine (c = src centre, s = max(src_h, src_w)).  The warp is a bit-for-bit restatement of
+ * cv2.warpAffine(INTER_LINEAR) for 8-bit frames (OpenCV's fixed-point remap: AB_SCALE 1024, INTER_BITS 5,
+ * 15-bit integer weights), so the batched path feeds the network exactly what base_detector.py:128-134 does. */
 int cp_preprocess(const uint8_t* frames, float* out, int32_t B, int32_t src_h, int32_t src_w,
                   int32_t dst_h, int32_t dst_w, const float mean[3], const float std[3], void* stream);
+/* Same with an explicit forward affine: trans_input = HOST pointer to the row-major 2x3 double matrix
+ * meta['trans_input'] (source frame -> network input), e.g. for fix_short / keep_res or rotated crops. */
+int cp_preprocess_affine(const uint8_t* frames, float* out, int32_t B, int32_t src_h, int32_t src_w, int32_t dst_h,
+                         int32_t dst_w, const double trans_input[6], const float mean[3], const float std[3], void* stream);
 
 /* ---- misc ------------------------------------------------------------------ */
 int cp_version(void);

@@ -152,8 +152,81 @@ def run_reference():
     return {"opt": opts, "frames": golden}
 
 
+RENDER_OUT = os.path.join(ROOT, "tests", "golden", "track_render.npz")
+RENDER_CASES = [          # (frames stepped before rendering, network input h, w)
+    ("f2_512", 2, 512, 512),
+    ("f4_256", 4, 256, 256),       # object 2 is lost here: lost tracks are rendered too
+    ("f6_320x384", 6, 320, 384),
+]
+
+
+def render_meta(inp_h, inp_w):
+    """meta as pre_process (fix_res) builds it for the 512 x 512 frames of the sequence and a network input of
+    inp_h x inp_w: c = image centre, s = max side; trans_* through the reference's own get_affine_transform."""
+    from lib.utils.image import get_affine_transform
+    c = np.array([WIDTH / 2., HEIGHT / 2.], dtype=np.float32)
+    s = max(HEIGHT, WIDTH) * 1.0
+    return {"c": c, "s": s, "height": HEIGHT, "width": WIDTH, "inp_height": inp_h, "inp_width": inp_w,
+            "out_height": inp_h // 4, "out_width": inp_w // 4, "camera_matrix": K_CAM.copy(),
+            "trans_input": get_affine_transform(c, s, 0, [inp_w, inp_h]),
+            "trans_output": get_affine_transform(c, s, 0, [inp_w // 4, inp_h // 4])}
+
+
+def run_reference_render():
+    """The UNMODIFIED `BaseDetector._get_additional_inputs` (base_detector.py:150-388) on the reference tracker's own
+    track dicts after N frames of the seeded sequence -> previous-frame heat maps."""
+    import types
+    import torch
+    sys.path.insert(0, ROOT)
+    from oracle import ref_shims, tracker_ref
+    ref_shims.install()
+    opt = ref_shims.make_opt("dla_34", tracking_task=True, rep_mode=1, c="chair")
+    opt.device = torch.device("cpu")
+    from lib.utils.tracker import Tracker
+    from lib.utils.pnp.cuboid_pnp_shell import pnp_shell
+    from lib.detectors.base_detector import BaseDetector
+    stub = types.SimpleNamespace(opt=opt)
+    stub._trans_bbox = lambda *a: BaseDetector._trans_bbox(stub, *a)
+    out = {}
+    for name, nframes, ih, iw in RENDER_CASES:
+        meta, frames = make_sequence()
+        trk = Tracker(opt)
+        trk.init_track(meta)
+        for dets in frames[:nframes]:
+            results = copy.deepcopy(dets)
+            boxes = []
+            for det in results:
+                m, sd = tracker_ref.gaussian_fusion(det, opt.hps_uncertainty)
+                det["kps_fusion_mean"], det["kps_fusion_std"] = m, sd
+                r = pnp_shell(opt, meta, det, assemble_points(det), det["obj_scale"], OPENCV_RETURN=opt.show_axes)
+                if r is not None:
+                    boxes.append(r)
+            trk.step(results, boxes)
+        rm = render_meta(ih, iw)
+        hm, hm_hp, _ = BaseDetector._get_additional_inputs(stub, trk.tracks, rm, with_hm=True, with_hm_hp=True)
+        # fixture size: the smallest case is stored whole; the larger ones as every 4th pixel + per-channel sum / non-zero
+        # count (a wrong radius, centre or heat changes all of them)
+        for key, v in (("_hm", hm.numpy()[0]), ("_hm_hp", hm_hp.numpy()[0])):
+            if ih * iw <= 256 * 256:
+                out[name + key] = v
+            else:
+                out[name + key + "_sub4"] = np.ascontiguousarray(v[:, ::4, ::4])
+                out[name + key + "_sum"] = v.astype(np.float64).sum(axis=(1, 2))
+                out[name + key + "_nnz"] = (v != 0).sum(axis=(1, 2)).astype(np.int64)
+        out[name + "_trans_input"] = rm["trans_input"]
+        print(name, "tracks", len(trk.tracks), "hm max", float(hm.max()), "hm_hp max per joint",
+              [round(float(v), 3) for v in hm_hp[0].amax(dim=(1, 2))])
+    out["pre_thresh"] = float(opt.pre_thresh)
+    out["render_hm_mode"] = int(opt.render_hm_mode)
+    out["render_hmhp_mode"] = int(opt.render_hmhp_mode)
+    return out
+
+
 if __name__ == "__main__":
     g = run_reference()
     with open(OUT, "w") as f:
         json.dump(g, f)
     print("wrote", OUT, "frames", len(g["frames"]), [len(fr["tracks"]) for fr in g["frames"]])
+    r = run_reference_render()
+    np.savez_compressed(RENDER_OUT, **r)
+    print("wrote", RENDER_OUT)

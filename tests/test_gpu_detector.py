@@ -60,17 +60,25 @@ def test_run_batch_matches_run(cplib):
             assert np.abs(d["kps"] - poses[b, i, L.P_KPS:L.P_KPS + 16]).max() <= 0.05
 
 
-def test_preprocess_matches_cv2(cplib):
+def test_preprocess_is_bit_exact(cplib):
+    """Row f-1: the batched pre-process kernel reproduces cv2.warpAffine(INTER_LINEAR) + the normalisation of
+    base_detector.py:128-134 BIT FOR BIT on the Objectron frame shapes (byte work: the bar is exact)."""
     cv2 = pytest.importorskip("cv2")
+    from oracle import preprocess_ref as pr
     det, opt = _detector()
-    for (h, w) in ((512, 512), (600, 800), (480, 640)):
+    for (h, w) in ((512, 512), (600, 800), (480, 640), (800, 600), (375, 500)):
         fr = synth.synthetic_frames(2, h, w, seed=h)
         got = cpb.preprocess(torch.from_numpy(fr).cuda(), 512, 512, opt.mean, opt.std).cpu().numpy()
         for b in range(2):
-            want, _ = det.pre_process(fr[b], 1.0)
-            d = np.abs(got[b] - want[0].numpy())
-            if (h, w) == (512, 512):
-                assert d.max() == 0.0                                  # identity warp: bit exact
-            else:
-                assert np.percentile(d, 99.9) <= 2.5 / 255 / 0.27      # <= ~2 grey levels on random-noise frames
-                assert d.mean() <= 0.3 / 255 / 0.27
+            want, meta = det.pre_process(fr[b], 1.0)              # the reference's cv2 path
+            assert np.array_equal(got[b], want[0].numpy()), (h, w, np.abs(got[b] - want[0].numpy()).max())
+            assert np.array_equal(got[b], pr.pre_process(fr[b], 512, 512, opt.mean, opt.std)[0])
+        # explicit trans_input (what run() computes) and an arbitrary rotated crop
+        got2 = cpb.preprocess(torch.from_numpy(fr).cuda(), 512, 512, opt.mean, opt.std, trans_input=meta["trans_input"]).cpu().numpy()
+        assert np.array_equal(got2[1], want[0].numpy())
+    fr = synth.synthetic_frames(1, 300, 420, seed=2)
+    M = cv2.getRotationMatrix2D((210, 150), 17.0, 0.8)
+    got = cpb.preprocess(torch.from_numpy(fr).cuda(), 192, 256, opt.mean, opt.std, trans_input=M).cpu().numpy()
+    inp = cv2.warpAffine(fr[0], M, (256, 192), flags=cv2.INTER_LINEAR)
+    want = ((inp / 255. - det.mean) / det.std).astype(np.float32).transpose(2, 0, 1)
+    assert np.array_equal(got[0], want)

@@ -122,26 +122,157 @@ def calibrate_head_bias(model, eng, x, target=TARGET_OBJECTS):
     return model
 
 
-def cpu_reference_step(sd, opt, frames_u8, cam, budget_s=None):
+def cpu_reference_step(sd, opt, frames_u8, cam, budget_s=None, stages=None):
     """The reference algorithm (oracle port) for a few frames on the host: returns the number of images
-    processed (stops early, after at least one frame, once `budget_s` seconds of wall clock are spent)."""
+    processed (stops early, after at least one frame, once `budget_s` seconds of wall clock are spent).
+    `stages` (dict) accumulates the seconds per stage with the keys of the reference's run() stamps
+    (base_detector.py:770-772): net, dec, post, merge, pnp."""
     t_begin = time.time()
     import centerpose_b200 as cpb  # noqa: F401
-    from centerpose_b200 import _lib as L
     from centerpose_b200 import synth
-    from oracle import decode_ref, net_ref
-    from tests.util import oracle_records
+    from oracle import decode_ref, net_ref, pnp_ref
     n = frames_u8.shape[0]
     prm = decode_ref.DecodeParams(rep_mode=opt.rep_mode, vis_thresh=opt.vis_thresh, category=opt.c)
     c = np.array([256., 256.], np.float32)
+    st = stages if stages is not None else {}
+    for k in ("net", "dec", "post", "merge", "pnp"):
+        st.setdefault(k, 0.0)
     for i in range(n):                                   # the reference's run() is one image per call
+        t0 = time.time()
         x = torch.from_numpy(synth.normalize_frames(frames_u8[i:i + 1]))
         heads = net_ref.forward(x, sd, opt.heads, "dla_34")
         hb = {k: v[0].numpy() for k, v in heads.items()}
-        oracle_records(hb, prm, cam, 512, 512, c, 512.0, L)
+        t1 = time.time()
+        dets = decode_ref.decode(decode_ref.process_heads(hb), prm)
+        t2 = time.time()
+        pp = decode_ref.post_process(dets, c, 512.0, hb["hm"].shape[1], hb["hm"].shape[2])
+        t3 = time.time()
+        res = decode_ref.merge_outputs(pp, prm)
+        t4 = time.time()
+        for d in res:
+            pnp_ref.pnp_shell(d, pnp_ref.assemble_points(d, prm.rep_mode), cam, 512, 512, category=prm.category)
+        t5 = time.time()
+        for k, dt in (("net", t1 - t0), ("dec", t2 - t1), ("post", t3 - t2), ("merge", t4 - t3), ("pnp", t5 - t4)):
+            st[k] += dt
         if budget_s is not None and time.time() - t_begin > budget_s:
             return i + 1
     return n
+
+
+def gpu_torch_forward_ms(sd, opt, x, allow_tf32, reps=10):
+    """BASELINE config 2 baseline leg: the reference graph (oracle/net_ref.py: torch / cuDNN convolutions, BatchNorm,
+    torchvision.ops.deform_conv2d for the DCNv2 layers -- the `_ext` stand-in of SURVEY.md Appendix E) on the GPU.
+    Returns (ms per forward, heads)."""
+    from oracle import net_ref
+    import torchvision
+    sdg = {k: v.to(x.device) for k, v in sd.items()}
+    orig = net_ref.dcn_v2_forward_ref
+    net_ref.dcn_v2_forward_ref = lambda a, off, mask, w, b: torchvision.ops.deform_conv2d(a, off, w, b, padding=1, mask=mask)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = bool(allow_tf32)
+    torch.backends.cudnn.benchmark = True
+    try:
+        with torch.no_grad():
+            for _ in range(3):
+                out = net_ref.forward(x, sdg, opt.heads, "dla_34")
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                out = net_ref.forward(x, sdg, opt.heads, "dla_34")
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, out
+    finally:
+        net_ref.dcn_v2_forward_ref = orig
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+
+
+def extra_configs(args, det, eng32, sd, opt, cam, dev, ev_time):
+    """BASELINE.json configs[0], [1] and [4] measured in the same run (single GPU, rank 0): extra keys of the JSON line."""
+    import centerpose_b200 as cpb
+    from centerpose_b200 import synth
+    from centerpose_b200.engine import InferGraph, decode_params, make_meta
+    out = {}
+    prm = decode_params(opt)
+    # ---- config 2: batch 1, dla_34, ours vs the reference graph in PyTorch on the same GPU, same input
+    try:
+        x1 = torch.from_numpy(synth.normalize_frames(synth.synthetic_frames(1, 512, 512, seed=99))).to(dev)
+        meta1 = make_meta(1, np.array([256., 256.], np.float32), 512.0, 512, 512, cam).to(dev)
+        eng1 = det.model.engine(1, 512, 512, dev)          # a batch-32 plan serves batch 1 too (same kernels)
+        eager = ev_time(lambda: eng1.infer(x1, meta1, prm), reps=20)
+        graph = InferGraph(eng1, 1, prm)
+        graphed = ev_time(lambda: graph(x1, meta1), reps=20)
+        fwd_only = ev_time(lambda: eng1.forward(x1), reps=20)
+        ours = eng1.forward(x1)
+        c2 = {"batch": 1, "ours_ms": eager, "ours_cuda_graph_ms": graphed, "ours_forward_only_ms": fwd_only,
+              "what": "network + decode + soft-NMS + PnP for one 512 x 512 frame (CUDA events, mean of 20); the torch legs are the "
+                      "NETWORK ONLY (the reference's decode / post-process / PnP run on the host: cpu_baseline)"}
+        try:
+            ms32, ref32 = gpu_torch_forward_ms(sd, opt, x1, allow_tf32=False)
+            mstf, _ = gpu_torch_forward_ms(sd, opt, x1, allow_tf32=True)
+            c2["torch_gpu_forward_ms"] = {"fp32": ms32, "tf32_allowed": mstf}
+            c2["heads_max_abs_diff_vs_torch_fp32_rel"] = max(
+                float((ours[h] - ref32[h]).abs().max() / ref32[h].abs().max()) for h in opt.heads)
+            c2["speedup_forward_vs_torch_fp32"] = ms32 / fwd_only
+        except Exception as e:                              # torchvision missing on the box, ...
+            c2["torch_gpu_forward_ms"] = {"unavailable": repr(e)[:200]}
+        out["config2"] = c2
+        del graph
+    except Exception as e:
+        out["config2"] = {"error": repr(e)[:300]}
+    # ---- config 5: CenterPoseTrack, batch = 8 video streams, two-frame network + decode + tracker step + heat-map rendering
+    try:
+        topt = cpb.default_opt("dla_34", tracking_task=True)
+        tm = cpb.create_model(topt.arch, topt.heads, topt.head_conv, topt)
+        tm.precision = args.precision
+        tm.load_state_dict(synth.seeded_state_dict(tm, seed=0, offset_std=0.3, head_gain=HEAD_GAIN))
+        tdet = cpb.ObjectPoseDetector(topt, model=tm)
+        vids = [torch.from_numpy(synth.synthetic_frames(8, 512, 512, seed=500 + i)).to(dev) for i in range(4)]
+        xcal = torch.from_numpy(synth.normalize_frames(synth.synthetic_frames(8, 512, 512, seed=500))).to(dev)
+        teng = tdet.model.engine(8, 512, 512, dev)
+        z1, z8 = torch.zeros((8, 1, 512, 512), device=dev), torch.zeros((8, 8, 512, 512), device=dev)
+        synth.calibrate_head_bias(tdet.model, teng.forward(xcal, xcal, z1, z8), TARGET_OBJECTS)
+        state = {"i": 0}
+
+        def track_step():
+            tdet.run_batch(vids[state["i"] % 4], cam, track=True, to_host=False)
+            state["i"] += 1
+        ms = ev_time(track_step, reps=12)
+        _, nt = tdet.run_batch(vids[0], cam, track=True)
+        out["config5"] = {"batch": 8, "pairs_per_s": 8 / (ms * 1e-3), "ms_per_step": ms, "tracks_per_stream": float(np.mean(nt)),
+                          "what": "8 video streams: pre-process, render pre_hm / pre_hm_hp from the tracker state, two-frame "
+                                  "dla_34 (3 stems, 11 heads / 71 ch), decode + PnP, tracker step (association, Kalman, scale pool, "
+                                  "second PnP) -- all on the device, frames resident", "precision": args.precision}
+        del tdet, tm
+    except Exception as e:
+        out["config5"] = {"error": repr(e)[:300]}
+    # ---- config 1: one 512 x 512 image, dlav1_34 (DCN + convGRU + GroupNorm)
+    try:
+        vopt = cpb.default_opt("dlav1_34")
+        vm = cpb.create_model(vopt.arch, vopt.heads, vopt.head_conv, vopt)
+        vm.precision = args.precision
+        vsd = synth.seeded_state_dict(vm, seed=0, offset_std=0.3, head_gain=HEAD_GAIN)
+        vm.load_state_dict(vsd)
+        vdet = cpb.ObjectPoseDetector(vopt, model=vm)
+        fr = synth.synthetic_frames(1, 512, 512, seed=7)
+        x1 = torch.from_numpy(synth.normalize_frames(fr)).to(dev)
+        meta1 = make_meta(1, np.array([256., 256.], np.float32), 512.0, 512, 512, cam).to(dev)
+        veng = vdet.model.engine(1, 512, 512, dev)
+        ms = ev_time(lambda: veng.infer(x1, meta1, decode_params(vopt)), reps=10)
+        c1 = {"arch": "dlav1_34", "batch": 1, "ours_ms": ms}
+        if not args.no_cpu_baseline:
+            from oracle import net_ref
+            torch.set_num_threads(usable_cores())
+            t0 = time.time()
+            net_ref.forward(x1.cpu(), vsd, vopt.heads, "dlav1_34")
+            c1["cpu_port_forward_s"] = time.time() - t0
+            c1["cpu_cores"] = usable_cores()
+        out["config1"] = c1
+        del vdet, vm
+    except Exception as e:
+        out["config1"] = {"error": repr(e)[:300]}
+    return out
 
 
 def run_reference(args):
@@ -196,6 +327,8 @@ def main():
                     help="tf32x3 (default): tcgen05 3-term split, fp32-equivalent (meets the fp32 parity bar); fp32: CUDA-core "
                          "parity mode; tf32: tcgen05 single pass (cuDNN-default-like math); bf16: tcgen05 bf16 operands")
     ap.add_argument("--no-fast-mode", action="store_true", help="skip the extra single-pass tf32 measurement")
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="skip the BASELINE.json configs 1 / 2 / 5 legs (batch-1 latency vs PyTorch-GPU, dlav1_34, tracking)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -206,8 +339,8 @@ def main():
     import centerpose_b200 as cpb
     from centerpose_b200 import _lib as L
     from centerpose_b200 import synth
-    from centerpose_b200.dist import all_gather_poses
-    from centerpose_b200.engine import decode_params, make_meta, preprocess
+    from centerpose_b200.dist import PoseBuffer
+    from centerpose_b200.engine import InferGraph, decode_params, make_meta, preprocess
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -243,21 +376,22 @@ def main():
                    for i in range(N_ROTATE)]
     dev_frames = [f.to(dev) for f in host_frames]
     x_buf = torch.empty((B, 3, 512, 512), dtype=torch.float32, device=dev)
-    poses = torch.empty((B, prm.K, L.CP_POSE_RECORD), dtype=torch.float32, device=dev)
-    n_valid = torch.empty((B,), dtype=torch.int32, device=dev)
+    # ONE persistent buffer per rank: cp_infer writes the pose records + n_valid straight into the layout the all-gather
+    # and the pinned device -> host copy use (centerpose_b200/dist.py); no packing kernel on the hot path
+    pbuf = PoseBuffer(B, prm.K, dev, world=world)
+    poses, n_valid = pbuf.poses, pbuf.n_valid
 
     def step_resident(i):
         preprocess(dev_frames[i % N_ROTATE], 512, 512, opt.mean, opt.std, out=x_buf)
         eng.infer(x_buf, meta, prm, poses=poses, n_valid=n_valid)
-        if world > 1:
-            return all_gather_poses(poses, n_valid)
-        return poses, n_valid
+        return pbuf.all_gather()
 
     def step_e2e(i):
-        p, n = det.run_batch(host_frames[i % N_ROTATE], cam, to_host=False)
-        if world > 1:
-            p, n = all_gather_poses(p, n)
-        return p.cpu(), n.cpu()                           # D2H of the step's result
+        det.run_batch(host_frames[i % N_ROTATE], cam, to_host=False, out=(poses, n_valid))
+        pbuf.all_gather()
+        if rank == 0:                                     # the caller's copy of the step's result: pinned, one D2H
+            pbuf.to_host(sync=True)
+        return pbuf.host
 
     def barrier():
         if world > 1:
@@ -349,16 +483,22 @@ def main():
                  "forward": ev_time(lambda: eng.forward(x_buf)),
                  "decode_softnms_pnp": ev_time(lambda: decode_pnp(heads_out, meta, prm, want_dets=False))}
 
-    # ---- HBM roofline of the decode / grouping / soft-NMS / PnP kernels (north_star): algorithmic bytes = the head maps
-    # they read once + the pose records they write
-    head_bytes = sum(int(v.numel()) * 4 for v in heads_out.values())
-    dec_bytes = head_bytes + B * prm.K * L.CP_POSE_RECORD * 4
+    # ---- HBM roofline of the decode / grouping / soft-NMS / PnP kernels (north_star).  Algorithmic bytes = SURVEY.md 8(d):
+    # scan hm + hm_hp once (9 x 128^2 x 4 B), gathers at the K centres, the pose records written = 0.68 MB per image
+    dec_bytes_img = (1 + 8) * 128 * 128 * 4 + prm.K * (2 + 16 + 2 + 3) * 4 + 8 * prm.K * 2 * 4 + prm.K * L.CP_POSE_RECORD * 4
+    dec_bytes = dec_bytes_img * B
     dec_gbs = dec_bytes / (breakdown["decode_softnms_pnp"] * 1e-3) / 1e9
+    heads1 = {k: v[:1].contiguous() for k, v in heads_out.items()}
+    meta1 = meta[:1].contiguous()
+    dec_b1_ms = ev_time(lambda: decode_pnp(heads1, meta1, prm, want_dets=False), reps=20)
     roofline_decode = {"bound": "hbm", "achieved": dec_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                        "frac": dec_gbs / peaks["hbm_gbs"], "traffic": None,
                        "kernel": "peaks_topk_kernel + group_pose_kernel", "algorithmic_bytes_per_step": dec_bytes,
-                       "ms_per_step": breakdown["decode_softnms_pnp"],
-                       "note": "latency-bound: per-channel radix select + one warp per object for the double-precision PnP"}
+                       "algorithmic_bytes_per_image": dec_bytes_img, "ms_per_step": breakdown["decode_softnms_pnp"],
+                       "note": "SURVEY.md 8(d) bytes (0.68 MB / image); latency-bound: per-channel radix select + one warp "
+                               "per object for the double-precision PnP"}
+    decode_us_per_frame = {"b32": breakdown["decode_softnms_pnp"] * 1e3 / B, "b1": dec_b1_ms * 1e3,
+                           "what": "sigmoid + NMS + top-K + grouping + affine + soft-NMS + PnP, CUDA events"}
 
     # ---- same step in the single-pass tf32 mode (what cuDNN does by default for fp32 convs on this class of GPU);
     # reported beside the headline, which stays on the fp32-equivalent mode
@@ -371,9 +511,7 @@ def main():
         def step_fast(i):
             preprocess(dev_frames[i % N_ROTATE], 512, 512, opt.mean, opt.std, out=x_buf)
             eng_fast.infer(x_buf, meta, prm, poses=poses, n_valid=n_valid)
-            if world > 1:
-                return all_gather_poses(poses, n_valid)
-            return poses, n_valid
+            return pbuf.all_gather()
 
         ms_fast = timed(step_fast, args.steps, args.warmup)
         fast_mode = {"precision": "tf32 (tcgen05 single pass)", "value": total_images / (ms_fast / 1e3), "unit": UNIT,
@@ -382,6 +520,10 @@ def main():
         eng = eng_main
         del eng_fast
 
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_extra_configs:
+        extra = extra_configs(args, det, eng, sd, opt, cam, dev, ev_time)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = usable_cores()
@@ -389,14 +531,16 @@ def main():
         fr = synth.synthetic_frames(args.cpu_sample, 512, 512, seed=317)
         cpu_reference_step(sd, opt, fr[:1], cam)
         t0 = time.time()
-        n = cpu_reference_step(sd, opt, fr, cam, budget_s=30.0)
+        stages = {}
+        n = cpu_reference_step(sd, opt, fr, cam, budget_s=30.0, stages=stages)
         dt = time.time() - t0
         cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "%d frames of the same workload, one frame per call like run()" % n}
+                        "sample": "%d frames of the same workload, one frame per call like run()" % n,
+                        "stage_ms_per_image": {k: v / n * 1e3 for k, v in stages.items()}}
 
     if rank == 0:
         h2d = B * 512 * 512 * 3 + meta.numel() * 8
-        d2h = B * prm.K * L.CP_POSE_RECORD * 4 * (world if world > 1 else 1) + B * 4 * world
+        d2h = pbuf.row * 4 * world                       # rank 0 reads the gathered records once (pinned)
         launches_per_step = eng.forward_launches + 2 + 1
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -412,6 +556,9 @@ def main():
                                              "math); deformable / strided ops on the 3-term split kernel"}[args.precision],
                        "weights": "seeded random init; hm / hm_hp biases calibrated so ~%d peaks per frame pass the "
                                   "thresholds" % TARGET_OBJECTS,
+                       "stage_b_bar": "network heads vs the reference: max-abs <= 3e-4 * max|head| on the small fixtures, 1e-3 at "
+                                      "512 x 512 (SURVEY.md 8d says 1e-4; the reference's own fp32 heads are 1e-4 from fp64 "
+                                      "there), always with gpu-vs-fp64 <= 4 x reference-vs-fp64 + 3e-5 (tests/util.py)",
                        "l2": "inputs rotate over %d distinct batches; per-step activations (~8 GB) exceed the 126 MB L2" % N_ROTATE,
                        "detections_per_image": det_per_img, "parallelism": "dp%d, 1 all-gather of pose records" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -420,6 +567,8 @@ def main():
             "clocks": clocks.summary(),
             "roofline": roofline,
             "roofline_decode": roofline_decode,
+            "decode_us_per_frame": decode_us_per_frame,
+            "config1": extra.get("config1"), "config2": extra.get("config2"), "config5": extra.get("config5"),
             "fast_mode": fast_mode,
             "stage_ms": breakdown,
             "cpu_baseline": cpu_baseline,

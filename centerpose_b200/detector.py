@@ -439,7 +439,8 @@ class ObjectPoseDetector(object):
             return path
 
     # ------------------------------------------------------------------ batched API (not in the reference)
-    def run_batch(self, frames, camera_matrix, pre_images=None, pre_hms=None, pre_hm_hp=None, to_host=True, track=False):
+    def run_batch(self, frames, camera_matrix, pre_images=None, pre_hms=None, pre_hm_hp=None, to_host=True, track=False,
+                  out=None):
         """frames: uint8 [B,H,W,3] (numpy / pinned CPU tensor / CUDA tensor) or a
         pre-processed fp32 [B,3,h,w] CUDA tensor.  One native cp_infer call for the
         whole batch.  Returns (poses [B,K,192], n_valid [B]) -- on the host when
@@ -447,7 +448,10 @@ class ObjectPoseDetector(object):
 
         track=True (tracking models): the batch is B independent VIDEO STREAMS and every call is their next frame.
         The previous frames, the tracker state and the rendered previous-frame heat maps stay on the device; returns
-        (tracks [B,T,320], n_tracks [B]) (layout: cp_track_field) instead."""
+        (tracks [B,T,320], n_tracks [B]) (layout: cp_track_field) instead.
+
+        out: optional (poses, n_valid) CUDA tensors to write into (e.g. the views of a dist.PoseBuffer, so that the
+        records land directly in the buffer of the all-gather / the pinned D2H copy)."""
         dev = self.opt.device
         if isinstance(frames, np.ndarray):
             frames = torch.from_numpy(frames)
@@ -481,7 +485,8 @@ class ObjectPoseDetector(object):
             if to_host:
                 return tracks.cpu().numpy(), nt.cpu().numpy()
             return tracks, nt
-        _, poses, n_valid = eng.infer(x, meta, prm, pre_images, pre_hms, pre_hm_hp)
+        _, poses, n_valid = eng.infer(x, meta, prm, pre_images, pre_hms, pre_hm_hp,
+                                      poses=out[0] if out is not None else None, n_valid=out[1] if out is not None else None)
         if to_host:
             return poses.cpu().numpy(), n_valid.cpu().numpy()
         return poses, n_valid

@@ -265,6 +265,48 @@ class Engine(object):
         return dets, poses, n_valid
 
 
+class InferGraph(object):
+    """cp_infer captured once in a CUDA graph (static buffers): a step is two small copies + one graph launch instead of
+    ~80 kernel launches driven from the host -- what matters at batch 1, where the launch sequence, not the kernels,
+    sets the latency.  `graph(x, meta)` -> (poses, n_valid) (views of the graph's own output buffers)."""
+
+    def __init__(self, eng, batch, prm, tracking=False):
+        self.eng, self.prm = eng, prm
+        dev = eng.device
+        H, W = eng.height, eng.width
+        self.x = torch.zeros((batch, 3, H, W), dtype=torch.float32, device=dev)
+        self.meta = torch.zeros((batch, _lib.CP_META_DOUBLES), dtype=torch.float64, device=dev)
+        self.meta[:, 2] = float(max(H, W))
+        self.meta[:, 3], self.meta[:, 4] = W, H
+        self.meta[:, 5], self.meta[:, 9], self.meta[:, 13] = 1.0, 1.0, 1.0
+        self.pre = None
+        if tracking:
+            self.pre = (torch.zeros_like(self.x), torch.zeros((batch, 1, H, W), dtype=torch.float32, device=dev),
+                        torch.zeros((batch, 8, H, W), dtype=torch.float32, device=dev))
+        self.poses = torch.zeros((batch, prm.K, _lib.CP_POSE_RECORD), dtype=torch.float32, device=dev)
+        self.n_valid = torch.zeros((batch,), dtype=torch.int32, device=dev)
+        pre = self.pre if self.pre is not None else (None, None, None)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):            # warm-up outside the capture: lazy allocations, launch attributes
+            for _ in range(2):
+                eng.infer(self.x, self.meta, prm, *pre, poses=self.poses, n_valid=self.n_valid)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            eng.infer(self.x, self.meta, prm, *pre, poses=self.poses, n_valid=self.n_valid)
+
+    def __call__(self, x, meta, pre_img=None, pre_hm=None, pre_hm_hp=None):
+        self.x.copy_(x, non_blocking=True)
+        self.meta.copy_(meta, non_blocking=True)
+        if self.pre is not None:
+            for dst, src in zip(self.pre, (pre_img, pre_hm, pre_hm_hp)):
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.poses, self.n_valid
+
+
 def preprocess(frames_u8, dst_h, dst_w, mean, std, out=None, trans_input=None):
     """cp_preprocess: uint8 [B,H,W,3] CUDA -> fp32 [B,3,dst_h,dst_w] CUDA (bit-exact cv2.warpAffine + normalise).
     trans_input: optional 2x3 forward affine (meta['trans_input']); default = the fix_res affine of the frame size."""

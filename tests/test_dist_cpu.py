@@ -8,7 +8,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from centerpose_b200 import _lib as L
-from centerpose_b200.dist import all_gather_poses, pack, shard_range, unpack
+from centerpose_b200.dist import PoseBuffer, all_gather_poses, pack, shard_range, unpack
 
 
 def test_shard_range_covers_batch():
@@ -24,8 +24,20 @@ def test_shard_range_covers_batch():
 def test_pack_roundtrip():
     p = torch.randn(3, 100, L.CP_POSE_RECORD)
     n = torch.tensor([0, 7, 100], dtype=torch.int32)
-    p2, n2 = unpack(pack(p, n), 100)
+    p2, n2 = unpack(pack(p, n), 3, 100)
     assert torch.equal(p, p2) and torch.equal(n, n2)
+
+
+def test_pose_buffer_views_alias_one_flat_tensor():
+    buf = PoseBuffer(4, 100, "cpu", world=1)
+    buf.poses.copy_(torch.arange(buf.n_pose, dtype=torch.float32).view(4, 100, L.CP_POSE_RECORD))
+    buf.n_valid.copy_(torch.tensor([3, 0, 100, 7], dtype=torch.int32))
+    assert buf.poses.data_ptr() == buf.flat.data_ptr() and buf.poses.is_contiguous() and buf.n_valid.is_contiguous()
+    buf.all_gather()
+    buf.to_host()
+    p, n = buf.host_views()
+    assert p.shape == (4, 100, L.CP_POSE_RECORD) and float(p[3, 99, -1]) == buf.n_pose - 1
+    assert n.tolist() == [3, 0, 100, 7]
 
 
 def _worker(rank, world, port, ret):
@@ -40,6 +52,16 @@ def _worker(rank, world, port, ret):
         nv = torch.arange(B, dtype=torch.int32)
         poses, n_valid = all_gather_poses(full[lo:hi].clone(), nv[lo:hi].clone())
         ok = torch.equal(poses, full) and torch.equal(n_valid, nv)
+        # the persistent-buffer form the bench / serving path uses
+        buf = PoseBuffer(hi - lo, K, "cpu", world=world, pin=False)
+        buf.poses.copy_(full[lo:hi])
+        buf.n_valid.copy_(nv[lo:hi])
+        buf.all_gather()
+        buf.to_host()
+        hp, hn = buf.host_views()
+        ok = ok and np.array_equal(hp, full.numpy()) and hn.tolist() == nv.tolist()
+        dp, dn = buf.views(buf.gathered)
+        ok = ok and torch.equal(dp, full) and torch.equal(dn, nv)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

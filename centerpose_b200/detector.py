@@ -113,7 +113,7 @@ class ObjectPoseDetector(object):
         self.model = model if model is not None else create_model(opt.arch, opt.heads, opt.head_conv, opt)
         if getattr(opt, "load_model", ""):
             self.model = load_model(self.model, opt.load_model)
-        self.model = self.model.to(opt.device)
+        self.model = self._to_device(self.model)
         self.model.eval()
         self.mean = np.array(opt.mean, dtype=np.float32).reshape(1, 1, 3)
         self.std = np.array(opt.std, dtype=np.float32).reshape(1, 1, 3)
@@ -133,6 +133,10 @@ class ObjectPoseDetector(object):
             self.tracker = Tracker(opt, streams=1, device=opt.device)
         self._batch_tracker = None
         self._batch_pre = None
+
+    def _to_device(self, t):
+        """base_detector.py:41,436: everything the network touches lives on opt.device (always CUDA here)."""
+        return t.to(self.opt.device)
 
     # base_detector.py:91-148 -- the reference's cv2 pre-processing (host side), all three modes
     def pre_process(self, image, scale, input_meta={}):
@@ -241,7 +245,7 @@ class ObjectPoseDetector(object):
         else:
             images = torch.from_numpy(np.expand_dims(image, axis=0))
             meta = meta_inp
-        images = images.to(self.opt.device)
+        images = self._to_device(images)
 
         pre_hms, pre_hm_hp, pre_inds = None, None, None
         if tracking:

@@ -1,0 +1,162 @@
+"""Drop-in proof (SURVEY.md rows a-12 / b / f-3): the reference's own `src/demo.py`, UNMODIFIED, is
+run twice through `runpy` on the same image and checkpoint --
+
+  arm A: the unmodified reference (`lib.*` as shipped, CPU, `--gpus -1`),
+  arm B: after `centerpose_b200.dropin.install()`: `lib.models.model` / `lib.detectors.detector_factory` resolve to this
+         package, so demo.py builds OUR ObjectPoseDetector from the reference's own `opts().parse / init` Namespace and
+         calls OUR `run()` (pre_process, result structures, dict_out, save_results).
+
+and the JSON files both arms write with `--debug 4` (object_pose.py:357-414) are compared key by key.  There is no GPU
+in the build container, so in arm B the two device stages (`DLASegB200.forward`, `cp_decode_pnp`) are replaced by the CPU
+oracle (test infrastructure) -- everything else of arm B is the product's host code.  On the GPU box (no reference tree
+there) `test_demo_flow_on_gpu` runs the same flow with the real engine on the committed sample frames.
+"""
+import copy
+import json
+import os
+import runpy
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import centerpose_b200 as cpb
+from centerpose_b200 import _lib as L
+from centerpose_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FRAME = os.path.join(ROOT, "tests", "data", "frame_0.png")
+OBJECT_KEYS = {"class", "ct", "bbox", "confidence", "kps_displacement_mean", "kps_heatmap_mean", "kps_heatmap_std",
+               "kps_heatmap_height", "obj_scale", "location", "quaternion_xyzw", "kps_pnp", "kps_3d_cam"}
+
+
+def _oracle_process(self, images, pre_images=None, pre_hms=None, pre_hm_hp=None, pre_inds=None, return_time=False, meta=None):
+    """CPU stand-in for the two device stages of ObjectPoseDetector.process (network + fused decode / PnP)."""
+    import time
+    from centerpose_b200.detector import dets_to_dict
+    from oracle import decode_ref, net_ref
+    from tests.util import oracle_records
+    sd = {k: v.detach().cpu() for k, v in self.model.state_dict().items()}
+    heads = net_ref.forward(images.cpu(), sd, self.opt.heads, "dla_34")
+    forward_time = time.time()
+    prm = decode_ref.DecodeParams(rep_mode=self.opt.rep_mode, vis_thresh=self.opt.vis_thresh, category=self.opt.c)
+    hb = {k: v[0].numpy() for k, v in heads.items()}
+    s = meta["s"]
+    s = float(s[0]) if isinstance(s, np.ndarray) and s.ndim else float(s)
+    dets, recs = oracle_records(hb, prm, np.asarray(meta["camera_matrix"], np.float64), meta["width"], meta["height"],
+                                np.asarray(meta["c"], np.float32), s, L)
+    poses = np.zeros((1, self.opt.K, L.CP_POSE_RECORD), np.float32)
+    poses[0, :recs.shape[0]] = recs
+    self._last = (poses, np.array([recs.shape[0]], np.int32))
+    self._last_dev = None
+    output = {k: v.clone() for k, v in heads.items()}
+    output["hm"] = output["hm"].sigmoid_()
+    output["hm_hp"] = output["hm_hp"].sigmoid_()
+    packed = np.zeros((1, self.opt.K, L.CP_DETS_RECORD), np.float32)
+    d = dets_to_dict(packed)
+    return (output, d, forward_time) if return_time else (output, d)
+
+
+@pytest.fixture(scope="module")
+def checkpoint(tmp_path_factory):
+    """Seeded dla_34 weights whose heat-map biases let a few centres pass vis_thresh on the sample frame, saved the way
+    the reference saves checkpoints."""
+    from oracle import net_ref
+    import cv2
+    opt = cpb.default_opt("dla_34")
+    m = cpb.create_model(opt.arch, opt.heads, opt.head_conv, opt)
+    m.load_state_dict(synth.seeded_state_dict(m, seed=9, offset_std=0.3, head_gain=6.0))
+    img = cv2.imread(FRAME)
+    # the reference pre-process at 512 x 512 (cv2), then calibrate the two heat-map biases on the oracle heads
+    from oracle import preprocess_ref as pr
+    x = torch.from_numpy(pr.pre_process(img, 512, 512, opt.mean, opt.std))
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    synth.calibrate_head_bias(m, net_ref.forward(x, sd, opt.heads, "dla_34"), target=10)
+    path = str(tmp_path_factory.mktemp("ckpt") / "chair_seeded.pth")
+    cpb.save_model(path, 1, m)
+    return path
+
+
+def _run_demo(argv, cwd):
+    saved_argv, saved_cwd = sys.argv, os.getcwd()
+    sys.argv = ["demo.py"] + argv
+    os.chdir(cwd)
+    try:
+        runpy.run_path("/root/reference/src/demo.py", run_name="__main__")
+    finally:
+        sys.argv = saved_argv
+        os.chdir(saved_cwd)
+
+
+def test_demo_py_runs_unchanged_on_the_dropin(reference, checkpoint, tmp_path, monkeypatch):
+    from centerpose_b200 import dropin
+    src = "/root/reference/src"
+    monkeypatch.syspath_prepend(src)
+    out_a, out_b = str(tmp_path / "ref") + "/", str(tmp_path / "ours") + "/"
+    common = ["--demo", FRAME, "--arch", "dla_34", "--load_model", checkpoint, "--debug", "4", "--c", "shoe"]
+    # ---- arm A: the unmodified reference on the CPU (torch-1.1 comparison semantics)
+    with reference.legacy_bool_arith():
+        _run_demo(common + ["--gpus", "-1", "--demo_save", out_a], src)
+    ja = json.load(open(os.path.join(out_a, "frame_0", "frame_0.json")))
+    # ---- arm B: same script, same argv, our package behind the reference's import names
+    saved = {k: sys.modules.get(k) for k in ("lib.models.model", "lib.detectors.detector_factory", "_ext")}
+    try:
+        dropin.install(ext=False)
+        monkeypatch.setattr(cpb.ObjectPoseDetector, "process", _oracle_process)
+        monkeypatch.setattr(cpb.ObjectPoseDetector, "_to_device", lambda self, t: t)
+        _run_demo(common + ["--gpus", "0", "--demo_save", out_b], src)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    jb = json.load(open(os.path.join(out_b, "frame_0", "frame_0.json")))
+    # ---- same schema, same objects
+    assert set(ja) == set(jb) == {"camera_data", "objects"}
+    assert np.allclose(ja["camera_data"], jb["camera_data"])
+    assert len(ja["objects"]) == len(jb["objects"]) >= 1, (len(ja["objects"]), len(jb["objects"]))
+    for oa, ob in zip(ja["objects"], jb["objects"]):
+        assert set(oa) == set(ob) == OBJECT_KEYS, (sorted(oa), sorted(ob))
+        assert oa["class"] == ob["class"]
+        for k in OBJECT_KEYS - {"class"}:
+            a, b = np.asarray(oa[k], np.float64), np.asarray(ob[k], np.float64)
+            assert a.shape == b.shape, k
+            if k == "quaternion_xyzw" and np.dot(a, b) < 0:
+                b = -b
+            # The keypoints of a random-weight network are not a projected cuboid, so the PnP problem is far from
+            # consistent and cv2's LM (arm A) and the restated LM (arm B, 20-iteration cap) stop at
+            # slightly different points: the four PnP outputs get a loose bound here; on consistent keypoints the two
+            # agree to 1e-6 (tests/test_pose_core_host.py, tests/test_oracle_decode.py).
+            tol = {"quaternion_xyzw": 5e-2, "location": 5e-2, "kps_3d_cam": 5e-2, "kps_pnp": 5e-2, "confidence": 1e-5,
+                   "kps_heatmap_height": 1e-5, "obj_scale": 1e-5}.get(k, 2e-3)      # pixels: fp32 records
+            scale = max(1.0, np.abs(a).max()) if k in ("location", "kps_3d_cam", "kps_pnp") else 1.0
+            assert np.abs(a - b).max() <= tol * scale, (k, float(np.abs(a - b).max()))
+    # the rendered image exists in both arms (the reference's Debugger is importable inside its tree)
+    assert any(f.endswith(".png") for f in os.listdir(os.path.join(out_b, "frame_0")))
+
+
+@pytest.mark.gpu
+def test_demo_flow_on_gpu(cplib, tmp_path):
+    """The demo flow (demo.py:22-87: Detector(opt) from a checkpoint path -> run(image path, meta_inp) per file ->
+    --debug 4 JSON) with the real engine, on the committed sample frames."""
+    opt = cpb.default_opt("dla_34", debug=4)
+    m = cpb.create_model(opt.arch, opt.heads, opt.head_conv, opt)
+    m.load_state_dict(synth.seeded_state_dict(m, seed=9, offset_std=0.3, head_gain=6.0))
+    ck = str(tmp_path / "chair_seeded.pth")
+    cpb.save_model(ck, 1, m)
+    opt.load_model = ck
+    opt.demo = os.path.join(ROOT, "tests", "data")
+    opt.demo_save = str(tmp_path / "save")
+    cam = np.array([[663.0287679036459, 0, 300.2775065104167], [0, 663.0287679036459, 395.00066121419275], [0, 0, 1]])
+    det = cpb.detector_factory["object_pose"](opt)
+    det.pause = False
+    names = sorted(f for f in os.listdir(opt.demo) if f.endswith(".png"))
+    for f in names:
+        ret = det.run(os.path.join(opt.demo, f), meta_inp={"camera_matrix": cam})
+        assert set(ret) == {"results", "boxes", "output", "tot", "load", "pre", "net", "dec", "post", "merge", "pnp", "track"}
+        j = json.load(open(os.path.join(opt.demo_save, "data", os.path.splitext(f)[0] + ".json")))
+        assert set(j) == {"camera_data", "objects"} and len(j["objects"]) == len(ret["boxes"])
+        for o in j["objects"]:
+            assert set(o) == OBJECT_KEYS

@@ -441,7 +441,9 @@ def main():
         args.precision, "igemm_umma_kernel")
     traffic = None
     pipe_pct = None
-    tpath = os.path.join(ROOT, "profiles", "r01_dominant_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_dominant_traffic.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r01_dominant_traffic.json")
     if os.path.exists(tpath):          # dram__bytes_read + dram__bytes_write of this launch, from the committed ncu capture
         tj = json.load(open(tpath))
         traffic = tj.get(kname + "@" + dom["name"])

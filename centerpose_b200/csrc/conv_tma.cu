@@ -158,6 +158,93 @@ __device__ __forceinline__ void fused_part_smem(const float (&sums)[128], float 
   }
 }
 
+// ---- MMA issue loop (one warp; see the comment at its call site) --------------------------------------------------------
+struct IssueCtx {
+  uint32_t idesc, dhi, rowu, a_lo_u, b_lo_u, sub_u, a0_u, a_stage_u, b0_u, b_stage_u, tmem_base, buf_cols, bn;
+  uint32_t bar_a, bar_a_empty, bar_b_full, bar_b_empty, bar_p_full, bar_p_empty;
+  uint32_t tap_u[9];
+  int group, KB, SA, SB, nslab, cluster;
+  uint16_t cmask;
+};
+struct IssueState {
+  int sa = 0, sb = 0, buf = 0;
+  uint32_t pa = 0, pb = 0, pe = 0;        // pe bit b: phase of p_empty[b]
+};
+
+template <bool X3, int MS, int TAPS, int KS>
+__device__ __forceinline__ void issue_tile(const IssueCtx& c, IssueState& st, uint32_t tap0, bool sub1_live) {
+  int kbi = 0, gk = 0;                     // K-block index inside the tile (slab-major, tap-minor) / inside its group
+  for (int s = 0; s < c.nslab; ++s) {
+    mbar_wait(c.bar_a + 8u * (uint32_t)st.sa, st.pa);
+    tc_fence_after();
+    const uint32_t a_slab = c.a0_u + (uint32_t)st.sa * c.a_stage_u + tap0;
+#pragma unroll
+    for (int tap = 0; tap < TAPS; ++tap, ++kbi) {
+      const bool first = X3 ? (gk == 0) : (kbi == 0);
+      if (first)                           // new accumulation group / tile: the epilogue must have drained this TMEM buffer
+        mbar_wait(c.bar_p_empty + 8u * (uint32_t)st.buf, ((st.pe >> st.buf) & 1u) ^ 1u);
+      mbar_wait(c.bar_b_full + 8u * (uint32_t)st.sb, st.pb);
+      tc_fence_after();
+      const uint32_t da = a_slab + c.tap_u[tap];
+      const uint32_t db = c.b0_u + (uint32_t)st.sb * c.b_stage_u;
+      const uint32_t d_tmem = c.tmem_base + (uint32_t)st.buf * c.buf_cols;
+      const bool last = X3 ? (gk == c.group - 1 || kbi == c.KB - 1) : (kbi == c.KB - 1);
+      if (elect_one()) {
+        if (X3) {
+          // The accumulator truncates every add (error ~ its magnitude x chain length): the two cross terms of all K
+          // slices go first, while the accumulator still holds small values, the hi x hi terms last.
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+#pragma unroll
+            for (int sub = 0; sub < MS; ++sub) {          // rows [128 sub, 128 sub + 128) of the tile
+              if (sub > 0 && !sub1_live) continue;        // no output position in the second half (image tail)
+              const uint32_t das = da + (uint32_t)sub * c.sub_u + 2u * ks;
+              const uint32_t dt = d_tmem + (uint32_t)sub * c.bn;
+              umma_tf32_lohi(dt, das + c.a_lo_u, db + 2u * ks, c.dhi, c.idesc, acc);
+              umma_tf32_lohi(dt, das, db + c.b_lo_u + 2u * ks, c.dhi, c.idesc, 1u);
+            }
+          }
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int sub = 0; sub < MS; ++sub) {
+              if (sub > 0 && !sub1_live) continue;
+              umma_tf32_lohi(d_tmem + (uint32_t)sub * c.bn, da + (uint32_t)sub * c.sub_u + 2u * ks, db + 2u * ks, c.dhi,
+                             c.idesc, 1u);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks)
+            umma_tf32_lohi(d_tmem, da + 2u * ks, db + 2u * ks, c.dhi, c.idesc, (first && ks == 0) ? 0u : 1u);
+        }
+        if (c.cluster > 1)
+          umma_commit_multicast(c.bar_b_empty + 8u * (uint32_t)st.sb, c.cmask);
+        else
+          umma_commit(c.bar_b_empty + 8u * (uint32_t)st.sb);
+        if (last) umma_commit(c.bar_p_full + 8u * (uint32_t)st.buf);        // group / tile finished -> epilogue
+        if (tap == TAPS - 1) umma_commit(c.bar_a_empty + 8u * (uint32_t)st.sa);
+      }
+      if (++st.sb == c.SB) {
+        st.sb = 0;
+        st.pb ^= 1u;
+      }
+      if (last) {
+        st.pe ^= 1u << st.buf;
+        st.buf ^= 1;
+        gk = 0;
+      } else {
+        ++gk;
+      }
+    }
+    if (++st.sa == c.SA) {
+      st.sa = 0;
+      st.pa ^= 1u;
+    }
+  }
+}
+
 // PERSISTENT kernel: gridDim.x = min(#tiles, #SMs); CTA c processes tiles c, c + gridDim.x, ...  Every role keeps its
 // pipeline state across tiles, so the TMA / split / MMA of tile i+1 overlap the epilogue of tile i and the fixed cost
 // of a CTA (barrier init, TMEM allocation, descriptor fetch, pipeline fill) is paid once per SM instead of per tile.
@@ -228,9 +315,9 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   if (warp < 4) {
   if (X3) {
     if (FUSE)
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     else
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
   }
   if (warp == 0) {
     // ===================== activation slabs via TMA =====================
@@ -296,102 +383,60 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     // (descriptors and barrier addresses stay in uniform registers), one elected lane issues, and a descriptor is a
     // constant template plus (shared byte address >> 4) - stepping through taps and K slices is one add on the low word
     // (the 14-bit address field cannot carry: shared addresses stay below 256 KB).
-    const uint32_t idesc = make_idesc_tf32(p.BN);
+    // Measured again in round 2 (profiles/r02_l2conv_ncu.md): with every operand pipeline full the warp spends 1500 clk
+    // per 16-channel K block on ~170 dependent instructions (12 % issue rate: constant re-loads, uniform-register chains,
+    // tap arithmetic) for 384 - 768 clk of MMA work -- the heads launch was bound by THIS loop, not by the L2 -> SM
+    // stream.  The loop below is specialised at compile time on (taps, K slices): the nine taps are unrolled with their
+    // descriptor offsets in registers, all parameters are hoisted, and a K block costs two barrier polls + its MMAs.
+    IssueCtx c;
+    c.idesc = make_idesc_tf32(p.BN);
     const uint64_t dtmpl = make_desc(0, 0, p.cslab);
-    const uint32_t dhi = (uint32_t)(dtmpl >> 32), dlo0 = (uint32_t)dtmpl;     // descriptors are handled as 32-bit low words
-    const uint32_t rowu = rowb >> 4;                              // row pitch in descriptor units
-    const uint32_t a_lo_u = p.slab_stride >> 4;                   // x3: lo slab behind the hi slab
-    const uint32_t b_lo_u = ((uint32_t)p.BN * rowb) >> 4;         // x3: lo tile behind the hi tile
-    const int group = p.group;
-    int sa = 0, sb = 0, buf = 0;
-    uint32_t pa = 0, pb = 0, pe = 0;                              // pe bit b: phase of p_empty[b]
+    c.dhi = (uint32_t)(dtmpl >> 32);
+    const uint32_t dlo0 = (uint32_t)dtmpl;
+    c.rowu = rowb >> 4;
+    c.a_lo_u = p.slab_stride >> 4;
+    c.b_lo_u = ((uint32_t)p.BN * rowb) >> 4;
+    c.sub_u = (uint32_t)TM_BM * c.rowu;
+    c.a0_u = dlo0 + (slabs0 >> 4);
+    c.a_stage_u = a_stage >> 4;
+    c.b0_u = dlo0 + (btiles0 >> 4);
+    c.b_stage_u = btile_bytes >> 4;
+    c.tmem_base = tmem_base;
+    c.buf_cols = (uint32_t)(p.BN * MS);
+    c.bn = (uint32_t)p.BN;
+    c.group = p.group;
+    c.KB = KB;
+    c.SA = p.SA;
+    c.SB = p.SB;
+    c.nslab = nslab;
+    c.bar_a = smem_u32(X3 ? &ctl->a_split[0] : &ctl->a_full[0]);
+    c.bar_a_empty = smem_u32(&ctl->a_empty[0]);
+    c.bar_b_full = smem_u32(&ctl->b_full[0]);
+    c.bar_b_empty = smem_u32(&ctl->b_empty[0]);
+    c.bar_p_full = smem_u32(&ctl->p_full[0]);
+    c.bar_p_empty = smem_u32(&ctl->p_empty[0]);
+    c.cluster = p.cluster;
+    c.cmask = cmask;
+    for (int t = 0; t < 9; ++t) c.tap_u[t] = (p.k == 3) ? (uint32_t)((t / 3) * p.Wt + (t % 3)) * c.rowu : 0u;
+    IssueState st;
+    const int Wt = p.Wt, HWt = p.H * p.Wt, k = p.k;
+    const long long total_pos = (long long)p.B * p.H * p.W;
     for (long long it = 0, tile = tile_at(0); tile < total_tiles; tile = tile_at(++it)) {
       bool live;
       const TileGeo g = decode_tile(p, tile, n_tiles, rank, &live);
-      const uint32_t tap0 = (p.k == 3) ? (uint32_t)(g.g0 - 1 - g.r_lo * p.Wt) * rowu : 0u;
+      const uint32_t tap0 = (k == 3) ? (uint32_t)(g.g0 - 1 - g.r_lo * Wt) * c.rowu : 0u;
       // x3: small feature maps end inside the first 128 rows of their last tile; the second accumulator is then skipped
-      const bool sub1_live = (p.k == 3) ? (g.g0 + TM_BM < p.H * p.Wt) : (g.pos0 + TM_BM < (long long)p.B * p.H * p.W);
-      int kbi = 0, gk = 0;               // K-block index inside the tile (slab-major, tap-minor) / inside its group
-      for (int s = 0; s < nslab; ++s) {
-        mbar_wait(smem_u32(X3 ? &ctl->a_split[sa] : &ctl->a_full[sa]), pa);
-        tc_fence_after();
-        const uint32_t a_slab = dlo0 + ((slabs0 + (uint32_t)sa * a_stage) >> 4) + tap0;
-        for (int ky = 0; ky < p.k; ++ky) {
-          for (int kx = 0; kx < p.k; ++kx, ++kbi) {
-            const bool first = X3 ? (gk == 0) : (kbi == 0);
-            if (first) {                 // new accumulation group / tile: the epilogue must have drained this TMEM buffer
-              mbar_wait(smem_u32(&ctl->p_empty[buf]), ((pe >> buf) & 1u) ^ 1u);
-            }
-            mbar_wait(smem_u32(&ctl->b_full[sb]), pb);
-            tc_fence_after();
-            const uint32_t da = a_slab + (uint32_t)(ky * p.Wt + kx) * rowu;
-            const uint32_t db = dlo0 + ((btiles0 + (uint32_t)sb * btile_bytes) >> 4);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN * MS);
-            const bool last = X3 ? (gk == group - 1 || kbi == KB - 1) : (kbi == KB - 1);
-            const bool slab_done = (ky == p.k - 1) && (kx == p.k - 1);
-            if (elect_one()) {
-              if (X3) {
-                // The accumulator truncates every add (error ~ its magnitude x chain length): the two cross terms of
-                // all K slices go first, while the accumulator still holds small values, the hi x hi terms last.
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  if (ks < kslices) {
-                    const uint32_t acc = (first && ks == 0) ? 0u : 1u;
-#pragma unroll
-                    for (int sub = 0; sub < MS; ++sub) {          // rows [128 sub, 128 sub + 128) of the tile
-                      if (sub > 0 && !sub1_live) continue;        // no output position in the second half (image tail)
-                      const uint32_t das = da + (uint32_t)(sub * TM_BM) * rowu + 2u * ks;
-                      const uint32_t dt = d_tmem + (uint32_t)(sub * p.BN);
-                      umma_tf32_lohi(dt, das + a_lo_u, db + 2u * ks, dhi, idesc, acc);
-                      umma_tf32_lohi(dt, das, db + b_lo_u + 2u * ks, dhi, idesc, 1u);
-                    }
-                  }
-                }
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  if (ks < kslices) {
-#pragma unroll
-                    for (int sub = 0; sub < MS; ++sub) {
-                      if (sub > 0 && !sub1_live) continue;
-                      const uint32_t das = da + (uint32_t)(sub * TM_BM) * rowu + 2u * ks;
-                      umma_tf32_lohi(d_tmem + (uint32_t)(sub * p.BN), das, db + 2u * ks, dhi, idesc, 1u);
-                    }
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  if (ks < kslices) {
-                    const uint32_t acc = (first && ks == 0) ? 0u : 1u;
-                    umma_tf32_lohi(d_tmem, da + 2u * ks, db + 2u * ks, dhi, idesc, acc);
-                  }
-                }
-              }
-              if (p.cluster > 1)
-                umma_commit_multicast(smem_u32(&ctl->b_empty[sb]), cmask);
-              else
-                umma_commit(smem_u32(&ctl->b_empty[sb]));
-              if (last) umma_commit(smem_u32(&ctl->p_full[buf]));        // group / tile finished -> epilogue
-              if (slab_done) umma_commit(smem_u32(&ctl->a_empty[sa]));
-            }
-            __syncwarp();
-            if (++sb == p.SB) {
-              sb = 0;
-              pb ^= 1u;
-            }
-            if (last) {
-              pe ^= 1u << buf;
-              buf ^= 1;
-              gk = 0;
-            } else {
-              ++gk;
-            }
-          }
-        }
-        if (++sa == p.SA) {
-          sa = 0;
-          pa ^= 1u;
-        }
+      const bool sub1_live = (k == 3) ? (g.g0 + TM_BM < HWt) : (g.pos0 + TM_BM < total_pos);
+      if (k == 3) {
+        if (kslices == 2)
+          issue_tile<X3, MS, 9, 2>(c, st, tap0, sub1_live);
+        else
+          issue_tile<X3, MS, 9, 4>(c, st, tap0, sub1_live);
+      } else {
+        if (kslices == 2)
+          issue_tile<X3, MS, 1, 2>(c, st, tap0, sub1_live);
+        else
+          issue_tile<X3, MS, 1, 4>(c, st, tap0, sub1_live);
       }
     }
   } else if (X3 && FUSE) {
@@ -412,7 +457,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     __syncwarp();
   }
   } else if (X3 && warp >= 12) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     // ===================== hi / lo splitters (x3): slab -> tf32-exact hi (in place) + lo slab =====================
     const int st = tid - 384;
     int stage = 0;
@@ -452,7 +497,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   } else if (warp >= 4 && warp < 4 + 4 * MS) {
     if (X3) {
       if (FUSE)
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
       else
         asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     }
@@ -515,14 +560,22 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
         for (int gi = 0; gi < ngroups; ++gi) {
           mbar_wait(smem_u32(&ctl->p_full[buf]), (pf >> buf) & 1u);
           tc_fence_after();
+          // 32 columns per tcgen05.ld: with one accumulation group = 12 MMAs the drain of a TMEM buffer has to finish inside
+          // the ~1500 clk the tensor pipe needs for the next group, and every ld + wait round trip costs ~150 clk
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            if (c * 16 < p.BN) {
-              uint32_t rr[16];
-              tmem_ld16(lane_base + (uint32_t)(buf * p.BN * MS + c * 16), rr);
+          for (int c = 0; c < 4; ++c) {
+            if (c * 32 < p.BN) {
+              uint32_t rr[32];
+              if (c * 32 + 16 < p.BN) {
+                tmem_ld32(lane_base + (uint32_t)(buf * p.BN * MS + c * 32), rr);
+              } else {
+                tmem_ld16(lane_base + (uint32_t)(buf * p.BN * MS + c * 32), rr);
+#pragma unroll
+                for (int j = 16; j < 32; ++j) rr[j] = 0u;
+              }
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 16; ++j) sums[(X3 ? c * 16 + j : 0)] += __uint_as_float(rr[j]);
+              for (int j = 0; j < 32; ++j) sums[(X3 ? c * 32 + j : 0)] += __uint_as_float(rr[j]);
             }
           }
           tc_fence_before();

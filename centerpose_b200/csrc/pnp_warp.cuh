@@ -195,7 +195,11 @@ __device__ void solve_and_shell_warp(const double* pts, int n_in, const float* o
   const int n = pose::pnp_collect(pts, n_in, obj_scale, V, X, uv);
   o->n_pts = n;
   o->status = CP_PNP_FEW_POINTS;
-  if (n < 6) return;
+  if (n < 4) return;
+  if (n < 6) {          // EPnP (rare path): evaluated redundantly by every lane, identical results
+    pose::pnp_few_points(V, X, uv, n, Kc, width, height, visible_thresh, opencv_return, o);
+    return;
+  }
   double R[9], t[3];
   dlt_init_warp(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t, sm, lane);
   const double cost = refine_lm_warp(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t, sm, lane);
@@ -210,7 +214,11 @@ __device__ void solve_and_shell_warp_v(const double* pts, int n_in, const double
   const int n = pose::pnp_collect_v(pts, n_in, V, X, uv);
   o->n_pts = n;
   o->status = CP_PNP_FEW_POINTS;
-  if (n < 6) return;
+  if (n < 4) return;
+  if (n < 6) {          // EPnP (rare path): evaluated redundantly by every lane, identical results
+    pose::pnp_few_points(V, X, uv, n, Kc, width, height, visible_thresh, opencv_return, o);
+    return;
+  }
   double R[9], t[3];
   dlt_init_warp(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t, sm, lane);
   const double cost = refine_lm_warp(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t, sm, lane);

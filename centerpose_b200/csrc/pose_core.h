@@ -132,10 +132,10 @@ CP_HD void cuboid_vertices(const float* scale, double* V /*[8][3]*/) {
       }
 }
 
-// cyclic Jacobi eigen-decomposition of a symmetric N x N matrix (row-major, destroyed);
-// returns the eigenvector of the smallest eigenvalue in `vmin`.
+// cyclic Jacobi eigen-decomposition of a symmetric N x N matrix (row-major, destroyed: eigenvalues end on the diagonal);
+// the eigenvectors are the COLUMNS of V.
 template <int N>
-CP_HDN void jacobi_min_eigvec(double* A, double* V, double* vmin) {
+CP_HDN void jacobi_eig(double* A, double* V) {
   for (int i = 0; i < N; ++i)
     for (int j = 0; j < N; ++j) V[i * N + j] = (i == j) ? 1.0 : 0.0;
   for (int sweep = 0; sweep < 60; ++sweep) {
@@ -170,6 +170,12 @@ CP_HDN void jacobi_min_eigvec(double* A, double* V, double* vmin) {
         }
       }
   }
+}
+
+// returns the eigenvector of the smallest eigenvalue in `vmin`.
+template <int N>
+CP_HDN void jacobi_min_eigvec(double* A, double* V, double* vmin) {
+  jacobi_eig<N>(A, V);
   int m = 0;
   for (int i = 1; i < N; ++i)
     if (A[i * N + i] < A[m * N + m]) m = i;
@@ -342,6 +348,296 @@ CP_HDN double refine_lm(const double* X, const double* uv, int n, double fx, dou
   return cost;
 }
 
+
+// ---- EPnP (Lepetit, Moreno-Noguer, Fua, IJCV 2009) for 4 - 5 valid points -------------------------------------------------
+// cuboid_pnp_solver.py:157-171 switches to cv2.SOLVEPNP_EPNP below 6 points (third party: OpenCV calib3d epnp.cpp, whose
+// published algorithm is restated here: 4 control points from the PCA of the object points, barycentric coordinates,
+// the 2n x 12 system M, its 4 smallest right singular vectors, the three beta approximations, 5 Gauss-Newton steps each,
+// absolute orientation, best reprojection error).  With 4 or 5 points M has rank <= 2n < 12: the null space is 4- / 2-
+// dimensional BY CONSTRUCTION and any orthonormal basis of it is a valid set of "smallest singular vectors" -- OpenCV
+// takes whatever LAPACK returns, this code what the Jacobi sweep returns.  The two agree to 1e-12 on consistent 5-point
+// input; on 4 points and on noisy input both return a valid EPnP pose but not the same one (tests/test_pose_core_host.py
+// pins the consistent case against cv2 and bounds the reprojection error otherwise).
+CP_HDN bool lstsq_small(const double* A, const double* b, int m, int n, double* x) {      // min |A x - b|, n <= 5, via normal equations + pivoted elimination
+  double N[25], g[5];
+  for (int i = 0; i < n; ++i) {
+    g[i] = 0.0;
+    for (int r = 0; r < m; ++r) g[i] += A[r * n + i] * b[r];
+    for (int j = 0; j < n; ++j) {
+      double s = 0.0;
+      for (int r = 0; r < m; ++r) s += A[r * n + i] * A[r * n + j];
+      N[i * n + j] = s;
+    }
+  }
+  // Tikhonov floor keeps the rank-deficient approximations of the 4 / 5 point case finite (pinv-like behaviour)
+  double tr = 0.0;
+  for (int i = 0; i < n; ++i) tr += N[i * n + i];
+  for (int i = 0; i < n; ++i) N[i * n + i] += 1e-13 * tr + 1e-300;
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r)
+      if (fabs(N[r * n + c]) > fabs(N[piv * n + c])) piv = r;
+    if (N[piv * n + c] == 0.0) return false;
+    if (piv != c) {
+      for (int j = 0; j < n; ++j) {
+        const double t = N[c * n + j];
+        N[c * n + j] = N[piv * n + j];
+        N[piv * n + j] = t;
+      }
+      const double t = g[c];
+      g[c] = g[piv];
+      g[piv] = t;
+    }
+    for (int r = c + 1; r < n; ++r) {
+      const double f = N[r * n + c] / N[c * n + c];
+      for (int j = c; j < n; ++j) N[r * n + j] -= f * N[c * n + j];
+      g[r] -= f * g[c];
+    }
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = g[i];
+    for (int j = i + 1; j < n; ++j) s -= N[i * n + j] * x[j];
+    x[i] = s / N[i * n + i];
+  }
+  return true;
+}
+
+CP_HD double dot3(const double* p, const double* q) { return p[0] * q[0] + p[1] * q[1] + p[2] * q[2]; }
+
+// absolute orientation of the camera-frame points pcs against the object points X (epnp.cpp estimate_R_and_t):
+// R = U V^T of sum (pc - pc0)(pw - pw0)^T through the polar factor, det fixed by flipping the last row
+CP_HDN void epnp_rt(const double* X, const double* pcs, int n, double* R, double* t) {
+  double pc0[3] = {0, 0, 0}, pw0[3] = {0, 0, 0};
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < 3; ++k) {
+      pc0[k] += pcs[3 * i + k] / n;
+      pw0[k] += X[3 * i + k] / n;
+    }
+  double H[9];
+  for (int i = 0; i < 9; ++i) H[i] = 0.0;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < 3; ++j)
+      for (int k = 0; k < 3; ++k) H[j * 3 + k] += (pcs[3 * i + j] - pc0[j]) * (X[3 * i + k] - pw0[k]);
+  // U V^T = H (H^T H)^(-1/2): eigen-decomposition of the symmetric 3 x 3 H^T H
+  double S[9], E[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) S[i * 3 + j] = H[0 * 3 + i] * H[0 * 3 + j] + H[1 * 3 + i] * H[1 * 3 + j] + H[2 * 3 + i] * H[2 * 3 + j];
+  jacobi_eig<3>(S, E);
+  // order the eigenvalues descending; a (near-)zero smallest one (coplanar points) is completed by the cross product
+  int o[3] = {0, 1, 2};
+  for (int a = 0; a < 2; ++a)
+    for (int b = a + 1; b < 3; ++b)
+      if (S[o[b] * 3 + o[b]] > S[o[a] * 3 + o[a]]) {
+        const int tt = o[a];
+        o[a] = o[b];
+        o[b] = tt;
+      }
+  double Vc[3][3], Uc[3][3];      // columns
+  for (int c = 0; c < 3; ++c)
+    for (int k = 0; k < 3; ++k) Vc[c][k] = E[k * 3 + o[c]];
+  const double big = S[o[0] * 3 + o[0]];
+  for (int c = 0; c < 2; ++c) {
+    const double sv = sqrt(fmax(S[o[c] * 3 + o[c]], 0.0));
+    for (int k = 0; k < 3; ++k) Uc[c][k] = (H[k * 3] * Vc[c][0] + H[k * 3 + 1] * Vc[c][1] + H[k * 3 + 2] * Vc[c][2]) / (sv > 0 ? sv : 1.0);
+  }
+  const double s2 = sqrt(fmax(S[o[2] * 3 + o[2]], 0.0));
+  if (s2 > 1e-9 * sqrt(fmax(big, 1e-300))) {
+    for (int k = 0; k < 3; ++k) Uc[2][k] = (H[k * 3] * Vc[2][0] + H[k * 3 + 1] * Vc[2][1] + H[k * 3 + 2] * Vc[2][2]) / s2;
+  } else {
+    Uc[2][0] = Uc[0][1] * Uc[1][2] - Uc[0][2] * Uc[1][1];
+    Uc[2][1] = Uc[0][2] * Uc[1][0] - Uc[0][0] * Uc[1][2];
+    Uc[2][2] = Uc[0][0] * Uc[1][1] - Uc[0][1] * Uc[1][0];
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R[i * 3 + j] = Uc[0][i] * Vc[0][j] + Uc[1][i] * Vc[1][j] + Uc[2][i] * Vc[2][j];
+  if (mat3_det(R) < 0) {
+    R[6] = -R[6];
+    R[7] = -R[7];
+    R[8] = -R[8];
+  }
+  for (int k = 0; k < 3; ++k) t[k] = pc0[k] - (R[k * 3] * pw0[0] + R[k * 3 + 1] * pw0[1] + R[k * 3 + 2] * pw0[2]);
+}
+
+// X: n x 3 object points, uv: n x 2 pixels (4 <= n <= 16).  Returns the mean reprojection error (pixels) of the chosen pose.
+CP_HDN double epnp_solve(const double* X, const double* uv, int n, double fx, double fy, double cx, double cy, double* Rout,
+                         double* tout) {
+  // control points: centroid + principal directions scaled by sqrt(eigenvalue / n)
+  double cws[4][3];
+  for (int k = 0; k < 3; ++k) {
+    cws[0][k] = 0.0;
+    for (int i = 0; i < n; ++i) cws[0][k] += X[3 * i + k] / n;
+  }
+  double C[9], E[9];
+  for (int i = 0; i < 9; ++i) C[i] = 0.0;
+  for (int i = 0; i < n; ++i)
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) C[a * 3 + b] += (X[3 * i + a] - cws[0][a]) * (X[3 * i + b] - cws[0][b]);
+  jacobi_eig<3>(C, E);
+  int o[3] = {0, 1, 2};
+  for (int a = 0; a < 2; ++a)
+    for (int b = a + 1; b < 3; ++b)
+      if (C[o[b] * 3 + o[b]] > C[o[a] * 3 + o[a]]) {
+        const int tt = o[a];
+        o[a] = o[b];
+        o[b] = tt;
+      }
+  for (int i = 1; i < 4; ++i) {
+    const double k = sqrt(fmax(C[o[i - 1] * 3 + o[i - 1]], 0.0) / n);
+    for (int j = 0; j < 3; ++j) cws[i][j] = cws[0][j] + k * E[j * 3 + o[i - 1]];
+  }
+  // barycentric coordinates
+  double CC[9], CCit[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 1; j < 4; ++j) CC[3 * i + j - 1] = cws[j][i] - cws[0][i];
+  if (fabs(mat3_det(CC)) < 1e-300) return 1e300;      // coplanar object points: EPnP's general case does not apply
+  mat3_inv_t(CC, CCit);                               // CCit = (CC^-1)^T
+  double al[16][4];
+  for (int i = 0; i < n; ++i) {
+    const double d[3] = {X[3 * i] - cws[0][0], X[3 * i + 1] - cws[0][1], X[3 * i + 2] - cws[0][2]};
+    for (int j = 0; j < 3; ++j) al[i][1 + j] = CCit[0 * 3 + j] * d[0] + CCit[1 * 3 + j] * d[1] + CCit[2 * 3 + j] * d[2];
+    al[i][0] = 1.0 - al[i][1] - al[i][2] - al[i][3];
+  }
+  // M^T M (12 x 12) accumulated row pair by row pair
+  double MtM[144], V[144];
+  for (int i = 0; i < 144; ++i) MtM[i] = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double r1[12], r2[12];
+    for (int j = 0; j < 4; ++j) {
+      r1[3 * j] = al[i][j] * fx;
+      r1[3 * j + 1] = 0.0;
+      r1[3 * j + 2] = al[i][j] * (cx - uv[2 * i]);
+      r2[3 * j] = 0.0;
+      r2[3 * j + 1] = al[i][j] * fy;
+      r2[3 * j + 2] = al[i][j] * (cy - uv[2 * i + 1]);
+    }
+    for (int a = 0; a < 12; ++a)
+      for (int b = 0; b < 12; ++b) MtM[a * 12 + b] += r1[a] * r1[b] + r2[a] * r2[b];
+  }
+  jacobi_eig<12>(MtM, V);
+  int ord[12];
+  for (int i = 0; i < 12; ++i) ord[i] = i;
+  for (int a = 0; a < 4; ++a)                    // the four smallest eigenvalues, ascending
+    for (int b = a + 1; b < 12; ++b)
+      if (MtM[ord[b] * 12 + ord[b]] < MtM[ord[a] * 12 + ord[a]]) {
+        const int tt = ord[a];
+        ord[a] = ord[b];
+        ord[b] = tt;
+      }
+  double v[4][12];
+  for (int i = 0; i < 4; ++i)
+    for (int k = 0; k < 12; ++k) v[i][k] = V[k * 12 + ord[i]];
+  // L (6 x 10) and rho
+  double dv[4][6][3];
+  for (int i = 0; i < 4; ++i) {
+    int a = 0, b = 1;
+    for (int j = 0; j < 6; ++j) {
+      for (int k = 0; k < 3; ++k) dv[i][j][k] = v[i][3 * a + k] - v[i][3 * b + k];
+      if (++b > 3) {
+        ++a;
+        b = a + 1;
+      }
+    }
+  }
+  double L[60], rho[6];
+  for (int i = 0; i < 6; ++i) {
+    double* r = L + 10 * i;
+    r[0] = dot3(dv[0][i], dv[0][i]);
+    r[1] = 2 * dot3(dv[0][i], dv[1][i]);
+    r[2] = dot3(dv[1][i], dv[1][i]);
+    r[3] = 2 * dot3(dv[0][i], dv[2][i]);
+    r[4] = 2 * dot3(dv[1][i], dv[2][i]);
+    r[5] = dot3(dv[2][i], dv[2][i]);
+    r[6] = 2 * dot3(dv[0][i], dv[3][i]);
+    r[7] = 2 * dot3(dv[1][i], dv[3][i]);
+    r[8] = 2 * dot3(dv[2][i], dv[3][i]);
+    r[9] = dot3(dv[3][i], dv[3][i]);
+  }
+  {
+    const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
+    for (int i = 0; i < 6; ++i) {
+      double d = 0.0;
+      for (int k = 0; k < 3; ++k) d += (cws[pa[i]][k] - cws[pb[i]][k]) * (cws[pa[i]][k] - cws[pb[i]][k]);
+      rho[i] = d;
+    }
+  }
+  double best = 1e300;
+  for (int ap = 0; ap < 3; ++ap) {
+    double be[4] = {0, 0, 0, 0};
+    if (ap == 0) {            // betas ~ [B11 B12 B13 B14]
+      const int cols[4] = {0, 1, 3, 6};
+      double A4[24], b4[4];
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 4; ++j) A4[i * 4 + j] = L[10 * i + cols[j]];
+      if (!lstsq_small(A4, rho, 6, 4, b4)) continue;
+      if (b4[0] < 0) {
+        be[0] = sqrt(-b4[0]);
+        for (int j = 1; j < 4; ++j) be[j] = -b4[j] / be[0];
+      } else {
+        be[0] = sqrt(b4[0]);
+        for (int j = 1; j < 4; ++j) be[j] = b4[j] / be[0];
+      }
+    } else {                  // [B11 B12 B22] / [B11 B12 B22 B13 B23]
+      const int nc = ap == 1 ? 3 : 5;
+      double A5[30], b5[5];
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < nc; ++j) A5[i * nc + j] = L[10 * i + j];
+      if (!lstsq_small(A5, rho, 6, nc, b5)) continue;
+      if (b5[0] < 0) {
+        be[0] = sqrt(-b5[0]);
+        be[1] = b5[2] < 0 ? sqrt(-b5[2]) : 0.0;
+      } else {
+        be[0] = sqrt(b5[0]);
+        be[1] = b5[2] > 0 ? sqrt(b5[2]) : 0.0;
+      }
+      if (b5[1] < 0) be[0] = -be[0];
+      if (ap == 2) be[2] = b5[3] / be[0];
+    }
+    if (!(be[0] == be[0]) || be[0] == 0.0) continue;
+    for (int it = 0; it < 5; ++it) {          // Gauss-Newton on the six control-point distances
+      double A[24], b[6], dx[4];
+      for (int i = 0; i < 6; ++i) {
+        const double* r = L + 10 * i;
+        A[i * 4 + 0] = 2 * r[0] * be[0] + r[1] * be[1] + r[3] * be[2] + r[6] * be[3];
+        A[i * 4 + 1] = r[1] * be[0] + 2 * r[2] * be[1] + r[4] * be[2] + r[7] * be[3];
+        A[i * 4 + 2] = r[3] * be[0] + r[4] * be[1] + 2 * r[5] * be[2] + r[8] * be[3];
+        A[i * 4 + 3] = r[6] * be[0] + r[7] * be[1] + r[8] * be[2] + 2 * r[9] * be[3];
+        b[i] = rho[i] - (r[0] * be[0] * be[0] + r[1] * be[0] * be[1] + r[2] * be[1] * be[1] + r[3] * be[0] * be[2] +
+                         r[4] * be[1] * be[2] + r[5] * be[2] * be[2] + r[6] * be[0] * be[3] + r[7] * be[1] * be[3] +
+                         r[8] * be[2] * be[3] + r[9] * be[3] * be[3]);
+      }
+      if (!lstsq_small(A, b, 6, 4, dx)) break;
+      for (int j = 0; j < 4; ++j) be[j] += dx[j];
+    }
+    // control points in the camera frame, the points themselves, sign, absolute orientation
+    double ccs[4][3], pcs[48];
+    for (int j = 0; j < 4; ++j)
+      for (int k = 0; k < 3; ++k) ccs[j][k] = be[0] * v[0][3 * j + k] + be[1] * v[1][3 * j + k] + be[2] * v[2][3 * j + k] + be[3] * v[3][3 * j + k];
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < 3; ++k) pcs[3 * i + k] = al[i][0] * ccs[0][k] + al[i][1] * ccs[1][k] + al[i][2] * ccs[2][k] + al[i][3] * ccs[3][k];
+    if (pcs[2] < 0.0)
+      for (int i = 0; i < 3 * n; ++i) pcs[i] = -pcs[i];
+    double R[9], t[3];
+    epnp_rt(X, pcs, n, R, t);
+    double err = 0.0;
+    bool fin = true;
+    for (int i = 0; i < n; ++i) {
+      const double* x = X + 3 * i;
+      const double px = R[0] * x[0] + R[1] * x[1] + R[2] * x[2] + t[0];
+      const double py = R[3] * x[0] + R[4] * x[1] + R[5] * x[2] + t[1];
+      const double pz = R[6] * x[0] + R[7] * x[1] + R[8] * x[2] + t[2];
+      const double du = cx + fx * px / pz - uv[2 * i], dvv = cy + fy * py / pz - uv[2 * i + 1];
+      err += sqrt(du * du + dvv * dvv) / n;
+    }
+    fin = err == err;
+    if (fin && err < best) {
+      best = err;
+      for (int i = 0; i < 9; ++i) Rout[i] = R[i];
+      for (int i = 0; i < 3; ++i) tout[i] = t[i];
+    }
+  }
+  return best;
+}
+
 // solve_pnp + pnp_shell for one detection, in three steps so that the CUDA decode kernel can run the two heavy ones
 // (DLT eigen-solve, LM) warp-cooperatively (decode.cu) while host tests run the serial chain below.
 //   pts: n_in x 2 image points (n_in = 8 or 16; 3-D vertex of point i is V[i / (n_in/8)])
@@ -474,13 +770,30 @@ CP_HDN void pnp_finish(const double* V, const double* R, const double* t, double
   if (!(o->kpspnp[0] > 0 && o->kpspnp[0] < 1 && o->kpspnp[1] > 0 && o->kpspnp[1] < 1)) o->status = 2;
 }
 
+// 4 - 5 valid points: cv2.SOLVEPNP_EPNP (cuboid_pnp_solver.py:162-163), no iterative refinement
+CP_HDN void pnp_few_points(const double* V, const double* X, const double* uv, int n, const double* Kc, double width,
+                           double height, int visible_thresh, int opencv_return, PnPOut* o) {
+  double R[9], t[3];
+  const double err = epnp_solve(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t);
+  if (!(err < 1e299)) {
+    o->status = 5;  // CP_PNP_SOLVER_FAIL
+    return;
+  }
+  pnp_finish(V, R, t, reproj_cost(X, uv, n, R, t, Kc[0], Kc[4], Kc[2], Kc[5]), n, Kc, width, height, visible_thresh,
+             opencv_return, o);
+}
+
 CP_HDN void solve_and_shell(const double* pts, int n_in, const float* obj_scale, const double* Kc, double width,
                             double height, int visible_thresh, int opencv_return, PnPOut* o) {
   double V[24], X[48], uv[32];
   const int n = pnp_collect(pts, n_in, obj_scale, V, X, uv);
   o->n_pts = n;
   o->status = 4;  // CP_PNP_FEW_POINTS
-  if (n < 6) return;
+  if (n < 4) return;
+  if (n < 6) {
+    pnp_few_points(V, X, uv, n, Kc, width, height, visible_thresh, opencv_return, o);
+    return;
+  }
   double R[9], t[3];
   dlt_init(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t);
   const double cost = refine_lm(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t);
@@ -494,7 +807,11 @@ CP_HDN void solve_and_shell_v(const double* pts, int n_in, const double* V, cons
   const int n = pnp_collect_v(pts, n_in, V, X, uv);
   o->n_pts = n;
   o->status = 4;  // CP_PNP_FEW_POINTS
-  if (n < 6) return;
+  if (n < 4) return;
+  if (n < 6) {
+    pnp_few_points(V, X, uv, n, Kc, width, height, visible_thresh, opencv_return, o);
+    return;
+  }
   double R[9], t[3];
   dlt_init(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t);
   const double cost = refine_lm(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], R, t);

@@ -119,11 +119,12 @@ def _logit(p):
 
 
 def planted_heads(n_obj=3, seed=0, heads=None, out_h=128, out_w=128, down=4, cam=None,
-                  disagree_px=0.0, peak=0.95, sigma=1.5):
+                  disagree_px=0.0, peak=0.95, sigma=1.5, drop_joints=()):
     """One image worth of head logits with `n_obj` planted cuboids.
 
     Returns (heads_dict {name: fp32 [C,out_h,out_w]}, truth dict).  All values
-    are generated in float64 and rounded to fp32 once."""
+    are generated in float64 and rounded to fp32 once.  `drop_joints`: keypoint indices whose heat-map peak is NOT
+    planted (the decode then reports the -10000 sentinel for them in rep_mode 4: the 4 - 5 point EPnP path)."""
     heads = dict(heads or DEFAULT_HEADS)
     rng = np.random.default_rng(seed)
     if cam is None:
@@ -182,7 +183,7 @@ def planted_heads(n_obj=3, seed=0, heads=None, out_h=128, out_w=128, down=4, cam
             out["hps"][2 * j + 1, iy, ix] = ky[j] - iy + dxy[1]
             if "tracking_hp" in out:
                 out["tracking_hp"][2 * j:2 * j + 2, iy, ix] = rng.normal(0, 1.0, size=2)
-            if "hm_hp" in out:
+            if "hm_hp" in out and j not in drop_joints:
                 jx, jy = cells[j]
                 pj = (peak - 0.02 * j) * np.exp(-((xx - jx) ** 2 + (yy - jy) ** 2) / (2 * sigma * sigma))
                 out["hm_hp"][j] = np.maximum(out["hm_hp"][j], pj)

@@ -230,7 +230,7 @@ enum cp_pnp_status {
   CP_PNP_OK = 1,          /* pnp_shell returned a tuple -> goes into `boxes`                    */
   CP_PNP_INVISIBLE = 2,   /* pose stored in the result, visibility gate returned None (:59-79)  */
   CP_PNP_BEHIND = 3,      /* z < 0 (cuboid_pnp_solver.py:208-220)                               */
-  CP_PNP_FEW_POINTS = 4,  /* < 6 valid points (reference: <4 fails, 4-5 switch to EPNP)         */
+  CP_PNP_FEW_POINTS = 4,  /* < 4 valid points (cuboid_pnp_solver.py:157-160); 4-5 points are solved by EPnP   */
   CP_PNP_SOLVER_FAIL = 5
 };
 

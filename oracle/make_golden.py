@@ -48,6 +48,8 @@ DECODE_CASES = [
     ("decode_rep0_3obj", False, 0, 3, 1.0, 1, 31, "cup"),
     ("decode_rep4_2obj", False, 4, 2, 0.5, 1, 41, "shoe"),
     ("decode_track_rep1_3obj", True, 1, 3, 1.0, 2, 51, "chair"),
+    # rep_mode 4 with three keypoint peaks missing: kps carries the -10000 sentinel, 5 valid points -> cv2 SOLVEPNP_EPNP
+    ("decode_rep4_5pts_epnp", False, 4, 2, 0.0, 1, 61, "shoe", (1, 4, 6)),
 ]
 
 
@@ -155,16 +157,21 @@ def reference_pipeline(heads_b, opt, cam, width, height, c, s):
     return dets, (np.stack(recs) if recs else np.zeros((0, L.CP_POSE_RECORD)))
 
 
-def make_decode():
-    for name, trk, rep, nobj, dis, B, seed, cat in DECODE_CASES:
+def make_decode(only=None):
+    for case in DECODE_CASES:
+        name, trk, rep, nobj, dis, B, seed, cat = case[:8]
+        drop = tuple(case[8]) if len(case) > 8 else ()
+        if only and name not in only:
+            continue
         opt = ref_shims.make_opt("dla_34", tracking_task=trk, rep_mode=rep, c=cat)
         heads = synth.TRACKING_HEADS if trk else synth.DEFAULT_HEADS
-        hb, truths = synth.planted_batch(B, n_obj=nobj, seed=seed, heads=heads, disagree_px=dis)
+        hb, truths = synth.planted_batch(B, n_obj=nobj, seed=seed, heads=heads, disagree_px=dis, drop_joints=drop)
         cam = truths[0]["cam"]
         c = np.array([256., 256.], np.float32)
         s = 512.0
         out = {"tracking": int(trk), "rep_mode": rep, "n_obj": nobj, "disagree_px": dis, "batch": B, "seed": seed,
-               "category": cat, "vis_thresh": float(opt.vis_thresh), "cam": cam}
+               "category": cat, "vis_thresh": float(opt.vis_thresh), "cam": cam,
+               "drop_joints": np.array(drop, np.int64)}
         for b in range(B):
             dets, recs = reference_pipeline({k: v[b] for k, v in hb.items()}, opt, cam, 512, 512, c, s)
             for k, v in dets.items():
@@ -208,5 +215,5 @@ if __name__ == "__main__":
     if not only:
         make_dcn()
     make_net(only)
-    if not only:
-        make_decode()
+    if not only or any(n.startswith("decode_") for n in only):
+        make_decode(only)

@@ -15,6 +15,14 @@ distortion (OpenCV calib3d `findExtrinsicCameraParams2`):
   3. Levenberg-Marquardt on the 6-DoF reprojection error (pixels).
 The answer is the local least-squares minimum reached from the DLT start.
 
+With 4 or 5 valid points the reference passes `cv2.SOLVEPNP_EPNP` (cuboid_pnp_solver.py:162-163).  `epnp` restates the
+published algorithm of OpenCV's calib3d epnp.cpp (Lepetit, Moreno-Noguer, Fua 2009): control points from the PCA of the
+object points, barycentric coordinates, the 2n x 12 system and the 4 smallest singular vectors of M^T M, three beta
+approximations each refined by 5 Gauss-Newton steps, absolute orientation, smallest mean reprojection error.  M has
+rank <= 2n < 12 there, so its null space is degenerate by construction and its basis is whatever the SVD routine
+returns: pinned against cv2 on CONSISTENT 5-point input (1e-9); on 4 points or noisy input cv2 and this file return
+different, equally valid EPnP poses (tests/test_oracle_pnp.py reports the gap).
+
 Parity status: PINNED against cv2 4.13 (`tests/test_oracle_pnp.py` compares
 with `cv2.solvePnPGeneric` directly -- cv2 is part of the image on both the
 build container and the GPU box) and against the reference's own
@@ -35,7 +43,7 @@ ST_NOT_RUN = 0
 ST_OK = 1            # pnp_shell returned a tuple (goes into `boxes`)
 ST_INVISIBLE = 2     # pose written into the result dict, but a visibility gate returned None
 ST_BEHIND = 3        # z < 0 on the OpenCV tvec  (cuboid_pnp_solver.py:208-220)
-ST_FEW_POINTS = 4    # < 4 valid points, or 4-5 points (reference switches to EPNP; not restated)
+ST_FEW_POINTS = 4    # < 4 valid points (4-5 points: EPnP, restated in `epnp`)
 ST_SOLVER_FAIL = 5
 
 
@@ -200,6 +208,94 @@ def refine_lm(X, uv, Kc, R, t, max_iter=20):
     return R, t, cost
 
 
+def epnp(pws, us, Kc):
+    """cv2.solvePnP(..., flags=SOLVEPNP_EPNP) without distortion: (R, t, mean reprojection error in pixels)."""
+    pws = np.asarray(pws, np.float64)
+    us = np.asarray(us, np.float64)
+    n = len(pws)
+    fu, fv, uc, vc = Kc[0, 0], Kc[1, 1], Kc[0, 2], Kc[1, 2]
+    cws = np.zeros((4, 3))
+    cws[0] = pws.mean(0)
+    PW0 = pws - cws[0]
+    U, D, _ = np.linalg.svd(PW0.T @ PW0)
+    for i in range(1, 4):
+        cws[i] = cws[0] + np.sqrt(D[i - 1] / n) * U[:, i - 1]
+    CC = (cws[1:] - cws[0]).T
+    if abs(np.linalg.det(CC)) < 1e-300:
+        return None
+    CCi = np.linalg.inv(CC)
+    al = np.zeros((n, 4))
+    al[:, 1:] = (pws - cws[0]) @ CCi.T
+    al[:, 0] = 1 - al[:, 1:].sum(1)
+    M = np.zeros((2 * n, 12))
+    for j in range(4):
+        M[0::2, 3 * j] = al[:, j] * fu
+        M[0::2, 3 * j + 2] = al[:, j] * (uc - us[:, 0])
+        M[1::2, 3 * j + 1] = al[:, j] * fv
+        M[1::2, 3 * j + 2] = al[:, j] * (vc - us[:, 1])
+    U, D, _ = np.linalg.svd(M.T @ M)
+    v = [U[:, 11], U[:, 10], U[:, 9], U[:, 8]]
+    pairs = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
+    dv = np.array([[vi[3 * a:3 * a + 3] - vi[3 * b:3 * b + 3] for a, b in pairs] for vi in v])     # [4, 6, 3]
+    L = np.zeros((6, 10))
+    for i in range(6):
+        d = dv[:, i]
+        L[i] = [d[0] @ d[0], 2 * d[0] @ d[1], d[1] @ d[1], 2 * d[0] @ d[2], 2 * d[1] @ d[2], d[2] @ d[2],
+                2 * d[0] @ d[3], 2 * d[1] @ d[3], 2 * d[2] @ d[3], d[3] @ d[3]]
+    rho = np.array([((cws[a] - cws[b]) ** 2).sum() for a, b in pairs])
+    lsq = lambda A, b: np.linalg.lstsq(A, b, rcond=None)[0]      # noqa: E731
+
+    def start(ap):
+        be = np.zeros(4)
+        if ap == 0:
+            b4 = lsq(L[:, [0, 1, 3, 6]], rho)
+            be[0] = np.sqrt(abs(b4[0]))
+            be[1:] = (-b4[1:] if b4[0] < 0 else b4[1:]) / be[0]
+            return be
+        b = lsq(L[:, :3] if ap == 1 else L[:, :5], rho)
+        if b[0] < 0:
+            be[0], be[1] = np.sqrt(-b[0]), (np.sqrt(-b[2]) if b[2] < 0 else 0.0)
+        else:
+            be[0], be[1] = np.sqrt(b[0]), (np.sqrt(b[2]) if b[2] > 0 else 0.0)
+        if b[1] < 0:
+            be[0] = -be[0]
+        if ap == 2:
+            be[2] = b[3] / be[0]
+        return be
+
+    best = None
+    for ap in range(3):
+        be = start(ap)
+        if not np.isfinite(be).all() or be[0] == 0:
+            continue
+        for _ in range(5):
+            A = np.zeros((6, 4))
+            r = L
+            A[:, 0] = 2 * r[:, 0] * be[0] + r[:, 1] * be[1] + r[:, 3] * be[2] + r[:, 6] * be[3]
+            A[:, 1] = r[:, 1] * be[0] + 2 * r[:, 2] * be[1] + r[:, 4] * be[2] + r[:, 7] * be[3]
+            A[:, 2] = r[:, 3] * be[0] + r[:, 4] * be[1] + 2 * r[:, 5] * be[2] + r[:, 8] * be[3]
+            A[:, 3] = r[:, 6] * be[0] + r[:, 7] * be[1] + r[:, 8] * be[2] + 2 * r[:, 9] * be[3]
+            b = rho - (r[:, 0] * be[0] ** 2 + r[:, 1] * be[0] * be[1] + r[:, 2] * be[1] ** 2 + r[:, 3] * be[0] * be[2] +
+                       r[:, 4] * be[1] * be[2] + r[:, 5] * be[2] ** 2 + r[:, 6] * be[0] * be[3] + r[:, 7] * be[1] * be[3] +
+                       r[:, 8] * be[2] * be[3] + r[:, 9] * be[3] ** 2)
+            be = be + lsq(A, b)
+        ccs = sum(be[i] * v[i].reshape(4, 3) for i in range(4))
+        pcs = al @ ccs
+        if pcs[0, 2] < 0:
+            pcs = -pcs
+        pc0, pw0 = pcs.mean(0), pws.mean(0)
+        Uo, _, Vt = np.linalg.svd((pcs - pc0).T @ (pws - pw0))
+        R = Uo @ Vt
+        if np.linalg.det(R) < 0:
+            R[2] = -R[2]
+        t = pc0 - R @ pw0
+        P = pws @ R.T + t
+        err = np.sqrt((us[:, 0] - (uc + fu * P[:, 0] / P[:, 2])) ** 2 + (us[:, 1] - (vc + fv * P[:, 1] / P[:, 2])) ** 2).mean()
+        if np.isfinite(err) and (best is None or err < best[2]):
+            best = (R, t, err)
+    return best
+
+
 def solve_pnp(points2d, vertices, Kc, opencv_return=False):
     """cuboid_pnp_solver.py:91-239.  Returns dict(status, location, quaternion,
     projected_points[8,2], reproj_err, R_cv, t_cv)."""
@@ -213,12 +309,20 @@ def solve_pnp(points2d, vertices, Kc, opencv_return=False):
         o3.append(vertices[int(i // (n_in / 8))])
     out = {"status": ST_FEW_POINTS, "location": None, "quaternion": None,
            "projected_points": pts, "reproj_err": None, "n_pts": len(o2)}
-    if len(o2) < 6:
-        return out          # <4: reference fails; 4-5: reference uses EPNP (not restated)
+    if len(o2) < 4:
+        return out          # cuboid_pnp_solver.py:157-160
     o2 = np.array(o2)
     o3 = np.array(o3)
-    R, t = dlt_init(o3, o2, Kc)
-    R, t, cost = refine_lm(o3, o2, Kc, R, t)
+    if len(o2) < 6:         # :162-163 SOLVEPNP_EPNP
+        sol = epnp(o3, o2, np.asarray(Kc, np.float64))
+        if sol is None:
+            out["status"] = ST_SOLVER_FAIL
+            return out
+        R, t = sol[0], sol[1]
+        cost = float(((project(o3, R, t, Kc) - o2) ** 2).sum())
+    else:
+        R, t = dlt_init(o3, o2, Kc)
+        R, t, cost = refine_lm(o3, o2, Kc, R, t)
     if not np.all(np.isfinite(R)) or not np.all(np.isfinite(t)):
         out["status"] = ST_SOLVER_FAIL
         return out

@@ -14,7 +14,7 @@ from tests.util import DETS_KEYS, compare_records, decode_case_inputs, golden, o
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["decode_rep1_3obj", "decode_rep1_10obj_noisy", "decode_rep0_3obj", "decode_rep4_2obj",
+CASES = ["decode_rep1_3obj", "decode_rep1_10obj_noisy", "decode_rep0_3obj", "decode_rep4_2obj", "decode_rep4_5pts_epnp",
          "decode_track_rep1_3obj"]
 C512 = np.array([256., 256.], np.float32)
 

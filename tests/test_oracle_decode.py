@@ -11,7 +11,7 @@ from centerpose_b200 import synth
 from oracle import decode_ref, pnp_ref
 from tests.util import DETS_KEYS, compare_records, decode_case_inputs, golden, oracle_records
 
-CASES = ["decode_rep1_3obj", "decode_rep1_10obj_noisy", "decode_rep0_3obj", "decode_rep4_2obj",
+CASES = ["decode_rep1_3obj", "decode_rep1_10obj_noisy", "decode_rep0_3obj", "decode_rep4_2obj", "decode_rep4_5pts_epnp",
          "decode_track_rep1_3obj"]
 
 

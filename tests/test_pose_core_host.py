@@ -66,9 +66,9 @@ def test_pnp_failure_paths(pose_host):
     cam = synth.default_camera(512, 512)
     scale = np.array([1.0, 1.0, 1.0], np.float32)
     pts = np.full((16, 2), -10000.0)
-    pts[:10:2] = np.random.default_rng(1).uniform(100, 400, (5, 2))    # only 5 valid points
+    pts[:6:2] = np.random.default_rng(1).uniform(100, 400, (3, 2))     # only 3 valid points
     st, npt, _ = _solve(pose_host, pts, scale, cam, 512, 512)
-    assert st == 4 and npt == 5                                        # reference would switch to EPNP
+    assert st == 4 and npt == 3                                        # < 4 points: cuboid_pnp_solver.py:157-160
     # a cuboid far outside the image: pose found, visibility gate rejects it (cuboid_pnp_shell.py:59-79)
     V = pnp_ref.cuboid_vertices(scale)
     uv = pnp_ref.project(V, np.eye(3), np.array([6.0, 0.0, 4.0]), cam)
@@ -76,6 +76,66 @@ def test_pnp_failure_paths(pose_host):
     assert st == 2
     st3, _, _ = _solve(pose_host, np.repeat(uv, 2, 0), scale, cam, 512, 512, 0, 0)     # bike/laptop/shoe: only centre gate
     assert st3 == 2
+
+
+def _epnp_case(rng, n, noise):
+    import cv2
+    K = np.array([[663.0, 0, 300.3], [0, 663.0, 395.0], [0, 0, 1.0]])
+    scale = rng.uniform(0.3, 2, 3).astype(np.float32)
+    V = pnp_ref.cuboid_vertices(scale)
+    rv = rng.normal(size=3) * 0.7
+    t = np.array([rng.uniform(-.3, .3), rng.uniform(-.3, .3), rng.uniform(2, 4)])
+    R = cv2.Rodrigues(rv)[0]
+    idx = np.sort(rng.choice(8, n, replace=False))
+    uv = pnp_ref.project(V, R, t, K) + rng.normal(size=(8, 2)) * noise
+    pts = np.full((8, 2), -10000.0)
+    pts[idx] = uv[idx]
+    ok, rvs, tvs, _ = cv2.solvePnPGeneric(V[idx].reshape(-1, 1, 3), uv[idx].reshape(-1, 1, 2), K, np.zeros(4),
+                                          flags=cv2.SOLVEPNP_EPNP)
+    return K, scale, V, idx, uv, pts, cv2.Rodrigues(rvs[0])[0], tvs[0].reshape(3)
+
+
+def _reproj(V, idx, uv, R, t, K):
+    return np.sqrt(((pnp_ref.project(V[idx], R, t, K) - uv[idx]) ** 2).sum(1)).mean()
+
+
+def test_epnp_five_consistent_points_match_cv2(pose_host):
+    """4 - 5 valid points take EPnP (cuboid_pnp_solver.py:162-163).  On consistent 5-point input the pose is unique and
+    both the C++ (host build of the device code) and the numpy restatement agree with cv2.SOLVEPNP_EPNP to 1e-8."""
+    pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    n_ok = 0
+    for _ in range(20):
+        K, scale, V, idx, uv, pts, Rc, tc = _epnp_case(rng, 5, 0.0)
+        if tc[2] < 0 or _reproj(V, idx, uv, Rc, tc, K) > 1e-6:
+            continue                                           # cv2 itself did not find the exact pose
+        st, npt, out = _solve(pose_host, pts, scale, K, 600, 800, 0, 1)
+        assert npt == 5 and st in (1, 2)
+        Ro = pnp_ref.quat_to_mat(out[3:7])
+        assert np.abs(Ro - Rc).max() <= 1e-8 and np.abs(out[0:3] - tc).max() <= 1e-8
+        sol = pnp_ref.epnp(V[idx], uv[idx], K)
+        assert np.abs(sol[0] - Rc).max() <= 1e-8 and np.abs(sol[1] - tc).max() <= 1e-8
+        n_ok += 1
+    assert n_ok >= 15
+
+
+def test_epnp_degenerate_cases_stay_valid(pose_host):
+    """4 points / noisy points: M has a structurally degenerate null space, cv2 (LAPACK basis) and this code (Jacobi basis)
+    return different valid EPnP poses.  Bound: a pose is produced and its reprojection error is of the order of cv2's."""
+    pytest.importorskip("cv2")
+    rng = np.random.default_rng(4)
+    ratios = []
+    for trial in range(40):
+        n, noise = (5, 1.0) if trial % 2 else (4, 0.5)
+        K, scale, V, idx, uv, pts, Rc, tc = _epnp_case(rng, n, noise)
+        st, npt, out = _solve(pose_host, pts, scale, K, 600, 800, 0, 1)
+        assert npt == n and st in (1, 2, 3, 5)
+        if st in (1, 2) and tc[2] > 0:
+            ours = _reproj(V, idx, uv, pnp_ref.quat_to_mat(out[3:7]), out[0:3], K)
+            ratios.append((ours + 0.5) / (_reproj(V, idx, uv, Rc, tc, K) + 0.5))
+    print("EPnP reprojection error vs cv2 (ratio of error + 0.5 px): median %.2f  90th pct %.2f  n %d"
+          % (np.median(ratios), np.percentile(ratios, 90), len(ratios)))
+    assert len(ratios) >= 25 and np.median(ratios) <= 1.5
 
 
 def test_soft_nms_matches_oracle(pose_host):

@@ -55,8 +55,9 @@ def dcn_case_inputs(g):
 def decode_case_inputs(g):
     from centerpose_b200 import synth
     heads = synth.TRACKING_HEADS if int(g["tracking"]) else synth.DEFAULT_HEADS
+    drop = tuple(int(v) for v in g["drop_joints"]) if "drop_joints" in g.files else ()
     hb, truths = synth.planted_batch(int(g["batch"]), n_obj=int(g["n_obj"]), seed=int(g["seed"]), heads=heads,
-                                     disagree_px=float(g["disagree_px"]))
+                                     disagree_px=float(g["disagree_px"]), drop_joints=drop)
     return hb, truths
 
 

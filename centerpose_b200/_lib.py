@@ -78,7 +78,7 @@ class CpDecodeParams(ctypes.Structure):
         ("rep_mode", ctypes.c_int32), ("use_moments", ctypes.c_int32), ("nms", ctypes.c_int32),
         ("visible_thresh", ctypes.c_int32), ("opencv_return", ctypes.c_int32),
         ("apply_sigmoid", ctypes.c_int32), ("use_pnp", ctypes.c_int32),
-        ("vis_thresh", ctypes.c_float), ("balance", ctypes.c_float), ("reserved", ctypes.c_float),
+        ("vis_thresh", ctypes.c_float), ("balance", ctypes.c_float), ("modern_bool_semantics", ctypes.c_int32),
     ]
 
 

@@ -162,7 +162,7 @@ __device__ __forceinline__ void fused_part_smem(const float (&sums)[128], float 
 struct IssueCtx {
   uint32_t idesc, dhi, rowu, a_lo_u, b_lo_u, sub_u, a0_u, a_stage_u, b0_u, b_stage_u, tmem_base, buf_cols, bn;
   uint32_t bar_a, bar_a_empty, bar_b_full, bar_b_empty, bar_p_full, bar_p_empty;
-  uint32_t tap_u[9];
+  uint32_t tap_u[2];
   int group, KB, SA, SB, nslab, cluster;
   uint16_t cmask;
 };
@@ -171,21 +171,31 @@ struct IssueState {
   uint32_t pa = 0, pb = 0, pe = 0;        // pe bit b: phase of p_empty[b]
 };
 
-template <bool X3, int MS, int TAPS, int KS>
-__device__ __forceinline__ void issue_tile(const IssueCtx& c, IssueState& st, uint32_t tap0, bool sub1_live) {
+template <bool X3, int MSL, int TAPS, int KS>
+__device__ __forceinline__ void issue_tile(const IssueCtx& c, IssueState& st, uint32_t tap0) {
   int kbi = 0, gk = 0;                     // K-block index inside the tile (slab-major, tap-minor) / inside its group
   for (int s = 0; s < c.nslab; ++s) {
     mbar_wait(c.bar_a + 8u * (uint32_t)st.sa, st.pa);
     tc_fence_after();
     const uint32_t a_slab = c.a0_u + (uint32_t)st.sa * c.a_stage_u + tap0;
-#pragma unroll
+    // the tap loop stays ROLLED (one copy of the body in the instruction cache); the descriptor offset of tap (ky, kx) =
+    // (ky Wt + kx) rows is stepped: + 1 row inside a kernel row, + (Wt - 2) rows at its end
+    uint32_t tap_off = 0;
+    int kx = 0;
+#pragma unroll 1
     for (int tap = 0; tap < TAPS; ++tap, ++kbi) {
       const bool first = X3 ? (gk == 0) : (kbi == 0);
       if (first)                           // new accumulation group / tile: the epilogue must have drained this TMEM buffer
         mbar_wait(c.bar_p_empty + 8u * (uint32_t)st.buf, ((st.pe >> st.buf) & 1u) ^ 1u);
       mbar_wait(c.bar_b_full + 8u * (uint32_t)st.sb, st.pb);
       tc_fence_after();
-      const uint32_t da = a_slab + c.tap_u[tap];
+      const uint32_t da = a_slab + tap_off;
+      if (++kx == 3) {
+        kx = 0;
+        tap_off += c.tap_u[1];       // (Wt - 2) rows
+      } else {
+        tap_off += c.tap_u[0];       // 1 row
+      }
       const uint32_t db = c.b0_u + (uint32_t)st.sb * c.b_stage_u;
       const uint32_t d_tmem = c.tmem_base + (uint32_t)st.buf * c.buf_cols;
       const bool last = X3 ? (gk == c.group - 1 || kbi == c.KB - 1) : (kbi == c.KB - 1);
@@ -197,8 +207,7 @@ __device__ __forceinline__ void issue_tile(const IssueCtx& c, IssueState& st, ui
           for (int ks = 0; ks < KS; ++ks) {
             const uint32_t acc = (first && ks == 0) ? 0u : 1u;
 #pragma unroll
-            for (int sub = 0; sub < MS; ++sub) {          // rows [128 sub, 128 sub + 128) of the tile
-              if (sub > 0 && !sub1_live) continue;        // no output position in the second half (image tail)
+            for (int sub = 0; sub < MSL; ++sub) {         // rows [128 sub, 128 sub + 128) of the tile
               const uint32_t das = da + (uint32_t)sub * c.sub_u + 2u * ks;
               const uint32_t dt = d_tmem + (uint32_t)sub * c.bn;
               umma_tf32_lohi(dt, das + c.a_lo_u, db + 2u * ks, c.dhi, c.idesc, acc);
@@ -208,11 +217,9 @@ __device__ __forceinline__ void issue_tile(const IssueCtx& c, IssueState& st, ui
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
-            for (int sub = 0; sub < MS; ++sub) {
-              if (sub > 0 && !sub1_live) continue;
+            for (int sub = 0; sub < MSL; ++sub)
               umma_tf32_lohi(d_tmem + (uint32_t)sub * c.bn, da + (uint32_t)sub * c.sub_u + 2u * ks, db + 2u * ks, c.dhi,
                              c.idesc, 1u);
-            }
           }
         } else {
 #pragma unroll
@@ -242,6 +249,33 @@ __device__ __forceinline__ void issue_tile(const IssueCtx& c, IssueState& st, ui
       st.sa = 0;
       st.pa ^= 1u;
     }
+  }
+}
+
+struct IssueTiles {            // 32-bit tile arithmetic (the launcher rejects > 2^31 tiles): no 64-bit divisions per tile
+  int cluster_id, num_clusters, tph, total_tiles;
+  int n_tiles, rank;
+};
+
+template <bool X3, int MS, int TAPS, int KS>
+__device__ __forceinline__ void issue_all_tiles(const TmaConvParams& p, const IssueCtx& c, const IssueTiles& tl) {
+  IssueState st;
+  const int Wt = p.Wt, HWt = p.H * p.Wt;
+  const long long total_pos = (long long)p.B * p.H * p.W;
+  for (int it = 0;; ++it) {
+    const int unit = it / tl.tph;
+    const int tile = (tl.cluster_id + unit * tl.num_clusters) * tl.tph + (it - unit * tl.tph);
+    if (tile >= tl.total_tiles) break;
+    bool live;
+    const TileGeo g = decode_tile(p, tile, tl.n_tiles, tl.rank, &live);
+    const uint32_t tap0 = (TAPS == 9) ? (uint32_t)(g.g0 - 1 - g.r_lo * Wt) * c.rowu : 0u;
+    // x3: small feature maps end inside the first 128 rows of their last tile; the second accumulator is then skipped.
+    // MSL = sub-tiles with output positions: a compile-time count, so the unrolled MMA list carries no predication
+    const bool sub1_live = (TAPS == 9) ? (g.g0 + TM_BM < HWt) : (g.pos0 + TM_BM < total_pos);
+    if (MS == 2 && sub1_live)
+      issue_tile<X3, MS, TAPS, KS>(c, st, tap0);
+    else
+      issue_tile<X3, 1, TAPS, KS>(c, st, tap0);
   }
 }
 
@@ -315,7 +349,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   if (warp < 4) {
   if (X3) {
     if (FUSE)
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     else
       asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
   }
@@ -417,27 +451,21 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     c.bar_p_empty = smem_u32(&ctl->p_empty[0]);
     c.cluster = p.cluster;
     c.cmask = cmask;
-    for (int t = 0; t < 9; ++t) c.tap_u[t] = (p.k == 3) ? (uint32_t)((t / 3) * p.Wt + (t % 3)) * c.rowu : 0u;
-    IssueState st;
-    const int Wt = p.Wt, HWt = p.H * p.Wt, k = p.k;
-    const long long total_pos = (long long)p.B * p.H * p.W;
-    for (long long it = 0, tile = tile_at(0); tile < total_tiles; tile = tile_at(++it)) {
-      bool live;
-      const TileGeo g = decode_tile(p, tile, n_tiles, rank, &live);
-      const uint32_t tap0 = (k == 3) ? (uint32_t)(g.g0 - 1 - g.r_lo * Wt) * c.rowu : 0u;
-      // x3: small feature maps end inside the first 128 rows of their last tile; the second accumulator is then skipped
-      const bool sub1_live = (k == 3) ? (g.g0 + TM_BM < HWt) : (g.pos0 + TM_BM < total_pos);
-      if (k == 3) {
-        if (kslices == 2)
-          issue_tile<X3, MS, 9, 2>(c, st, tap0, sub1_live);
-        else
-          issue_tile<X3, MS, 9, 4>(c, st, tap0, sub1_live);
-      } else {
-        if (kslices == 2)
-          issue_tile<X3, MS, 1, 2>(c, st, tap0, sub1_live);
-        else
-          issue_tile<X3, MS, 1, 4>(c, st, tap0, sub1_live);
-      }
+    c.tap_u[0] = c.rowu;                                   // step between taps of one kernel row
+    c.tap_u[1] = (uint32_t)(p.Wt - 2) * c.rowu;            // step from the last tap of a kernel row to the next row
+    // (taps, K slices) are chosen ONCE, outside the tile loop: each combination owns its copy of the loop, so the
+    // register allocation of the hot path is not shared between variants
+    const IssueTiles tl{(int)cluster_id, (int)num_clusters, (int)tph, (int)total_tiles, n_tiles, rank};
+    if (p.k == 3) {
+      if (kslices == 2)
+        issue_all_tiles<X3, MS, 9, 2>(p, c, tl);
+      else
+        issue_all_tiles<X3, MS, 9, 4>(p, c, tl);
+    } else {
+      if (kslices == 2)
+        issue_all_tiles<X3, MS, 1, 2>(p, c, tl);
+      else
+        issue_all_tiles<X3, MS, 1, 4>(p, c, tl);
     }
   } else if (X3 && FUSE) {
     // ===================== warp 3: 1x1 weights + 3x3 bias of every tile -> shared memory (x3 fused heads) =====================
@@ -951,6 +979,7 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.cluster = cluster;
   const long long m_groups = ((long long)m_tiles + cluster - 1) / cluster;
   q.total_tiles = m_groups * (p.CoutPad / q.BN);
+  if (q.total_tiles >= (1ll << 31)) return fail(CP_ERR_INVALID, "conv_tma: too many tiles");
   int num_sms = 0;
   if (int rc = device_sm_count(&num_sms)) return rc;
   long long nclusters = num_sms / cluster;

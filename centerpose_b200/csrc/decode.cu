@@ -326,7 +326,8 @@ __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
     d[CP_D_KPS + 2 * j] = kx;
     d[CP_D_KPS + 2 * j + 1] = ky;
     const bool ok2 = (sx > __fmul_rn(0.8f, l)) && (sx < __fmul_rn(1.2f, r)) && (sy > __fmul_rn(0.8f, t)) &&
-                     (sy < __fmul_rn(1.2f, bt)) && (ss > th) && (best < __fmul_rn(size, 0.5f)) && (c_score[k] > th);
+                     (sy < __fmul_rn(1.2f, bt)) && (ss > th) && (best < __fmul_rn(size, 0.5f)) && (c_score[k] > th) &&
+                     !P.modern_bool_semantics;      // torch >= 1.2: `mask_2 == 7` on a bool sum is never true
     float mean_x = SENT, mean_y = SENT, std_x = SENT, std_y = SENT, height = SENT;
     if ((P.rep_mode == 1 || P.rep_mode == 2) && ok2 && !(sx == SENT || sy == SENT)) {
       const float* hp = a.h.hm_hp + ((size_t)b * J + j) * HW;

@@ -28,13 +28,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the device
+// bounded wait: a protocol bug traps (reported as a CUDA launch failure) instead of hanging the device.  The slow path
+// is call-free (a printf here costs a real ABI call: ~20 extra instructions and the spill code of every live register at
+// each of the ~10 wait sites of a hot loop); build with -DCP_MBAR_DEBUG to get the diagnostic message back.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
+#ifdef CP_MBAR_DEBUG
       printf("tcgen05 kernel: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+#endif
       __trap();
     }
   }

@@ -45,6 +45,8 @@ def decode_params(opt=None, **over):
     p.vis_thresh = float(g("vis_thresh", 0.3))
     bal = g("balance_coefficient", None)
     p.balance = float(bal[cat]) if isinstance(bal, dict) else float(bal if bal is not None else 2.0)
+    # 0 = the reference as pinned (torch==1.1.0 integer adds), 1 = the reference on torch >= 1.2
+    p.modern_bool_semantics = int(bool(g("modern_bool_semantics", False)))
     if "use_moments" in over:
         p.use_moments = int(over["use_moments"])
     if "visible_thresh" in over:

@@ -174,7 +174,11 @@ typedef struct cp_decode_params {
   int32_t use_pnp;         /* opt.use_pnp                                                  */
   float vis_thresh;        /* opt.vis_thresh (0.3)                                         */
   float balance;           /* opt.balance_coefficient[opt.c] (2)                           */
-  float reserved;
+  int32_t modern_bool_semantics; /* 0 (default): the pinned torch==1.1.0 meaning of models/decode.py:183-188, where the
+                            * seven comparison results are ADDED as integers and `mask_2 == 7` = "all seven gates hold".
+                            * 1: what the unmodified reference computes on torch >= 1.2 (bool + bool is a logical OR, so
+                            * `== 7` is never true): the heat-map keypoint representation is never used, kps_heatmap_* stay
+                            * at the -10000 sentinel and the PnP sees the 8 displacement points only.                 */
 } cp_decode_params;
 
 /* meta: device fp64 [batch, CP_META_DOUBLES] per image:

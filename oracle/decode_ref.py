@@ -34,7 +34,7 @@ class DecodeParams(object):
     """The subset of the reference `opt` the decode path reads."""
 
     def __init__(self, K=100, rep_mode=1, use_moments=False, balance=2.0, vis_thresh=0.3,
-                 nms=True, category="chair", num_scales=1):
+                 nms=True, category="chair", num_scales=1, modern_bool=False):
         self.K = K
         self.rep_mode = rep_mode
         # opt.tracking_task or opt.refined_Kalman or rep_mode == 2  (decode.py:222)
@@ -44,6 +44,9 @@ class DecodeParams(object):
         self.nms = nms
         self.category = category
         self.num_scales = num_scales
+        # False: torch==1.1.0 (pinned) semantics of `mask_2 == 7` (decode.py:183-188); True: torch >= 1.2, where the sum of
+        # bools is a logical OR and the comparison with 7 is never true
+        self.modern_bool = bool(modern_bool)
 
 
 def sigmoid_f32(x):
@@ -204,6 +207,8 @@ def decode(heads, prm):
             kps_out[:, 2 * j + 1] = np.where(bad, kps[:, 2 * j + 1], sy)
         ok2 = (sx > F32(0.8) * l) & (sx < F32(1.2) * r) & (sy > F32(0.8) * t) & (sy < F32(1.2) * b) \
             & (ss > th) & (md < size * F32(0.5)) & (scores > th)
+        if prm.modern_bool:
+            ok2 = np.zeros_like(ok2)
         if prm.rep_mode in (1, 2):
             data = hm_hp_copy[j]
             for k in range(K):

@@ -50,6 +50,9 @@ DECODE_CASES = [
     ("decode_track_rep1_3obj", True, 1, 3, 1.0, 2, 51, "chair"),
     # rep_mode 4 with three keypoint peaks missing: kps carries the -10000 sentinel, 5 valid points -> cv2 SOLVEPNP_EPNP
     ("decode_rep4_5pts_epnp", False, 4, 2, 0.0, 1, 61, "shoe", (1, 4, 6)),
+    # the same scene as decode_rep1_3obj evaluated by the UNMODIFIED reference on the torch of this image (>= 1.2), i.e.
+    # WITHOUT ref_shims.legacy_bool_arith: `mask_2 == 7` is all-False there (cp_decode_params.modern_bool_semantics = 1)
+    ("decode_rep1_3obj_modern_torch", False, 1, 3, 0.0, 2, 11, "chair", (), True),
 ]
 
 
@@ -113,7 +116,7 @@ def result_to_record(d, k_src=-1):
     return r
 
 
-def reference_pipeline(heads_b, opt, cam, width, height, c, s):
+def reference_pipeline(heads_b, opt, cam, width, height, c, s, legacy=True):
     """Runs the reference's process()-after-network, post_process, merge_outputs and the
     PnP loop of run() on one image's head tensors."""
     from lib.models.decode import object_pose_decode
@@ -123,7 +126,8 @@ def reference_pipeline(heads_b, opt, cam, width, height, c, s):
     T = {k: torch.from_numpy(v[None].copy()) for k, v in heads_b.items()}
     T["hm"] = T["hm"].sigmoid_()
     T["hm_hp"] = T["hm_hp"].sigmoid_()
-    with ref_shims.legacy_bool_arith():
+    import contextlib
+    with (ref_shims.legacy_bool_arith() if legacy else contextlib.nullcontext()):
         dets = object_pose_decode(
             T["hm"], T["hps"], wh=T["wh"], kps_displacement_std=T.get("hps_uncertainty"), obj_scale=T["scale"],
             obj_scale_uncertainty=T.get("scale_uncertainty"), reg=T["reg"], hm_hp=T["hm_hp"],
@@ -161,6 +165,7 @@ def make_decode(only=None):
     for case in DECODE_CASES:
         name, trk, rep, nobj, dis, B, seed, cat = case[:8]
         drop = tuple(case[8]) if len(case) > 8 else ()
+        modern = bool(case[9]) if len(case) > 9 else False
         if only and name not in only:
             continue
         opt = ref_shims.make_opt("dla_34", tracking_task=trk, rep_mode=rep, c=cat)
@@ -171,9 +176,9 @@ def make_decode(only=None):
         s = 512.0
         out = {"tracking": int(trk), "rep_mode": rep, "n_obj": nobj, "disagree_px": dis, "batch": B, "seed": seed,
                "category": cat, "vis_thresh": float(opt.vis_thresh), "cam": cam,
-               "drop_joints": np.array(drop, np.int64)}
+               "drop_joints": np.array(drop, np.int64), "modern_bool": int(modern)}
         for b in range(B):
-            dets, recs = reference_pipeline({k: v[b] for k, v in hb.items()}, opt, cam, 512, 512, c, s)
+            dets, recs = reference_pipeline({k: v[b] for k, v in hb.items()}, opt, cam, 512, 512, c, s, legacy=not modern)
             for k, v in dets.items():
                 out["dets%d_%s" % (b, k)] = v[0]
             out["records%d" % b] = recs

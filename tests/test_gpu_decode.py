@@ -15,7 +15,7 @@ from tests.util import DETS_KEYS, compare_records, decode_case_inputs, golden, o
 pytestmark = pytest.mark.gpu
 
 CASES = ["decode_rep1_3obj", "decode_rep1_10obj_noisy", "decode_rep0_3obj", "decode_rep4_2obj", "decode_rep4_5pts_epnp",
-         "decode_track_rep1_3obj"]
+         "decode_track_rep1_3obj", "decode_rep1_3obj_modern_torch"]
 C512 = np.array([256., 256.], np.float32)
 
 
@@ -33,7 +33,9 @@ def _run(hb, cam, rep_mode, tracking, category, c=C512, s=512.0, w=512, h=512, *
 def test_matches_reference_golden(name, cplib):
     g = golden(name)
     hb, truths = decode_case_inputs(g)
-    dets, poses, n_valid = _run(hb, g["cam"], int(g["rep_mode"]), bool(int(g["tracking"])), str(g["category"]))
+    modern = bool(int(g["modern_bool"])) if "modern_bool" in g.files else False
+    dets, poses, n_valid = _run(hb, g["cam"], int(g["rep_mode"]), bool(int(g["tracking"])), str(g["category"]),
+                                modern_bool_semantics=modern)
     dd = dets_to_dict(dets)
     for b in range(int(g["batch"])):
         valid = g["dets%d_scores" % b][:, 0] > 0.05

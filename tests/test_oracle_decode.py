@@ -12,12 +12,13 @@ from oracle import decode_ref, pnp_ref
 from tests.util import DETS_KEYS, compare_records, decode_case_inputs, golden, oracle_records
 
 CASES = ["decode_rep1_3obj", "decode_rep1_10obj_noisy", "decode_rep0_3obj", "decode_rep4_2obj", "decode_rep4_5pts_epnp",
-         "decode_track_rep1_3obj"]
+         "decode_track_rep1_3obj", "decode_rep1_3obj_modern_torch"]
 
 
 def _params(g):
     return decode_ref.DecodeParams(K=100, rep_mode=int(g["rep_mode"]), use_moments=bool(int(g["tracking"])),
-                                   balance=2.0, vis_thresh=float(g["vis_thresh"]), category=str(g["category"]))
+                                   balance=2.0, vis_thresh=float(g["vis_thresh"]), category=str(g["category"]),
+                                   modern_bool=bool(int(g["modern_bool"])) if "modern_bool" in g.files else False)
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -69,6 +69,12 @@ struct TmaConvParams {
   int x3;             // 3-term split (fp32-equivalent): hi/lo slabs + hi/lo weight tiles, BN <= 128
   int group;          // x3: K blocks per TMEM accumulation group (promoted into fp32 registers after each group)
   const unsigned char* wtiles;
+  // split-K (x3, not fused): the K loop of a tile is dealt to `ksplit` CTAs (slab-aligned ranges of `sps` slabs); every
+  // CTA stores its promoted partial sums, the last one to arrive (per sub-tile counter) adds them in split order
+  // (deterministic) and runs the epilogue.  ksplit == 1: off.  Tile index = (m, n) tile * ksplit + split.
+  int ksplit, sps;
+  float* part;          // [mn tiles][ksplit][tile_m][BN] fp32
+  int* counters;        // [mn tiles * 2], zero between launches (the last CTA resets its counter)
   // fused per-head 1x1 (see IgemmParams): tph = N tiles per head, processed back to back by the same CTA
   int fuse, tph;
   const float* fuse_w[16];
@@ -254,7 +260,7 @@ __device__ __forceinline__ void issue_tile(const IssueCtx& c, IssueState& st, ui
 
 struct IssueTiles {            // 32-bit tile arithmetic (the launcher rejects > 2^31 tiles): no 64-bit divisions per tile
   int cluster_id, num_clusters, tph, total_tiles;
-  int n_tiles, rank;
+  int n_tiles, rank, ksplit;
 };
 
 template <bool X3, int MS, int TAPS, int KS>
@@ -267,7 +273,7 @@ __device__ __forceinline__ void issue_all_tiles(const TmaConvParams& p, const Is
     const int tile = (tl.cluster_id + unit * tl.num_clusters) * tl.tph + (it - unit * tl.tph);
     if (tile >= tl.total_tiles) break;
     bool live;
-    const TileGeo g = decode_tile(p, tile, tl.n_tiles, tl.rank, &live);
+    const TileGeo g = decode_tile(p, tile / tl.ksplit, tl.n_tiles, tl.rank, &live);
     const uint32_t tap0 = (TAPS == 9) ? (uint32_t)(g.g0 - 1 - g.r_lo * Wt) * c.rowu : 0u;
     // x3: small feature maps end inside the first 128 rows of their last tile; the second accumulator is then skipped.
     // MSL = sub-tiles with output positions: a compile-time count, so the unrolled MMA list carries no predication
@@ -286,6 +292,7 @@ template <bool X3, bool FUSE>
 __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmaConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   TmaCtl* ctl = reinterpret_cast<TmaCtl*>(smem);
+  __shared__ int s_last[2];                        // split-K: "this CTA finishes the tile" per M sub-tile
   // x3 computes TWO 128-row M sub-tiles per weight tile (tile = 256 positions): the weight stream from L2, the measured
   // limiter, is halved per MMA.  The sub-tiles are two accumulators side by side in TMEM and two sets of epilogue warps.
   constexpr int MS = X3 ? 2 : 1;
@@ -301,7 +308,10 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   const int n_tiles = p.CoutPad / p.BN;
   const int taps = p.k * p.k;
   const int nslab = p.Cin / p.cslab;
-  const int KB = nslab * taps;
+  const int KS_SPLIT = p.ksplit;                   // split-K factor (1 = off)
+  const int sps = p.sps;                           // slabs per split
+  const int KB = sps * taps;                       // K blocks THIS CTA runs per tile
+  const int KB_all = nslab * taps;                 // K blocks of the whole contraction (weight-tile addressing)
   const long long total_tiles = p.total_tiles;
   const int rank = (p.cluster > 1) ? (int)cluster_ctarank() : 0;
   const long long cluster_id = blockIdx.x / p.cluster;
@@ -360,8 +370,9 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
       uint32_t phase = 0;
       for (long long it = 0, tile = tile_at(0); tile < total_tiles; tile = tile_at(++it)) {
         bool live;
-        const TileGeo g = decode_tile(p, tile, n_tiles, rank, &live);
-        for (int s = 0; s < nslab; ++s) {
+        const TileGeo g = decode_tile(p, tile / KS_SPLIT, n_tiles, rank, &live);
+        const int s_begin = (int)(tile % KS_SPLIT) * sps;
+        for (int s = s_begin; s < s_begin + sps; ++s) {
           int src = 0, cb = 0;
           while (src + 1 < p.nsrc && s * p.cslab >= cb + p.srcC[src]) {
             cb += p.srcC[src];
@@ -389,8 +400,8 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
       int stage = 0;
       uint32_t phase = 0;
       for (long long it = 0, tile = tile_at(0); tile < total_tiles; tile = tile_at(++it)) {
-        const int n_tile = (int)(tile % n_tiles);       // identical for all CTAs of the cluster
-        const unsigned char* wsrc = p.wtiles + (size_t)n_tile * KB * btile_bytes;
+        const int n_tile = (int)((tile / KS_SPLIT) % n_tiles);       // identical for all CTAs of the cluster
+        const unsigned char* wsrc = p.wtiles + ((size_t)n_tile * KB_all + (size_t)(tile % KS_SPLIT) * KB) * btile_bytes;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(smem_u32(&ctl->b_empty[stage]), phase ^ 1u);
           const uint32_t bar = smem_u32(&ctl->b_full[stage]);
@@ -442,7 +453,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     c.KB = KB;
     c.SA = p.SA;
     c.SB = p.SB;
-    c.nslab = nslab;
+    c.nslab = sps;
     c.bar_a = smem_u32(X3 ? &ctl->a_split[0] : &ctl->a_full[0]);
     c.bar_a_empty = smem_u32(&ctl->a_empty[0]);
     c.bar_b_full = smem_u32(&ctl->b_full[0]);
@@ -455,7 +466,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     c.tap_u[1] = (uint32_t)(p.Wt - 2) * c.rowu;            // step from the last tap of a kernel row to the next row
     // (taps, K slices) are chosen ONCE, outside the tile loop: each combination owns its copy of the loop, so the
     // register allocation of the hot path is not shared between variants
-    const IssueTiles tl{(int)cluster_id, (int)num_clusters, (int)tph, (int)total_tiles, n_tiles, rank};
+    const IssueTiles tl{(int)cluster_id, (int)num_clusters, (int)tph, (int)total_tiles, n_tiles, rank, KS_SPLIT};
     if (p.k == 3) {
       if (kslices == 2)
         issue_all_tiles<X3, MS, 9, 2>(p, c, tl);
@@ -492,7 +503,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     uint32_t phase = 0;
     const uint32_t nchunk = p.slab_bytes >> 4;
     for (long long it = 0, tile = tile_at(0); tile < total_tiles; tile = tile_at(++it)) {
-      for (int s = 0; s < nslab; ++s) {
+      for (int s = 0; s < sps; ++s) {
         mbar_wait(smem_u32(&ctl->a_full[stage]), phase);
         const uint32_t hi = slabs0 + (uint32_t)stage * a_stage;
         const uint32_t lo = hi + p.slab_stride;
@@ -557,7 +568,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     for (int j = 0; j < (FUSE ? 16 : 1); ++j) acc2[j] = 0.f;
     for (long long it = 0, tile = tile_at(0); tile < total_tiles; tile = tile_at(++it)) {
       bool live;
-        const TileGeo g = decode_tile(p, tile, n_tiles, rank, &live);
+      const TileGeo g = decode_tile(p, tile / KS_SPLIT, n_tiles, rank, &live);
       bool valid;
       int n, oy, ox;
       if (p.k == 3) {
@@ -610,6 +621,39 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
           mbar_arrive(smem_u32(&ctl->p_empty[buf]));
           pf ^= 1u << buf;
           buf ^= 1;
+        }
+        if (!FUSE && KS_SPLIT > 1) {
+          // split-K: park the partial sums of this K range; the LAST CTA of the (tile, sub-tile) adds all ranges in
+          // split order -- a fixed summation order, so the result does not depend on which CTA arrives last
+          const long long mn = tile / KS_SPLIT;
+          const int ks = (int)(tile % KS_SPLIT);
+          float* mine = p.part + (((size_t)mn * KS_SPLIT + ks) * p.tile_m + i) * p.BN;
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c * 4 < p.BN)
+              __stcg(reinterpret_cast<float4*>(mine) + c, make_float4(sums[(X3 ? c * 4 : 0)], sums[(X3 ? c * 4 + 1 : 0)],
+                                                                   sums[(X3 ? c * 4 + 2 : 0)], sums[(X3 ? c * 4 + 3 : 0)]));
+          __threadfence();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + sub) : "memory");            // the four warps of this sub-tile
+          if ((tid & 127) == 0) s_last[sub] = (atomicAdd(p.counters + mn * 2 + sub, 1) == KS_SPLIT - 1) ? 1 : 0;
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + sub) : "memory");
+          if (!s_last[sub]) continue;                                             // another CTA finishes this tile
+          __threadfence();
+          if ((tid & 127) == 0) p.counters[mn * 2 + sub] = 0;                      // ready for the next launch
+#pragma unroll
+          for (int j = 0; j < (X3 ? 128 : 1); ++j) sums[j] = 0.f;
+          for (int q = 0; q < KS_SPLIT; ++q) {
+            const float4* src = reinterpret_cast<const float4*>(p.part + (((size_t)mn * KS_SPLIT + q) * p.tile_m + i) * p.BN);
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (c * 4 < p.BN) {
+                const float4 v = __ldcg(src + c);
+                sums[(X3 ? c * 4 : 0)] += v.x;
+                sums[(X3 ? c * 4 + 1 : 0)] += v.y;
+                sums[(X3 ? c * 4 + 2 : 0)] += v.z;
+                sums[(X3 ? c * 4 + 3 : 0)] += v.w;
+              }
+          }
         }
         if (FUSE) {
           // hidden = relu(conv3x3 + bias) never leaves the SM: multiply it with this head's 1x1 weights right here.
@@ -904,6 +948,11 @@ int tma_conv_encode(const IgemmParams& p, int Bmax, int x3, void* maps_out) {
   return CP_OK;
 }
 
+static int num_sms_hint() {
+  int n = 0;
+  return device_sm_count(&n) == CP_OK ? n : 148;
+}
+
 int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, int x3, cudaStream_t stream) {
   if (!p.wgt_umma) return fail(CP_ERR_INVALID, "conv_tma: weight tiles missing");
   TmaConvParams q;
@@ -972,6 +1021,10 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
     configured.here(slot) = true;
   }
   q.m_tiles = (long long)m_tiles;
+  q.ksplit = 1;
+  q.sps = q.Cin / q.cslab;
+  q.part = p.splitk_ws;
+  q.counters = p.splitk_counters;
   int cluster = 1;     // measured: multicast at cluster sizes 2/4 does not cut L2 traffic on this part and couples the CTAs
   if (const char* e = getenv("CP_TMA_CLUSTER")) cluster = atoi(e);
   if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 1;
@@ -979,6 +1032,22 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.cluster = cluster;
   const long long m_groups = ((long long)m_tiles + cluster - 1) / cluster;
   q.total_tiles = m_groups * (p.CoutPad / q.BN);
+  // split-K (tf32x3, plain epilogue): small feature maps give a persistent kernel fewer tiles than SMs while every tile
+  // walks a long serial K loop (level5 at batch 1: 8 tiles x 144 K blocks).  Deal slab-aligned K ranges to more CTAs.
+  if (x3 && !q.fuse && cluster == 1 && p.splitk_ws && p.splitk_counters && !getenv("CP_NO_SPLITK")) {
+    const int nslab = q.Cin / q.cslab;
+    const long long mn = q.total_tiles;
+    int S = 1;
+    for (int cand = 2; cand <= nslab; ++cand)
+      if (nslab % cand == 0 && mn * cand <= num_sms_hint() && mn * 2 <= kSplitkMaxTiles &&
+          (size_t)mn * cand * q.tile_m * q.BN <= p.splitk_ws_floats)
+        S = cand;
+    if (S > 1) {
+      q.ksplit = S;
+      q.sps = nslab / S;
+      q.total_tiles = mn * S;
+    }
+  }
   if (q.total_tiles >= (1ll << 31)) return fail(CP_ERR_INVALID, "conv_tma: too many tiles");
   int num_sms = 0;
   if (int rc = device_sm_count(&num_sms)) return rc;

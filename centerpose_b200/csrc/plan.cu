@@ -122,6 +122,8 @@ struct cp_plan {
   bool no_umma = false;          // CP_NO_UMMA=1: ops the TMA kernels do not take stay on the fp32 CUDA-core kernel (diagnostics)
   unsigned char* umma_wts = nullptr;
   size_t umma_bytes = 0;
+  float* splitk_ws = nullptr;      // conv_tma split-K partial sums (kSplitkWsFloats) + arrival counters
+  int* splitk_counters = nullptr;
 };
 
 namespace cp {
@@ -670,6 +672,11 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
   CP_CUDA_CHECK(cudaMemset(P->wts, 0, P->w_floats * sizeof(float)));
   CP_CUDA_CHECK(cudaMalloc(&P->gn_stats, sizeof(double) * (size_t)P->B * 64 * 2));
   if (P->umma_bytes) CP_CUDA_CHECK(cudaMalloc(&P->umma_wts, P->umma_bytes));
+  if (P->prec == 1) {
+    CP_CUDA_CHECK(cudaMalloc(&P->splitk_ws, kSplitkWsFloats * sizeof(float)));
+    CP_CUDA_CHECK(cudaMalloc(&P->splitk_counters, kSplitkMaxTiles * sizeof(int)));
+    CP_CUDA_CHECK(cudaMemset(P->splitk_counters, 0, kSplitkMaxTiles * sizeof(int)));
+  }
   for (auto& op : P->ops) {
     if (!op.use_dcn_tma) continue;
     IgemmParams q{};
@@ -718,6 +725,8 @@ int cp_plan_destroy(cp_plan* P) {
   cudaFree(P->wts);
   cudaFree(P->gn_stats);
   if (P->umma_wts) cudaFree(P->umma_wts);
+  if (P->splitk_ws) cudaFree(P->splitk_ws);
+  if (P->splitk_counters) cudaFree(P->splitk_counters);
   if (P->decode_ws) cudaFree(P->decode_ws);
   delete P;
   return CP_OK;
@@ -884,6 +893,9 @@ static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* 
           if ((rc = launch_dcn_tma(p, mp, P->prec == 1, P->prec == 2, s))) return rc;
         } else if (op.use_tma) {
           p.wgt_umma = P->umma_wts + op.umma_off;
+          p.splitk_ws = P->splitk_ws;
+          p.splitk_ws_floats = P->splitk_ws ? kSplitkWsFloats : 0;
+          p.splitk_counters = P->splitk_counters;
           const unsigned char* mp = (const unsigned char*)(((uintptr_t)op.tma_maps.data() + 63) & ~(uintptr_t)63);
           if ((rc = launch_conv_tma(p, mp, P->prec == 2, P->prec == 1, s))) return rc;
         } else if (op.use_umma) {

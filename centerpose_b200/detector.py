@@ -109,6 +109,7 @@ class ObjectPoseDetector(object):
         if opt.gpus[0] < 0:
             raise RuntimeError("centerpose_b200 runs on a CUDA device only (--gpus -1 is the reference's CPU path)")
         opt.device = torch.device("cuda")
+        self.opt = opt
         print("Creating model...")
         self.model = model if model is not None else create_model(opt.arch, opt.heads, opt.head_conv, opt)
         if getattr(opt, "load_model", ""):

@@ -86,22 +86,31 @@ def test_512_b1_matches_reference_golden(prec, cplib):
 
 @pytest.mark.parametrize("prec", ["tf32x3", "tf32"])
 def test_512_frame17_of_b32(prec, cplib):
-    """(ii) frame 17 of a 32-frame batch (the benched batch) == the same frame alone (bit-identical: frames are
-    independent) and matches the CPU oracle on that frame."""
+    """(ii) frames are independent: inside the benched batch of 32 a frame's heads do not depend on its
+    neighbours or its slot (bit-identical when the same frame sits in slot 3 or 17 of two different batches); the same
+    frame ALONE agrees to fp32 round-off only, because at batch 1 the plan deals the K loop of the small levels to
+    several CTAs (split-K: a different, still fixed, summation order); and frame 17 matches the CPU oracle."""
     from oracle import net_ref
     m, opt, sd = _model(12, prec)
     frames = synth.synthetic_frames(32, 512, 512, seed=4242)
     x = torch.from_numpy(synth.normalize_frames(frames))
     full = m(x.cuda())[-1]
+    perm = list(range(32))
+    perm[3], perm[17] = perm[17], perm[3]
+    other = torch.from_numpy(synth.normalize_frames(synth.synthetic_frames(32, 512, 512, seed=777)))
+    other[3] = x[17]
+    moved = m(other.cuda())[-1]
+    again = m(x.cuda())[-1]
     one = m(x[17:18].contiguous().cuda())[-1]
-    last = m(x[31:32].contiguous().cuda())[-1]
     for h in opt.heads:
-        assert torch.equal(full[h][17:18], one[h]), "frame 17 of the batch differs from the frame alone: " + h
-        assert torch.equal(full[h][31:32], last[h]), "the last frame of the batch differs from the frame alone: " + h
+        assert torch.equal(full[h], again[h]), "the plan is not re-entrant: " + h
+        assert torch.equal(full[h][17], moved[h][3]), "a frame's heads depend on its batch neighbours / slot: " + h
+        d = (full[h][17:18] - one[h]).abs().max().item() / one[h].abs().max().item()
+        assert d <= 2e-5, "frame 17 of the batch vs the frame alone: %s %.2e" % (h, d)
     want = net_ref.forward(x[17:18], sd, opt.heads, "dla_34")
     for h in opt.heads:
         w = want[h].numpy()
-        e = np.abs(one[h].cpu().numpy() - w).max() / np.abs(w).max()
+        e = np.abs(full[h][17:18].cpu().numpy() - w).max() / np.abs(w).max()
         print("512x512 b32[17] %-7s %-10s gpu-vs-oracle %.2e" % (prec, h, e))
         assert e <= TOL_512[prec], (h, e)
 

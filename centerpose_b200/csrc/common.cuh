@@ -11,6 +11,7 @@ namespace cp {
 
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
+extern thread_local long long g_launch_counter;      // kernels launched by this thread (every CP_LAUNCH_CHECK)
 
 #define CP_CUDA_CHECK(expr)                                                              \
   do {                                                                                   \
@@ -24,6 +25,7 @@ int fail(int code, const std::string& msg);
     cudaError_t _e = cudaGetLastError();                                                 \
     if (_e != cudaSuccess)                                                               \
       return ::cp::fail(CP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(_e));  \
+    ++::cp::g_launch_counter;                                                            \
   } while (0)
 
 // ---------------------------------------------------------------------------
@@ -66,10 +68,9 @@ struct IgemmParams {
   // conv_tma only: the per-head 1x1 convolutions fused into the epilogue of the merged heads 3x3 conv.  Head h owns the
   // output columns [h * fuse_hidden, (h + 1) * fuse_hidden); its 1x1 weights are [fuse_hidden][16] fp32 (rows = hidden
   // channel, 16 padded outputs), bias [16], output NCHW [B, fuse_cout[h], Hout, Wout].  fuse_n == 0: not fused.
-  // conv_tma split-K workspace (plan-owned; null = no split-K): partial sums + per-tile arrival counters (kept zero)
+  // conv_tma split-K workspace (plan-owned; null = no split-K): partial sums
   float* splitk_ws;
   size_t splitk_ws_floats;
-  int* splitk_counters;
   int fuse_n, fuse_hidden;
   const float* fuse_w[16];
   const float* fuse_b[16];
@@ -134,7 +135,6 @@ int tma_conv_encode(const IgemmParams& p, int Bmax, int x3, void* maps_out /* 4 
 int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, int x3, cudaStream_t stream);
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
-constexpr int kSplitkMaxTiles = 4096;            // counters: 2 per (m, n) tile
 constexpr size_t kSplitkWsFloats = (size_t)160 * 256 * 128;     // >= (#SMs) tile-splits of 256 positions x 128 columns
 
 // Launch attributes (cudaFuncSetAttribute) and the SM count are properties of the CURRENT DEVICE, not of the calling

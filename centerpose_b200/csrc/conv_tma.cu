@@ -70,11 +70,10 @@ struct TmaConvParams {
   int group;          // x3: K blocks per TMEM accumulation group (promoted into fp32 registers after each group)
   const unsigned char* wtiles;
   // split-K (x3, not fused): the K loop of a tile is dealt to `ksplit` CTAs (slab-aligned ranges of `sps` slabs); every
-  // CTA stores its promoted partial sums, the last one to arrive (per sub-tile counter) adds them in split order
-  // (deterministic) and runs the epilogue.  ksplit == 1: off.  Tile index = (m, n) tile * ksplit + split.
+  // CTA stores its promoted partial sums and conv_tma_splitk_finish adds them in split order (deterministic) and runs
+  // the epilogue.  ksplit == 1: off.  Tile index = (m, n) tile * ksplit + split.
   int ksplit, sps;
-  float* part;          // [mn tiles][ksplit][tile_m][BN] fp32
-  int* counters;        // [mn tiles * 2], zero between launches (the last CTA resets its counter)
+  float* part;          // [mn tiles][ksplit][BN / 4][tile_m] float4
   // fused per-head 1x1 (see IgemmParams): tph = N tiles per head, processed back to back by the same CTA
   int fuse, tph;
   const float* fuse_w[16];
@@ -93,6 +92,7 @@ struct TmaCtl {
   unsigned long long w2_full, w2_empty;      // x3 fused heads: 1x1 weights + 3x3 bias of the current tile in shared memory
   uint32_t tmem_base;
 };
+static_assert(sizeof(TmaCtl) <= 512, "control block");
 
 // x3 fused heads: [128 hidden][16] fp32 1x1 weights of the tile's (head, part) followed by the 128 biases of the 3x3 conv
 constexpr uint32_t TM_W2_BYTES = 128u * 16u * 4u;
@@ -292,7 +292,6 @@ template <bool X3, bool FUSE>
 __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmaConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   TmaCtl* ctl = reinterpret_cast<TmaCtl*>(smem);
-  __shared__ int s_last[2];                        // split-K: "this CTA finishes the tile" per M sub-tile
   // x3 computes TWO 128-row M sub-tiles per weight tile (tile = 256 positions): the weight stream from L2, the measured
   // limiter, is halved per MMA.  The sub-tiles are two accumulators side by side in TMEM and two sets of epilogue warps.
   constexpr int MS = X3 ? 2 : 1;
@@ -623,37 +622,19 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
           buf ^= 1;
         }
         if (!FUSE && KS_SPLIT > 1) {
-          // split-K: park the partial sums of this K range; the LAST CTA of the (tile, sub-tile) adds all ranges in
-          // split order -- a fixed summation order, so the result does not depend on which CTA arrives last
+          // split-K: park the partial sums of this K range, [mn tile][split][float4 column group][row] so that the 32
+          // lanes of a warp (32 consecutive rows) write one 512 B run; conv_tma_splitk_finish adds the ranges in split
+          // order (a fixed summation order) and runs the epilogue
           const long long mn = tile / KS_SPLIT;
           const int ks = (int)(tile % KS_SPLIT);
-          float* mine = p.part + (((size_t)mn * KS_SPLIT + ks) * p.tile_m + i) * p.BN;
+          const int G = p.BN >> 2;
+          float4* mine = reinterpret_cast<float4*>(p.part) + ((size_t)mn * KS_SPLIT + ks) * G * p.tile_m + i;
 #pragma unroll
           for (int c = 0; c < 32; ++c)
-            if (c * 4 < p.BN)
-              __stcg(reinterpret_cast<float4*>(mine) + c, make_float4(sums[(X3 ? c * 4 : 0)], sums[(X3 ? c * 4 + 1 : 0)],
-                                                                   sums[(X3 ? c * 4 + 2 : 0)], sums[(X3 ? c * 4 + 3 : 0)]));
-          __threadfence();
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + sub) : "memory");            // the four warps of this sub-tile
-          if ((tid & 127) == 0) s_last[sub] = (atomicAdd(p.counters + mn * 2 + sub, 1) == KS_SPLIT - 1) ? 1 : 0;
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + sub) : "memory");
-          if (!s_last[sub]) continue;                                             // another CTA finishes this tile
-          __threadfence();
-          if ((tid & 127) == 0) p.counters[mn * 2 + sub] = 0;                      // ready for the next launch
-#pragma unroll
-          for (int j = 0; j < (X3 ? 128 : 1); ++j) sums[j] = 0.f;
-          for (int q = 0; q < KS_SPLIT; ++q) {
-            const float4* src = reinterpret_cast<const float4*>(p.part + (((size_t)mn * KS_SPLIT + q) * p.tile_m + i) * p.BN);
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (c * 4 < p.BN) {
-                const float4 v = __ldcg(src + c);
-                sums[(X3 ? c * 4 : 0)] += v.x;
-                sums[(X3 ? c * 4 + 1 : 0)] += v.y;
-                sums[(X3 ? c * 4 + 2 : 0)] += v.z;
-                sums[(X3 ? c * 4 + 3 : 0)] += v.w;
-              }
-          }
+            if (c < G)
+              __stcg(mine + (size_t)c * p.tile_m, make_float4(sums[(X3 ? c * 4 : 0)], sums[(X3 ? c * 4 + 1 : 0)],
+                                                              sums[(X3 ? c * 4 + 2 : 0)], sums[(X3 ? c * 4 + 3 : 0)]));
+          continue;
         }
         if (FUSE) {
           // hidden = relu(conv3x3 + bias) never leaves the SM: multiply it with this head's 1x1 weights right here.
@@ -815,6 +796,74 @@ EncodeTiledFn get_encode() {
 }
 
 }  // namespace
+
+// split-K, second half: one thread per (output position, 4 channels) adds the `ksplit` partial sums in split order and
+// applies the epilogue.  Reads are coalesced (row-fastest layout); the whole grid works, not one CTA per tile.
+__global__ void __launch_bounds__(256) conv_tma_splitk_finish(const __grid_constant__ TmaConvParams p, long long mn_tiles) {
+  const int G = p.BN >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= mn_tiles * G * p.tile_m) return;
+  const int i = (int)(idx % p.tile_m);
+  const int c4 = (int)((idx / p.tile_m) % G);
+  const long long mn = idx / ((long long)p.tile_m * G);
+  const float4* src = reinterpret_cast<const float4*>(p.part) + ((size_t)mn * p.ksplit * G + c4) * p.tile_m + i;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int q = 0; q < p.ksplit; ++q) {
+    const float4 v = __ldcg(src + (size_t)q * G * p.tile_m);
+    a.x += v.x;
+    a.y += v.y;
+    a.z += v.z;
+    a.w += v.w;
+  }
+  bool live;
+  const TileGeo g = decode_tile(p, mn, p.CoutPad / p.BN, 0, &live);
+  bool valid;
+  int n, oy, ox;
+  if (p.k == 3) {
+    const int gg = g.g0 + i;
+    oy = gg / p.Wt;
+    const int xp = gg - oy * p.Wt;
+    ox = xp - 1;
+    n = g.img;
+    valid = live && (oy < p.H) && (xp >= 1) && (xp <= p.W);
+  } else {
+    const long long pix = g.pos0 + i;
+    valid = live && pix < (long long)p.B * p.H * p.W;
+    const long long pp = valid ? pix : 0;
+    ox = (int)(pp % p.W);
+    const long long t = pp / p.W;
+    oy = (int)(t % p.H);
+    n = (int)(t / p.H);
+  }
+  if (!valid) return;
+  const size_t m = ((size_t)n * p.H + oy) * p.W + ox;
+  const int col0 = g.n_tile * p.BN + c4 * 4;
+  const int col_end = min(p.Cout, (g.n_tile + 1) * p.BN);
+  float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool in = col0 + j < col_end;
+    if (col0 + j < p.CoutPad) v[j] += __ldg(p.bias + col0 + j);
+    if (p.residual && in && !p.res_after_relu) v[j] += __ldg(p.residual + m * p.resStride + col0 + j);
+    if (p.relu) v[j] = fmaxf(v[j], 0.f);
+    if (p.residual && in && p.res_after_relu) v[j] += __ldg(p.residual + m * p.resStride + col0 + j);
+    if (p.round_tf32) v[j] = tf32_round(v[j]);
+  }
+  if (p.out_nchw) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (col0 + j < col_end) p.out[(((size_t)n * p.Cout + col0 + j) * p.H + oy) * p.W + ox] = v[j];
+  } else {
+    float* o = p.out + m * p.outStride + col0;
+    if (col0 + 3 < col_end) {
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (col0 + j < col_end) o[j] = v[j];
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------- host side
 // Channels per activation slab.  32 (128-byte rows) by default; 16 (64-byte rows, SWIZZLE_64B) when Cin is not a
@@ -1024,7 +1073,6 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.ksplit = 1;
   q.sps = q.Cin / q.cslab;
   q.part = p.splitk_ws;
-  q.counters = p.splitk_counters;
   int cluster = 1;     // measured: multicast at cluster sizes 2/4 does not cut L2 traffic on this part and couples the CTAs
   if (const char* e = getenv("CP_TMA_CLUSTER")) cluster = atoi(e);
   if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 1;
@@ -1034,12 +1082,13 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.total_tiles = m_groups * (p.CoutPad / q.BN);
   // split-K (tf32x3, plain epilogue): small feature maps give a persistent kernel fewer tiles than SMs while every tile
   // walks a long serial K loop (level5 at batch 1: 8 tiles x 144 K blocks).  Deal slab-aligned K ranges to more CTAs.
-  if (x3 && !q.fuse && cluster == 1 && p.splitk_ws && p.splitk_counters && !getenv("CP_NO_SPLITK")) {
+  const char* ks_off = getenv("CP_NO_SPLITK");        // "1": no split-K anywhere, "conv": not here, "dcn": not in dcn_tma
+  if (x3 && !q.fuse && cluster == 1 && p.splitk_ws && !(ks_off && (ks_off[0] == '1' || ks_off[0] == 'c'))) {
     const int nslab = q.Cin / q.cslab;
     const long long mn = q.total_tiles;
     int S = 1;
     for (int cand = 2; cand <= nslab; ++cand)
-      if (nslab % cand == 0 && mn * cand <= num_sms_hint() && mn * 2 <= kSplitkMaxTiles &&
+      if (nslab % cand == 0 && mn * cand <= num_sms_hint() &&
           (size_t)mn * cand * q.tile_m * q.BN <= p.splitk_ws_floats)
         S = cand;
     if (S > 1) {
@@ -1067,6 +1116,12 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   cfg.numAttrs = 1;
   CP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, q));
   CP_LAUNCH_CHECK("conv_tma_kernel");
+  if (q.ksplit > 1) {
+    const long long mn = q.total_tiles / q.ksplit;
+    const long long threads = mn * (q.BN / 4) * q.tile_m;
+    conv_tma_splitk_finish<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(q, mn);
+    CP_LAUNCH_CHECK("conv_tma_splitk_finish");
+  }
   return CP_OK;
 }
 

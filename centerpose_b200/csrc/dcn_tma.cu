@@ -63,6 +63,10 @@ struct DcnTmaParams {
   float* out;
   int outStride, out_nchw, round_tf32;
   const unsigned char* wtiles;
+  // split-K (small maps: fewer tiles than SMs): tile = (m, n) tile * ksplit + split; a split walks `sps` slabs, stores its
+  // partial sums to `part` ([mn tile][split][BN / 4][128 rows] float4) and dcn_tma_splitk_finish runs the epilogue
+  int ksplit, sps;
+  float* part;
 };
 
 struct DcnCtl {
@@ -132,8 +136,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = p.CoutPad / p.BN;
-  const int nslab = p.Cin / DT_CS;
+  const int nslab = p.sps;                           // slabs one tile walks (all of them unless split-K)
   const int KB = nslab * 9;
+  const int KB_all = (p.Cin / DT_CS) * 9;
+  const int KS_SPLIT = p.ksplit;
   const long long total_tiles = p.total_tiles;
 
   if (tid == 0) {
@@ -172,7 +178,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const long long m_tile = tile / n_tiles;
+        const long long m_tile = (tile / KS_SPLIT) / n_tiles;
+        const int s0 = (int)(tile % KS_SPLIT) * nslab;
         const int img = (int)(m_tile / p.tiles_per_image);
         const int pt = (int)(m_tile - (long long)img * p.tiles_per_image);
         const int y0 = (pt / p.tiles_x) * DT_PH, x0 = (pt % p.tiles_x) * DT_PW;
@@ -180,7 +187,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
           mbar_wait(smem_u32(&ctl->s_empty[stage]), phase ^ 1u);
           const uint32_t bar = smem_u32(&ctl->s_full[stage]);
           mbar_arrive_expect_tx(bar, DT_SLAB_BYTES);
-          tma_load_4d(slabs0 + (uint32_t)stage * DT_SLAB_BYTES, &p.amap, s * DT_CS, x0 - DT_HALO, y0 - DT_HALO, img, bar);
+          tma_load_4d(slabs0 + (uint32_t)stage * DT_SLAB_BYTES, &p.amap, (s0 + s) * DT_CS, x0 - DT_HALO, y0 - DT_HALO, img,
+                      bar);
           if (++stage == 2) {
             stage = 0;
             phase ^= 1u;
@@ -195,8 +203,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = (int)(tile % n_tiles);
-        const unsigned char* wsrc = p.wtiles + (size_t)n_tile * KB * btile_bytes;
+        const int n_tile = (int)((tile / KS_SPLIT) % n_tiles);
+        const unsigned char* wsrc = p.wtiles + ((size_t)n_tile * KB_all + (size_t)(tile % KS_SPLIT) * KB) * btile_bytes;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(smem_u32(&ctl->b_empty[stage]), phase ^ 1u);
           const uint32_t bar = smem_u32(&ctl->b_full[stage]);
@@ -284,7 +292,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
     uint32_t ps = 0, pc = 0;
     uint32_t cnt = 0;                      // K blocks this half has produced; stage = 2 half + (cnt & 1)
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const long long m_tile = tile / n_tiles;
+      const long long m_tile = (tile / KS_SPLIT) / n_tiles;
+      const int s0 = (int)(tile % KS_SPLIT) * nslab;
       const int img = (int)(m_tile / p.tiles_per_image);
       mbar_wait(smem_u32(&ctl->c_full[cb]), pc);
       const uint32_t crow = coef0 + (uint32_t)cb * DT_COEF_BYTES + (uint32_t)row * 144u;
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
             }
           } else {      // corner rows outside the staged slab: same arithmetic from global memory
             const int hl = (int)((pk >> 7) & 127u), wl = (int)(pk & 127u);
-            const float* g = gimg + ((size_t)hl * p.W + wl) * p.srcStride + s * DT_CS;
+            const float* g = gimg + ((size_t)hl * p.W + wl) * p.srcStride + (s0 + s) * DT_CS;
             const size_t dx = (size_t)((pk >> RB_DX) & 1u) * p.srcStride;
             const size_t dy = (size_t)((pk >> RB_DY) & 1u) * p.W * p.srcStride;
 #pragma unroll
@@ -414,7 +423,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
     int cb = 0;
     uint32_t pc = 0;
     auto make_records = [&](long long t) {
-      const long long mt = t / n_tiles;
+      const long long mt = (t / KS_SPLIT) / n_tiles;
       const int im = (int)(mt / p.tiles_per_image);
       const int pt = (int)(mt - (long long)im * p.tiles_per_image);
       const int y0 = (pt / p.tiles_x) * DT_PH, x0 = (pt % p.tiles_x) * DT_PW;
@@ -432,13 +441,25 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
     if ((long long)blockIdx.x < total_tiles) make_records(blockIdx.x);
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       if (tile + gridDim.x < total_tiles) make_records(tile + gridDim.x);
-      const int n_tile = (int)(tile % n_tiles);
-      const long long m_tile = tile / n_tiles;
+      const int n_tile = (int)((tile / KS_SPLIT) % n_tiles);
+      const long long m_tile = (tile / KS_SPLIT) / n_tiles;
       const int n = (int)(m_tile / p.tiles_per_image);
       const int pt = (int)(m_tile - (long long)n * p.tiles_per_image);
       const int oy = (pt / p.tiles_x) * DT_PH + (i >> 4), ox = (pt % p.tiles_x) * DT_PW + (i & 15);
       const int m = (n * p.H + oy) * p.W + ox;
       const int col_end = min(p.Cout, (n_tile + 1) * p.BN);
+      // split-K: the 32 finished columns of this position go to the workspace instead of through the epilogue
+      float4* part_row = reinterpret_cast<float4*>(p.part) + (size_t)tile * (p.BN >> 2) * 128 + i;
+      auto emit = [&](float (&vv)[32], int c0) {
+        if (KS_SPLIT > 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (c0 + 4 * j < p.BN)
+              __stcg(part_row + (size_t)((c0 >> 2) + j) * 128, make_float4(vv[4 * j], vv[4 * j + 1], vv[4 * j + 2], vv[4 * j + 3]));
+        } else {
+          epilogue_sub_tile(ep, nullptr, vv, lane, true, m, n, oy, ox, n_tile * p.BN + c0, col_end);
+        }
+      };
       if (X3) {
         // two-level accumulation (see conv_tma.cu): every finished group of <= 36 MMAs is added, with round-to-nearest,
         // into running sums.  The sums live in a third TMEM region (columns [2 BN, 3 BN)) instead of registers, so the
@@ -478,7 +499,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
           float vv[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(rr[j]);
-          epilogue_sub_tile(ep, nullptr, vv, lane, true, m, n, oy, ox, n_tile * p.BN + c0, col_end);
+          emit(vv, c0);
         }
       } else {
         mbar_wait(smem_u32(&ctl->p_full[buf]), (pf >> buf) & 1u);
@@ -500,7 +521,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
           float vv[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(rr[j]);
-          epilogue_sub_tile(ep, nullptr, vv, lane, true, m, n, oy, ox, n_tile * p.BN + c0, col_end);
+          emit(vv, c0);
         }
         pf ^= 1u << buf;
         buf ^= 1;
@@ -511,6 +532,58 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// split-K, second half: one thread per (position, 4 channels) adds the partial sums in split order + epilogue
+__global__ void __launch_bounds__(256) dcn_tma_splitk_finish(const __grid_constant__ DcnTmaParams p, long long mn_tiles) {
+  const int G = p.BN >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= mn_tiles * G * 128) return;
+  const int i = (int)(idx & 127);
+  const int c4 = (int)((idx >> 7) % G);
+  const long long mn = idx / (128ll * G);
+  const float4* src = reinterpret_cast<const float4*>(p.part) + ((size_t)mn * p.ksplit * G + c4) * 128 + i;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int q = 0; q < p.ksplit; ++q) {
+    const float4 v = __ldcg(src + (size_t)q * G * 128);
+    a.x += v.x;
+    a.y += v.y;
+    a.z += v.z;
+    a.w += v.w;
+  }
+  const int n_tiles = p.CoutPad / p.BN;
+  const int n_tile = (int)(mn % n_tiles);
+  const long long m_tile = mn / n_tiles;
+  const int n = (int)(m_tile / p.tiles_per_image);
+  const int pt = (int)(m_tile - (long long)n * p.tiles_per_image);
+  const int oy = (pt / p.tiles_x) * DT_PH + (i >> 4), ox = (pt % p.tiles_x) * DT_PW + (i & 15);
+  const size_t m = ((size_t)n * p.H + oy) * p.W + ox;
+  const int col0 = n_tile * p.BN + c4 * 4;
+  const int col_end = min(p.Cout, (n_tile + 1) * p.BN);
+  float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool in = col0 + j < col_end;
+    if (col0 + j < p.CoutPad) v[j] += __ldg(p.bias + col0 + j);
+    if (p.residual && in && !p.res_after_relu) v[j] += __ldg(p.residual + m * p.resStride + col0 + j);
+    if (p.relu) v[j] = fmaxf(v[j], 0.f);
+    if (p.residual && in && p.res_after_relu) v[j] += __ldg(p.residual + m * p.resStride + col0 + j);
+    if (p.round_tf32) v[j] = tf32_round(v[j]);
+  }
+  if (p.out_nchw) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (col0 + j < col_end) p.out[(((size_t)n * p.Cout + col0 + j) * p.H + oy) * p.W + ox] = v[j];
+  } else {
+    float* o = p.out + m * p.outStride + col0;
+    if (col0 + 3 < col_end) {
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (col0 + j < col_end) o[j] = v[j];
+    }
+  }
 }
 
 }  // namespace
@@ -586,12 +659,34 @@ int launch_dcn_tma(const IgemmParams& p, const void* map, int x3, int round_out_
   }
   int num_sms = 0;
   if (int rc = device_sm_count(&num_sms)) return rc;
+  // split-K: at batch 1 the 512 -> 256 DCN at 16 x 16 is 4 tiles of 288 K blocks; deal slab ranges to idle SMs
+  q.ksplit = 1;
+  q.sps = p.Cin / DT_CS;
+  q.part = p.splitk_ws;
+  const long long mn = q.total_tiles;
+  const char* ks_off = getenv("CP_NO_SPLITK");        // "1": no split-K anywhere, "dcn": not here, "conv": not in conv_tma
+  if (p.splitk_ws && !(ks_off && (ks_off[0] == '1' || ks_off[0] == 'd'))) {
+    const int nslab = p.Cin / DT_CS;
+    int S = 1;
+    for (int cand = 2; cand <= nslab; ++cand)
+      if (nslab % cand == 0 && mn * cand <= num_sms && (size_t)mn * cand * 128 * q.BN <= p.splitk_ws_floats) S = cand;
+    if (S > 1) {
+      q.ksplit = S;
+      q.sps = nslab / S;
+      q.total_tiles = mn * S;
+    }
+  }
   const unsigned grid = (unsigned)(q.total_tiles < num_sms ? q.total_tiles : num_sms);
   if (x3)
     dcn_tma_kernel<true><<<grid, DT_THREADS, smem, stream>>>(q);
   else
     dcn_tma_kernel<false><<<grid, DT_THREADS, smem, stream>>>(q);
   CP_LAUNCH_CHECK("dcn_tma_kernel");
+  if (q.ksplit > 1) {
+    const long long threads = mn * (q.BN / 4) * 128;
+    dcn_tma_splitk_finish<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(q, mn);
+    CP_LAUNCH_CHECK("dcn_tma_splitk_finish");
+  }
   return CP_OK;
 }
 

@@ -23,6 +23,8 @@ namespace cp {
 
 thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+thread_local long long g_launch_counter = 0;
+
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
   return code;
@@ -122,8 +124,7 @@ struct cp_plan {
   bool no_umma = false;          // CP_NO_UMMA=1: ops the TMA kernels do not take stay on the fp32 CUDA-core kernel (diagnostics)
   unsigned char* umma_wts = nullptr;
   size_t umma_bytes = 0;
-  float* splitk_ws = nullptr;      // conv_tma split-K partial sums (kSplitkWsFloats) + arrival counters
-  int* splitk_counters = nullptr;
+  float* splitk_ws = nullptr;      // conv_tma / dcn_tma split-K partial sums (kSplitkWsFloats)
 };
 
 namespace cp {
@@ -672,10 +673,8 @@ int cp_plan_create(const cp_config* cfg, cp_plan** out) {
   CP_CUDA_CHECK(cudaMemset(P->wts, 0, P->w_floats * sizeof(float)));
   CP_CUDA_CHECK(cudaMalloc(&P->gn_stats, sizeof(double) * (size_t)P->B * 64 * 2));
   if (P->umma_bytes) CP_CUDA_CHECK(cudaMalloc(&P->umma_wts, P->umma_bytes));
-  if (P->prec == 1) {
+  if (P->prec == 1 || P->prec == 2) {
     CP_CUDA_CHECK(cudaMalloc(&P->splitk_ws, kSplitkWsFloats * sizeof(float)));
-    CP_CUDA_CHECK(cudaMalloc(&P->splitk_counters, kSplitkMaxTiles * sizeof(int)));
-    CP_CUDA_CHECK(cudaMemset(P->splitk_counters, 0, kSplitkMaxTiles * sizeof(int)));
   }
   for (auto& op : P->ops) {
     if (!op.use_dcn_tma) continue;
@@ -726,7 +725,6 @@ int cp_plan_destroy(cp_plan* P) {
   cudaFree(P->gn_stats);
   if (P->umma_wts) cudaFree(P->umma_wts);
   if (P->splitk_ws) cudaFree(P->splitk_ws);
-  if (P->splitk_counters) cudaFree(P->splitk_counters);
   if (P->decode_ws) cudaFree(P->decode_ws);
   delete P;
   return CP_OK;
@@ -820,6 +818,7 @@ struct ProfCtx {
 static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* const* head_out, cudaStream_t s,
                        ProfCtx* prof = nullptr) {
   int rc;
+  const long long launches0 = g_launch_counter;
   for (auto& op : P->ops) {
     if (prof) {
       cudaEvent_t e;
@@ -889,13 +888,14 @@ static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* 
         }
         if (op.use_dcn_tma) {
           p.wgt_umma = P->umma_wts + op.umma_off;
+          p.splitk_ws = P->splitk_ws;
+          p.splitk_ws_floats = P->splitk_ws ? kSplitkWsFloats : 0;
           const unsigned char* mp = (const unsigned char*)(((uintptr_t)op.tma_maps.data() + 63) & ~(uintptr_t)63);
           if ((rc = launch_dcn_tma(p, mp, P->prec == 1, P->prec == 2, s))) return rc;
         } else if (op.use_tma) {
           p.wgt_umma = P->umma_wts + op.umma_off;
           p.splitk_ws = P->splitk_ws;
           p.splitk_ws_floats = P->splitk_ws ? kSplitkWsFloats : 0;
-          p.splitk_counters = P->splitk_counters;
           const unsigned char* mp = (const unsigned char*)(((uintptr_t)op.tma_maps.data() + 63) & ~(uintptr_t)63);
           if ((rc = launch_conv_tma(p, mp, P->prec == 2, P->prec == 1, s))) return rc;
         } else if (op.use_umma) {
@@ -941,6 +941,7 @@ static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* 
     CP_CUDA_CHECK(cudaEventRecord(e, s));
     prof->ev.push_back(e);
   }
+  P->launches = (int)(g_launch_counter - launches0);      // measured, replaces the estimate of cp_plan_create
   return CP_OK;
 }
 

@@ -106,13 +106,48 @@ def test_512_frame17_of_b32(prec, cplib):
         assert torch.equal(full[h], again[h]), "the plan is not re-entrant: " + h
         assert torch.equal(full[h][17], moved[h][3]), "a frame's heads depend on its batch neighbours / slot: " + h
         d = (full[h][17:18] - one[h]).abs().max().item() / one[h].abs().max().item()
-        assert d <= 2e-5, "frame 17 of the batch vs the frame alone: %s %.2e" % (h, d)
+        # single-pass tf32: the truncating accumulator makes the result depend on the K partition at its own error level
+        assert d <= (5e-4 if prec == "tf32x3" else 5e-2), "frame 17 of the batch vs the frame alone: %s %.2e" % (h, d)
     want = net_ref.forward(x[17:18], sd, opt.heads, "dla_34")
     for h in opt.heads:
         w = want[h].numpy()
         e = np.abs(full[h][17:18].cpu().numpy() - w).max() / np.abs(w).max()
         print("512x512 b32[17] %-7s %-10s gpu-vs-oracle %.2e" % (prec, h, e))
         assert e <= TOL_512[prec], (h, e)
+
+
+@pytest.mark.parametrize("hw", [(512, 512), (256, 320)])
+def test_split_k_partitions_agree(hw, cplib):
+    """The plan picks the split-K factor of every small-map conv from the batch size (tiles vs SMs), so each batch size
+    below runs a different K partition of levels 3-5 / the IDA nodes.  The same frame must come out the same to fp32
+    round-off (the bound is a few times the reference's own fp32-vs-fp64 distance, see test_512_b1) whatever the
+    partition, and bit-identically at every batch size once split-K is switched off (CP_NO_SPLITK=1)."""
+    import os
+    m, opt, sd = _model(12, "tf32x3")
+    H, W = hw
+    frames = synth.synthetic_frames(12, H, W, seed=99)
+    x = torch.from_numpy(synth.normalize_frames(frames)).cuda()
+    base = m(x[:1].contiguous())[-1]
+    base = {h: base[h].clone() for h in opt.heads}
+    worst = 0.0
+    for B in (2, 3, 5, 12):
+        got = m(x[:B].contiguous())[-1]
+        for h in opt.heads:
+            d = (got[h][:1] - base[h]).abs().max().item() / base[h].abs().max().item()
+            worst = max(worst, d)
+            assert d <= 5e-4, "batch %d vs batch 1, %s: %.2e" % (B, h, d)
+    print("split-K partitions %dx%d: worst head difference %.2e" % (H, W, worst))
+    os.environ["CP_NO_SPLITK"] = "1"
+    try:
+        one = m(x[:1].contiguous())[-1]
+        one = {h: one[h].clone() for h in opt.heads}
+        many = m(x[:5].contiguous())[-1]
+        for h in opt.heads:
+            assert torch.equal(many[h][:1], one[h]), "without split-K a frame must not depend on the batch size: " + h
+            d = (one[h] - base[h]).abs().max().item() / base[h].abs().max().item()
+            assert d <= 5e-4, "split-K vs serial K loop, %s: %.2e" % (h, d)
+    finally:
+        del os.environ["CP_NO_SPLITK"]
 
 
 # ------------------------------------------------------------------------------------------- image -> pose

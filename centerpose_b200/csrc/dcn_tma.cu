@@ -23,8 +23,11 @@
 //   warps 4-7   : epilogue (TMEM lane == position); x3: promotes every accumulation group into fp32 registers.
 //                 Thread i also writes the sampling records (one 16-byte record per tap) of position i of the NEXT tile
 //   warps 8-15  : gather, one thread per position: 4 corners x 16 channels from the slab -> bilinear blend * mask ->
-//                 (hi, lo) tf32 split -> A tile in the UMMA SWIZZLE_64B K-major layout; warps 8-11 / 12-15 take
-//                 alternate K blocks and own two A stages each
+//                 (hi, lo) tf32 split -> A tile in the UMMA SWIZZLE_64B K-major layout.  NG = 2 groups of four warps
+//                 take K blocks kb = g, g + NG, ... and own AH A stages each.  (Measured, profiles/r02_dcn_ncu.md: every
+//                 role of this pipeline waits 25-40 % of its time on its neighbour and the SM issues 43 % of its slots;
+//                 16 gather warps in 4 groups at 80 registers were 15 % SLOWER -- the gather is not the limiter, the
+//                 hand-offs are -- so the shared memory goes into a second A stage per group instead.)
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -37,7 +40,7 @@ namespace {
 using namespace umma;
 
 constexpr int DT_BM = 128;
-constexpr int DT_THREADS = 512;
+constexpr int DT_THREADS = 512;     // 4 control + 4 epilogue + 8 gather warps
 constexpr int DT_CS = 16;            // channels per slab = one UMMA K block of 64-byte rows
 constexpr int DT_PH = 8, DT_PW = 16;  // output patch (rows x columns) = 128 positions
 constexpr int DT_HALO = 8;           // slab margin around the patch, both directions
@@ -56,7 +59,8 @@ struct DcnTmaParams {
   long long total_tiles;             // m tiles x n tiles (n fastest)
   int SB;
   int group;                         // x3: K blocks (16 channels) per TMEM accumulation group
-  int AH;                            // A stages per gather half (1 or 2)
+  int AH;                            // A stages per gather group (1 or 2)
+  int NG;                            // gather groups of four warps (2 or 4)
   const float* bias;
   const float* residual;
   int resStride, relu, res_after_relu;
@@ -71,7 +75,7 @@ struct DcnTmaParams {
 
 struct DcnCtl {
   unsigned long long s_full[2], s_empty[2];
-  unsigned long long a_full[4], a_empty[4];       // stages 2h, 2h+1 belong to gather half h
+  unsigned long long a_full[8], a_empty[8];       // stages g AH .. g AH + AH - 1 belong to gather group g
   unsigned long long c_full[2], c_empty[2];
   unsigned long long b_full[8], b_empty[8];
   unsigned long long p_full[2], p_empty[2];
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
   const uint32_t a_stage = X3 ? 16384u : 8192u;                // hi (+ lo) tile of 128 rows x 64 bytes
   const uint32_t atiles0 = slabs0 + 2u * DT_SLAB_BYTES;
   const uint32_t btile_bytes = (uint32_t)p.BN * 64u * (X3 ? 2u : 1u);
-  const uint32_t btiles0 = atiles0 + 2u * (uint32_t)p.AH * a_stage;
+  const uint32_t btiles0 = atiles0 + (uint32_t)(p.NG * p.AH) * a_stage;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = p.CoutPad / p.BN;
@@ -145,15 +149,15 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&ctl->s_full[s]), 1);
-      mbar_init(smem_u32(&ctl->s_empty[s]), 8);      // one arrival per gather warp
-      mbar_init(smem_u32(&ctl->a_full[s]), 4);       // written by the four gather warps of one half
-      mbar_init(smem_u32(&ctl->a_empty[s]), 1);
-      mbar_init(smem_u32(&ctl->a_full[2 + s]), 4);
-      mbar_init(smem_u32(&ctl->a_empty[2 + s]), 1);
-      mbar_init(smem_u32(&ctl->c_full[s]), 4);       // one arrival per epilogue warp
-      mbar_init(smem_u32(&ctl->c_empty[s]), 8);
+      mbar_init(smem_u32(&ctl->s_empty[s]), 4 * p.NG);      // one arrival per active gather warp
+      mbar_init(smem_u32(&ctl->c_full[s]), 4);              // one arrival per epilogue warp
+      mbar_init(smem_u32(&ctl->c_empty[s]), 4 * p.NG);
       mbar_init(smem_u32(&ctl->p_full[s]), 1);
       mbar_init(smem_u32(&ctl->p_empty[s]), 128);
+    }
+    for (int s = 0; s < p.NG * p.AH; ++s) {
+      mbar_init(smem_u32(&ctl->a_full[s]), 4);              // written by the four gather warps of one group
+      mbar_init(smem_u32(&ctl->a_empty[s]), 1);
     }
     for (int s = 0; s < p.SB; ++s) {
       mbar_init(smem_u32(&ctl->b_full[s]), 1);
@@ -172,6 +176,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
+  // warpgroup 0 (control warps) hands registers to warpgroup 1 (epilogue: 64 running sums + a 32-column TMEM read)
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 0) {
     // ===================== slabs via TMA =====================
     if (lane == 0) {
@@ -220,54 +226,64 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
     __syncwarp();
   } else if (warp == 2) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    // This loop is the critical path of the kernel (ncu: the MMA warp is busy 60 % of the time with ~130 dependent scalar
+    // instructions per K block): descriptors are 32-bit low words + one shared high word, every parameter lives in a
+    // register, and the two gather groups are handled by an explicit even / odd step.
     const uint32_t idesc = make_idesc_tf32(p.BN);
     const uint64_t dtmpl = make_desc(0, 0, DT_CS);
+    const uint32_t dhi = (uint32_t)(dtmpl >> 32);
+    const uint32_t dlo0 = (uint32_t)dtmpl;
     const uint32_t a_lo_u = 8192u >> 4;
     const uint32_t b_lo_u = ((uint32_t)p.BN * 64u) >> 4;
+    const uint32_t a0_u = dlo0 + (atiles0 >> 4), a_stage_u = a_stage >> 4;
+    const uint32_t b0_u = dlo0 + (btiles0 >> 4), b_stage_u = btile_bytes >> 4;
+    const uint32_t bar_a_full = smem_u32(&ctl->a_full[0]), bar_a_empty = smem_u32(&ctl->a_empty[0]);
+    const uint32_t bar_b_full = smem_u32(&ctl->b_full[0]), bar_b_empty = smem_u32(&ctl->b_empty[0]);
+    const uint32_t bar_p_full = smem_u32(&ctl->p_full[0]), bar_p_empty = smem_u32(&ctl->p_empty[0]);
+    const int SB = p.SB, AH = p.AH, group = p.group;
+    const uint32_t bn = (uint32_t)p.BN;
     int sb = 0, buf = 0;
     uint32_t pb = 0, pe = 0;
-    uint32_t cnt0 = 0, cnt1 = 0;          // K blocks consumed from gather half 0 / 1 (K block kbi of a tile belongs to half kbi & 1)
+    uint32_t cnt0 = 0, cnt1 = 0;          // K blocks consumed from gather group 0 / 1 (K block kbi of a tile -> group kbi & 1)
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int gk = 0;
       for (int kbi = 0; kbi < KB; ++kbi) {
+        const int grp = kbi & 1;
         const bool first = X3 ? (gk == 0) : (kbi == 0);
-        if (first) mbar_wait(smem_u32(&ctl->p_empty[buf]), ((pe >> buf) & 1u) ^ 1u);
-        const uint32_t hcnt = (kbi & 1) ? cnt1 : cnt0;
-        const int sa = (kbi & 1) * 2 + (int)(hcnt & (uint32_t)(p.AH - 1));
-        mbar_wait(smem_u32(&ctl->a_full[sa]), (hcnt >> (p.AH - 1)) & 1u);
-        mbar_wait(smem_u32(&ctl->b_full[sb]), pb);
+        if (first) mbar_wait(bar_p_empty + 8u * (uint32_t)buf, ((pe >> buf) & 1u) ^ 1u);
+        const uint32_t hcnt = grp ? cnt1 : cnt0;
+        const uint32_t sa = (uint32_t)(grp * AH) + (hcnt & (uint32_t)(AH - 1));
+        mbar_wait(bar_a_full + 8u * sa, (hcnt >> (AH - 1)) & 1u);
+        mbar_wait(bar_b_full + 8u * (uint32_t)sb, pb);
         tc_fence_after();
-        const uint64_t da = dtmpl + (uint64_t)((atiles0 + (uint32_t)((kbi & 1) * p.AH + (sa & 1)) * a_stage) >> 4);
-        const uint64_t db = dtmpl + (uint64_t)((btiles0 + (uint32_t)sb * btile_bytes) >> 4);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.BN);
-        const bool last = X3 ? (gk == p.group - 1 || kbi == KB - 1) : (kbi == KB - 1);
+        const uint32_t da = a0_u + sa * a_stage_u;
+        const uint32_t db = b0_u + (uint32_t)sb * b_stage_u;
+        const uint32_t d_tmem = tmem_base + (uint32_t)buf * bn;
+        const bool last = X3 ? (gk == group - 1 || kbi == KB - 1) : (kbi == KB - 1);
         if (elect_one()) {
           if (X3) {        // cross terms first, hi x hi last (see conv_tma.cu)
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              const uint32_t acc = (first && ks == 0) ? 0u : 1u;
-              umma_tf32(d_tmem, da + a_lo_u + 2 * ks, db + 2 * ks, idesc, acc);
-              umma_tf32(d_tmem, da + 2 * ks, db + b_lo_u + 2 * ks, idesc, 1u);
+              umma_tf32_lohi(d_tmem, da + a_lo_u + 2u * ks, db + 2u * ks, dhi, idesc, (first && ks == 0) ? 0u : 1u);
+              umma_tf32_lohi(d_tmem, da + 2u * ks, db + b_lo_u + 2u * ks, dhi, idesc, 1u);
             }
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) umma_tf32(d_tmem, da + 2 * ks, db + 2 * ks, idesc, 1u);
+            for (int ks = 0; ks < 2; ++ks) umma_tf32_lohi(d_tmem, da + 2u * ks, db + 2u * ks, dhi, idesc, 1u);
           } else {
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) umma_tf32(d_tmem, da + 2 * ks, db + 2 * ks, idesc, (first && ks == 0) ? 0u : 1u);
+            for (int ks = 0; ks < 2; ++ks) umma_tf32_lohi(d_tmem, da + 2u * ks, db + 2u * ks, dhi, idesc, (first && ks == 0) ? 0u : 1u);
           }
-          umma_commit(smem_u32(&ctl->b_empty[sb]));
-          umma_commit(smem_u32(&ctl->a_empty[sa]));
-          if (last) umma_commit(smem_u32(&ctl->p_full[buf]));
+          umma_commit(bar_b_empty + 8u * (uint32_t)sb);
+          umma_commit(bar_a_empty + 8u * sa);
+          if (last) umma_commit(bar_p_full + 8u * (uint32_t)buf);
         }
         __syncwarp();
-        if (++sb == p.SB) {
+        if (++sb == SB) {
           sb = 0;
           pb ^= 1u;
         }
-        if (kbi & 1)
-          ++cnt1;
-        else
-          ++cnt0;
+        cnt0 += (uint32_t)(grp ^ 1);
+        cnt1 += (uint32_t)grp;
         if (last) {
           pe ^= 1u << buf;
           buf ^= 1;
@@ -284,14 +300,15 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
     // blocks (kb = half, half + 2, ...) and each half owns one A stage, so the record of a (position, tap) is decoded
     // once for all 16 channels and a stage is synchronised once per 128-thread task =====================
     const int gt = tid - 256;
-    const int half = gt >> 7;
+    const int half = gt >> 7;              // gather group 0 .. NG - 1
     const int row = gt & 127;
+    const long long g_tiles = half < p.NG ? total_tiles : 0;      // groups past NG idle (shared memory had room for two)
     const uint32_t a_row = atiles0 + (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 64u;
     const uint32_t asw = (uint32_t)(row >> 1) & 3u;
     int ss = 0, cb = 0;
     uint32_t ps = 0, pc = 0;
     uint32_t cnt = 0;                      // K blocks this half has produced; stage = 2 half + (cnt & 1)
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (long long tile = blockIdx.x; tile < g_tiles; tile += gridDim.x) {
       const long long m_tile = (tile / KS_SPLIT) / n_tiles;
       const int s0 = (int)(tile % KS_SPLIT) * nslab;
       const int img = (int)(m_tile / p.tiles_per_image);
@@ -300,7 +317,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
       const float* gimg = p.src + (size_t)img * p.H * p.W * p.srcStride;
       int cur = -1;
       uint32_t slab = 0;
-      for (int kb = half; kb < KB; kb += 2) {
+      float4 rec_next = ld_shared_v4f(crow + (uint32_t)(half % 9) * 16u);      // tap of this group's first K block
+      for (int kb = half; kb < KB; kb += p.NG) {
         const int s = kb / 9, t = kb - s * 9;
         if (s != cur) {
           if (cur >= 0) {                     // done with the previous slab
@@ -315,7 +333,12 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
           slab = slabs0 + (uint32_t)ss * DT_SLAB_BYTES;
           cur = s;
         }
-        const float4 rec = ld_shared_v4f(crow + (uint32_t)t * 16u);
+        const float4 rec = rec_next;
+        {                                   // the record of this group's next K block: its latency hides behind this gather
+          const int kn = kb + p.NG;
+          const int tn = kn - (kn / 9) * 9;
+          rec_next = ld_shared_v4f(crow + (uint32_t)(kn < KB ? tn : 0) * 16u);
+        }
         const uint32_t pk = __float_as_uint(rec.w);
         float4 v[4];
 #pragma unroll
@@ -323,26 +346,36 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
         if ((pk >> RB_LIVE) & 1u) {
           const float lh = rec.x, lw = rec.y, mk = rec.z;
           const float hh = 1.f - lh, hw = 1.f - lw;
-          const float w1 = ((pk >> (RB_W + 0)) & 1u) ? hh * hw : 0.f;
-          const float w2 = ((pk >> (RB_W + 1)) & 1u) ? hh * lw : 0.f;
-          const float w3 = ((pk >> (RB_W + 2)) & 1u) ? lh * hw : 0.f;
-          const float w4 = ((pk >> (RB_W + 3)) & 1u) ? lh * lw : 0.f;
+          const float w1 = ((pk >> (RB_W + 0)) & 1u) ? hh * hw * mk : 0.f;
+          const float w2 = ((pk >> (RB_W + 1)) & 1u) ? hh * lw * mk : 0.f;
+          const float w3 = ((pk >> (RB_W + 2)) & 1u) ? lh * hw * mk : 0.f;
+          const float w4 = ((pk >> (RB_W + 3)) & 1u) ? lh * lw * mk : 0.f;
           if ((pk >> RB_SLAB) & 1u) {
             // slab rows are 64 bytes in TMA SWIZZLE_64B order: 16-byte chunk c of position q sits at c ^ ((q >> 1) & 3)
             const uint32_t q1 = pk & 0x3FFFu, q2 = q1 + ((pk >> RB_DX) & 1u);
             const uint32_t q3 = q1 + ((pk >> RB_DY) & 1u) * (uint32_t)DT_SW, q4 = q3 + ((pk >> RB_DX) & 1u);
-            const uint32_t b1 = slab + q1 * 64u, b2 = slab + q2 * 64u, b3 = slab + q3 * 64u, b4 = slab + q4 * 64u;
-            const uint32_t s1 = (q1 >> 1) & 3u, s2 = (q2 >> 1) & 3u, s3 = (q3 >> 1) & 3u, s4 = (q4 >> 1) & 3u;
+            // chunk c of position q: slab + 64 q + ((c ^ s) << 4) == (slab + 64 q + (s << 4)) ^ (c << 4)  (64-byte aligned rows)
+            const uint32_t b1 = slab + q1 * 64u + ((q1 << 3) & 0x30u), b2 = slab + q2 * 64u + ((q2 << 3) & 0x30u);
+            const uint32_t b3 = slab + q3 * 64u + ((q3 << 3) & 0x30u), b4 = slab + q4 * 64u + ((q4 << 3) & 0x30u);
+            // all sixteen 16-byte loads are issued before the first blend (ld_shared_v4f is volatile: source order is kept),
+            // so their latencies overlap instead of being paid one after the other by this warp
+            float4 c1[4], c2[4], c3[4], c4[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const float4 c1 = ld_shared_v4f(b1 + (((uint32_t)c ^ s1) << 4));
-              const float4 c2 = ld_shared_v4f(b2 + (((uint32_t)c ^ s2) << 4));
-              const float4 c3 = ld_shared_v4f(b3 + (((uint32_t)c ^ s3) << 4));
-              const float4 c4 = ld_shared_v4f(b4 + (((uint32_t)c ^ s4) << 4));
-              v[c].x = (w1 * c1.x + w2 * c2.x + w3 * c3.x + w4 * c4.x) * mk;
-              v[c].y = (w1 * c1.y + w2 * c2.y + w3 * c3.y + w4 * c4.y) * mk;
-              v[c].z = (w1 * c1.z + w2 * c2.z + w3 * c3.z + w4 * c4.z) * mk;
-              v[c].w = (w1 * c1.w + w2 * c2.w + w3 * c3.w + w4 * c4.w) * mk;
+              c1[c] = ld_shared_v4f(b1 ^ ((uint32_t)c << 4));
+              c2[c] = ld_shared_v4f(b2 ^ ((uint32_t)c << 4));
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              c3[c] = ld_shared_v4f(b3 ^ ((uint32_t)c << 4));
+              c4[c] = ld_shared_v4f(b4 ^ ((uint32_t)c << 4));
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              v[c].x = w1 * c1[c].x + w2 * c2[c].x + w3 * c3[c].x + w4 * c4[c].x;
+              v[c].y = w1 * c1[c].y + w2 * c2[c].y + w3 * c3[c].y + w4 * c4[c].y;
+              v[c].z = w1 * c1[c].z + w2 * c2[c].z + w3 * c3[c].z + w4 * c4[c].z;
+              v[c].w = w1 * c1[c].w + w2 * c2[c].w + w3 * c3[c].w + w4 * c4[c].w;
             }
           } else {      // corner rows outside the staged slab: same arithmetic from global memory
             const int hl = (int)((pk >> 7) & 127u), wl = (int)(pk & 127u);
@@ -355,27 +388,27 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
               const float4 c2 = __ldg(reinterpret_cast<const float4*>(g + dx) + c);
               const float4 c3 = __ldg(reinterpret_cast<const float4*>(g + dy) + c);
               const float4 c4 = __ldg(reinterpret_cast<const float4*>(g + dy + dx) + c);
-              v[c].x = (w1 * c1.x + w2 * c2.x + w3 * c3.x + w4 * c4.x) * mk;
-              v[c].y = (w1 * c1.y + w2 * c2.y + w3 * c3.y + w4 * c4.y) * mk;
-              v[c].z = (w1 * c1.z + w2 * c2.z + w3 * c3.z + w4 * c4.z) * mk;
-              v[c].w = (w1 * c1.w + w2 * c2.w + w3 * c3.w + w4 * c4.w) * mk;
+              v[c].x = w1 * c1.x + w2 * c2.x + w3 * c3.x + w4 * c4.x;
+              v[c].y = w1 * c1.y + w2 * c2.y + w3 * c3.y + w4 * c4.y;
+              v[c].z = w1 * c1.z + w2 * c2.z + w3 * c3.z + w4 * c4.z;
+              v[c].w = w1 * c1.w + w2 * c2.w + w3 * c3.w + w4 * c4.w;
             }
           }
         }
-        const int sa = half * 2 + (int)(cnt & (uint32_t)(p.AH - 1));          // barrier index; tile slot = half * AH + (sa & 1)
-        const uint32_t a_hi = a_row + (uint32_t)(half * p.AH + (sa & 1)) * a_stage;
+        const int sa = half * p.AH + (int)(cnt & (uint32_t)(p.AH - 1));          // barrier index == tile slot
+        const uint32_t a_hi = a_row + (uint32_t)sa * a_stage + (asw << 4);       // chunk c -> a_hi ^ (c << 4)
         mbar_wait(smem_u32(&ctl->a_empty[sa]), ((cnt >> (p.AH - 1)) & 1u) ^ 1u);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const uint32_t off = ((uint32_t)c ^ asw) << 4;
+          const uint32_t off = (uint32_t)c << 4;
           float4 h;
           h.x = tf32_round(v[c].x);
           h.y = tf32_round(v[c].y);
           h.z = tf32_round(v[c].z);
           h.w = tf32_round(v[c].w);
-          st_shared_v4f(a_hi + off, h.x, h.y, h.z, h.w);
+          st_shared_v4f(a_hi ^ off, h.x, h.y, h.z, h.w);
           if (X3)
-            st_shared_v4f(a_hi + 8192u + off, tf32_round(v[c].x - h.x), tf32_round(v[c].y - h.y), tf32_round(v[c].z - h.z),
+            st_shared_v4f((a_hi ^ off) + 8192u, tf32_round(v[c].x - h.x), tf32_round(v[c].y - h.y), tf32_round(v[c].z - h.z),
                           tf32_round(v[c].w - h.w));
         }
         fence_proxy_async_smem();
@@ -399,6 +432,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
     }
   } else {
     // ===================== epilogue (warps 4-7): TMEM lane == position of the tile =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
     const int q = warp & 3;
     const int i = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -466,6 +500,46 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
         // tile can be 128 columns wide with 128 epilogue threads: ld group + ld sum -> add -> st sum, 16 columns at a time.
         const uint32_t sum_base = lane_base + (uint32_t)(2 * p.BN);
         const int ngroups = (KB + p.group - 1) / p.group;
+        if (p.BN <= 64) {
+          // N tile <= 64: the running sums fit in 64 registers -- one TMEM read per group instead of two reads + a write
+          float sums[64];
+#pragma unroll
+          for (int j = 0; j < 64; ++j) sums[j] = 0.f;
+          for (int gi = 0; gi < ngroups; ++gi) {
+            mbar_wait(smem_u32(&ctl->p_full[buf]), (pf >> buf) & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              if (c * 32 < p.BN) {
+                uint32_t rr[32];
+                tmem_ld16(lane_base + (uint32_t)(buf * p.BN + c * 32), rr);
+                if (c * 32 + 16 < p.BN) {
+                  tmem_ld16(lane_base + (uint32_t)(buf * p.BN + c * 32 + 16), rr + 16);
+                } else {
+#pragma unroll
+                  for (int j = 16; j < 32; ++j) rr[j] = 0u;
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sums[c * 32 + j] += __uint_as_float(rr[j]);
+              }
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&ctl->p_empty[buf]));
+            pf ^= 1u << buf;
+            buf ^= 1;
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            if (c * 32 < p.BN) {
+              float vv[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) vv[j] = sums[c * 32 + j];
+              emit(vv, c * 32);
+            }
+          }
+          continue;
+        }
         for (int gi = 0; gi < ngroups; ++gi) {
           mbar_wait(smem_u32(&ctl->p_full[buf]), (pf >> buf) & 1u);
           tc_fence_after();
@@ -631,10 +705,16 @@ int launch_dcn_tma(const IgemmParams& p, const void* map, int x3, int round_out_
   q.total_tiles = (long long)q.tiles_per_image * p.B * (p.CoutPad / q.BN);
   const uint32_t a_stage = x3 ? 16384u : 8192u;
   q.group = x3_group_blocks() * 2;      // 16-channel K blocks: same MMA count per group as conv_tma.cu
-  q.AH = x3 ? 1 : 2;                  // shared memory: x3 tiles are twice as large
   const uint32_t btile = (uint32_t)q.BN * 64u * (x3 ? 2u : 1u);
-  const size_t fixed = 1024 + 2 * (size_t)DT_COEF_BYTES + 1024 + 2 * (size_t)DT_SLAB_BYTES + 2 * (size_t)q.AH * a_stage;
   const size_t budget = 226 * 1024;
+  // two A stages per gather group where >= 3 weight stages still fit (x3: N tile <= 64), else one
+  q.NG = 2;
+  q.AH = 2;
+  size_t fixed = 1024 + 2 * (size_t)DT_COEF_BYTES + 1024 + 2 * (size_t)DT_SLAB_BYTES + (size_t)q.NG * q.AH * a_stage;
+  if (getenv("CP_DCN_AH1") || fixed + 3 * (size_t)btile > budget) {
+    q.AH = 1;
+    fixed = 1024 + 2 * (size_t)DT_COEF_BYTES + 1024 + 2 * (size_t)DT_SLAB_BYTES + (size_t)q.NG * q.AH * a_stage;
+  }
   if (fixed + 2 * (size_t)btile > budget) return fail(CP_ERR_INVALID, "dcn_tma: tile does not fit shared memory");
   q.SB = (int)((budget - fixed) / btile);
   if (q.SB > 8) q.SB = 8;

@@ -104,10 +104,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Round to tf32 (10 mantissa bits), nearest, ties away from zero == cvt.rna.tf32.f32 for every finite input (the add
+// carries into the exponent exactly like the rounding does; FLT_MAX rounds to inf either way).  ptxas expands the cvt
+// into IADD + FSETP + SEL + LOP3 (NaN / inf preserved); activations are finite, so the two-instruction form is used:
+// the hi / lo split of the 3-term product runs it 32 times per position and K block.
 __device__ __forceinline__ float tf32_round(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   uint32_t r;

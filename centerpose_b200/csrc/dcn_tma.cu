@@ -61,6 +61,7 @@ struct DcnTmaParams {
   int group;                         // x3: K blocks (16 channels) per TMEM accumulation group
   int AH;                            // A stages per gather group (1 or 2)
   int NG;                            // gather groups of four warps (2 or 4)
+  int nbuf;                          // TMEM accumulation buffers (x3: one per in-flight accumulation group)
   const float* bias;
   const float* residual;
   int resStride, relu, res_after_relu;
@@ -78,7 +79,7 @@ struct DcnCtl {
   unsigned long long a_full[8], a_empty[8];       // stages g AH .. g AH + AH - 1 belong to gather group g
   unsigned long long c_full[2], c_empty[2];
   unsigned long long b_full[8], b_empty[8];
-  unsigned long long p_full[2], p_empty[2];
+  unsigned long long p_full[8], p_empty[8];
   uint32_t tmem_base;
 };
 
@@ -152,6 +153,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
       mbar_init(smem_u32(&ctl->s_empty[s]), 4 * p.NG);      // one arrival per active gather warp
       mbar_init(smem_u32(&ctl->c_full[s]), 4);              // one arrival per epilogue warp
       mbar_init(smem_u32(&ctl->c_empty[s]), 4 * p.NG);
+    }
+    for (int s = 0; s < p.nbuf; ++s) {
       mbar_init(smem_u32(&ctl->p_full[s]), 1);
       mbar_init(smem_u32(&ctl->p_empty[s]), 128);
     }
@@ -166,7 +169,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
     fence_mbar_init();
   }
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.BN * (X3 ? 3 : 2)) tmem_cols <<= 1;     // x3: + BN columns of promoted sums
+  // nbuf accumulation buffers of BN columns; x3 with an N tile > 64 keeps the promoted sums in BN more columns
+  while ((int)tmem_cols < p.BN * (p.nbuf + ((X3 && p.BN > 64) ? 1 : 0))) tmem_cols <<= 1;
   if (warp == 2) {
     tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     tmem_relinquish();
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
     const uint32_t bar_a_full = smem_u32(&ctl->a_full[0]), bar_a_empty = smem_u32(&ctl->a_empty[0]);
     const uint32_t bar_b_full = smem_u32(&ctl->b_full[0]), bar_b_empty = smem_u32(&ctl->b_empty[0]);
     const uint32_t bar_p_full = smem_u32(&ctl->p_full[0]), bar_p_empty = smem_u32(&ctl->p_empty[0]);
-    const int SB = p.SB, AH = p.AH, group = p.group;
+    const int SB = p.SB, AH = p.AH, group = p.group, nbuf = p.nbuf;
     const uint32_t bn = (uint32_t)p.BN;
     int sb = 0, buf = 0;
     uint32_t pb = 0, pe = 0;
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
         cnt1 += (uint32_t)grp;
         if (last) {
           pe ^= 1u << buf;
-          buf ^= 1;
+          if (++buf == nbuf) buf = 0;
           gk = 0;
         } else {
           ++gk;
@@ -498,7 +502,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
         // two-level accumulation (see conv_tma.cu): every finished group of <= 36 MMAs is added, with round-to-nearest,
         // into running sums.  The sums live in a third TMEM region (columns [2 BN, 3 BN)) instead of registers, so the
         // tile can be 128 columns wide with 128 epilogue threads: ld group + ld sum -> add -> st sum, 16 columns at a time.
-        const uint32_t sum_base = lane_base + (uint32_t)(2 * p.BN);
+        const uint32_t sum_base = lane_base + (uint32_t)(p.nbuf * p.BN);
         const int ngroups = (KB + p.group - 1) / p.group;
         if (p.BN <= 64) {
           // N tile <= 64: the running sums fit in 64 registers -- one TMEM read per group instead of two reads + a write
@@ -527,7 +531,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
             tc_fence_before();
             mbar_arrive(smem_u32(&ctl->p_empty[buf]));
             pf ^= 1u << buf;
-            buf ^= 1;
+            if (++buf == p.nbuf) buf = 0;
           }
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -558,7 +562,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
           tc_fence_before();
           mbar_arrive(smem_u32(&ctl->p_empty[buf]));
           pf ^= 1u << buf;
-          buf ^= 1;
+          if (++buf == p.nbuf) buf = 0;
         }
         for (int c0 = 0; c0 < p.BN; c0 += 32) {
           uint32_t rr[32];
@@ -598,7 +602,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
           emit(vv, c0);
         }
         pf ^= 1u << buf;
-        buf ^= 1;
+        if (++buf == p.nbuf) buf = 0;
       }
     }
   }
@@ -716,6 +720,12 @@ int launch_dcn_tma(const IgemmParams& p, const void* map, int x3, int round_out_
     fixed = 1024 + 2 * (size_t)DT_COEF_BYTES + 1024 + 2 * (size_t)DT_SLAB_BYTES + (size_t)q.NG * q.AH * a_stage;
   }
   if (fixed + 2 * (size_t)btile > budget) return fail(CP_ERR_INVALID, "dcn_tma: tile does not fit shared memory");
+  // x3 hands a TMEM buffer to the promoting warps every 12 MMAs (~400 clk of tensor work) and each hand-off costs a
+  // commit -> mbarrier -> tcgen05.ld -> arrive round trip of about the same length: with two buffers the MMA warp
+  // spent 32 % of its time waiting for a free one (ncu, profiles/r02_dcn_ncu.md).  Use all 512 TMEM columns.
+  q.nbuf = 2;
+  if (x3) q.nbuf = q.BN <= 64 ? 8 : (512 - q.BN) / q.BN;
+  if (const char* e = getenv("CP_DCN_NBUF")) q.nbuf = atoi(e) >= 2 && atoi(e) <= q.nbuf ? atoi(e) : q.nbuf;
   q.SB = (int)((budget - fixed) / btile);
   if (q.SB > 8) q.SB = 8;
   q.bias = p.bias;

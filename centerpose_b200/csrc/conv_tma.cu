@@ -68,6 +68,7 @@ struct TmaConvParams {
   int cslab;          // channels per slab: 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B; Cin = 16 layers)
   int x3;             // 3-term split (fp32-equivalent): hi/lo slabs + hi/lo weight tiles, BN <= 128
   int group;          // x3: K blocks per TMEM accumulation group (promoted into fp32 registers after each group)
+  int nbuf;           // TMEM accumulation buffers of tile_m x BN (2; x3 with narrow N tiles: up to 8, all 512 columns)
   const unsigned char* wtiles;
   // split-K (x3, not fused): the K loop of a tile is dealt to `ksplit` CTAs (slab-aligned ranges of `sps` slabs); every
   // CTA stores its promoted partial sums and conv_tma_splitk_finish adds them in split order (deterministic) and runs
@@ -88,7 +89,7 @@ struct TmaCtl {
   unsigned long long a_full[4], a_empty[4], a_split[4];
   unsigned long long b_full[8], b_empty[8];
   unsigned long long accum_full;
-  unsigned long long p_full[2], p_empty[2];
+  unsigned long long p_full[8], p_empty[8];
   unsigned long long w2_full, w2_empty;      // x3 fused heads: 1x1 weights + 3x3 bias of the current tile in shared memory
   uint32_t tmem_base;
 };
@@ -169,7 +170,8 @@ struct IssueCtx {
   uint32_t idesc, dhi, rowu, a_lo_u, b_lo_u, sub_u, a0_u, a_stage_u, b0_u, b_stage_u, tmem_base, buf_cols, bn;
   uint32_t bar_a, bar_a_empty, bar_b_full, bar_b_empty, bar_p_full, bar_p_empty;
   uint32_t tap_u[2];
-  int group, KB, SA, SB, nslab, cluster;
+  int group, KB, SA, SB, nslab, cluster, nbuf;
+  uint32_t sub0_a, sub0_d;        // descriptor / TMEM column offset of this issuer's first sub-tile (two issuers: sub-tile 1)
   uint16_t cmask;
 };
 struct IssueState {
@@ -195,7 +197,7 @@ __device__ __forceinline__ void issue_tile(const IssueCtx& c, IssueState& st, ui
         mbar_wait(c.bar_p_empty + 8u * (uint32_t)st.buf, ((st.pe >> st.buf) & 1u) ^ 1u);
       mbar_wait(c.bar_b_full + 8u * (uint32_t)st.sb, st.pb);
       tc_fence_after();
-      const uint32_t da = a_slab + tap_off;
+      const uint32_t da = a_slab + tap_off + c.sub0_a;
       if (++kx == 3) {
         kx = 0;
         tap_off += c.tap_u[1];       // (Wt - 2) rows
@@ -203,7 +205,7 @@ __device__ __forceinline__ void issue_tile(const IssueCtx& c, IssueState& st, ui
         tap_off += c.tap_u[0];       // 1 row
       }
       const uint32_t db = c.b0_u + (uint32_t)st.sb * c.b_stage_u;
-      const uint32_t d_tmem = c.tmem_base + (uint32_t)st.buf * c.buf_cols;
+      const uint32_t d_tmem = c.tmem_base + (uint32_t)st.buf * c.buf_cols + c.sub0_d;
       const bool last = X3 ? (gk == c.group - 1 || kbi == c.KB - 1) : (kbi == c.KB - 1);
       if (elect_one()) {
         if (X3) {
@@ -245,7 +247,7 @@ __device__ __forceinline__ void issue_tile(const IssueCtx& c, IssueState& st, ui
       }
       if (last) {
         st.pe ^= 1u << st.buf;
-        st.buf ^= 1;
+        if (++st.buf == c.nbuf) st.buf = 0;
         gk = 0;
       } else {
         ++gk;
@@ -263,8 +265,9 @@ struct IssueTiles {            // 32-bit tile arithmetic (the launcher rejects >
   int n_tiles, rank, ksplit;
 };
 
-template <bool X3, int MS, int TAPS, int KS>
-__device__ __forceinline__ void issue_all_tiles(const TmaConvParams& p, const IssueCtx& c, const IssueTiles& tl) {
+// DUAL: two warps issue, one M sub-tile each (issuer 1 only walks the barriers of a tile whose second sub-tile is empty)
+template <bool X3, int MS, int TAPS, int KS, bool DUAL>
+__device__ __forceinline__ void issue_all_tiles(const TmaConvParams& p, const IssueCtx& c, const IssueTiles& tl, int issuer) {
   IssueState st;
   const int Wt = p.Wt, HWt = p.H * p.Wt;
   const long long total_pos = (long long)p.B * p.H * p.W;
@@ -278,10 +281,16 @@ __device__ __forceinline__ void issue_all_tiles(const TmaConvParams& p, const Is
     // x3: small feature maps end inside the first 128 rows of their last tile; the second accumulator is then skipped.
     // MSL = sub-tiles with output positions: a compile-time count, so the unrolled MMA list carries no predication
     const bool sub1_live = (TAPS == 9) ? (g.g0 + TM_BM < HWt) : (g.pos0 + TM_BM < total_pos);
-    if (MS == 2 && sub1_live)
+    if (DUAL) {
+      if (issuer == 0 || sub1_live)
+        issue_tile<X3, 1, TAPS, KS>(c, st, tap0);
+      else
+        issue_tile<X3, 0, TAPS, KS>(c, st, tap0);
+    } else if (MS == 2 && sub1_live) {
       issue_tile<X3, MS, TAPS, KS>(c, st, tap0);
-    else
+    } else {
       issue_tile<X3, 1, TAPS, KS>(c, st, tap0);
+    }
   }
 }
 
@@ -295,6 +304,10 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   // x3 computes TWO 128-row M sub-tiles per weight tile (tile = 256 positions): the weight stream from L2, the measured
   // limiter, is halved per MMA.  The sub-tiles are two accumulators side by side in TMEM and two sets of epilogue warps.
   constexpr int MS = X3 ? 2 : 1;
+  // x3 without the fused 1x1: warps 2 AND 3 issue MMAs, one sub-tile each.  The issue loop of a single warp (~100 dependent
+  // scalar instructions per K block at ~5 clk each) bounds every layer whose K blocks carry little tensor work.
+  constexpr bool DUAL = X3 && !FUSE;
+  constexpr int NISSUE = DUAL ? 2 : 1;
   const uint32_t slabs0 = (smem_u32(smem) + 512u + 1023u) & ~1023u;
   const uint32_t rowb = (uint32_t)p.cslab * 4u;                               // bytes per position row
   const int kslices = p.cslab / 8;                                            // tf32 MMA K = 8
@@ -324,15 +337,15 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   if (tid == 0) {
     for (int s = 0; s < p.SA; ++s) {
       mbar_init(smem_u32(&ctl->a_full[s]), 1);
-      mbar_init(smem_u32(&ctl->a_empty[s]), 1);
+      mbar_init(smem_u32(&ctl->a_empty[s]), NISSUE);
       mbar_init(smem_u32(&ctl->a_split[s]), 128);
     }
     for (int s = 0; s < p.SB; ++s) {
       mbar_init(smem_u32(&ctl->b_full[s]), 1);
-      mbar_init(smem_u32(&ctl->b_empty[s]), p.cluster);      // every CTA of the cluster releases every CTA's slot
+      mbar_init(smem_u32(&ctl->b_empty[s]), p.cluster * NISSUE);      // every issuer of every CTA of the cluster releases every CTA's slot
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&ctl->p_full[s]), 1);       // x3: accumulation group ready / x1: tile accumulator ready
+    for (int s = 0; s < p.nbuf; ++s) {
+      mbar_init(smem_u32(&ctl->p_full[s]), NISSUE);  // x3: accumulation group ready / x1: tile accumulator ready
       mbar_init(smem_u32(&ctl->p_empty[s]), 128 * MS);   // drained by the epilogue threads
     }
     mbar_init(smem_u32(&ctl->w2_full), 1);
@@ -341,7 +354,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   }
   // two TMEM accumulator buffers of BN columns: x1 ping-pongs whole tiles, x3 ping-pongs accumulation groups
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.BN * 2 * MS) tmem_cols <<= 1;
+  while ((int)tmem_cols < p.BN * p.nbuf * MS) tmem_cols <<= 1;
   if (warp == 2) {
     tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     tmem_relinquish();
@@ -420,8 +433,8 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
       }
     }
     __syncwarp();
-  } else if (warp == 2) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 2 || (DUAL && warp == 3)) {
+    // ===================== MMA issuer(s) =====================
     // The issue loop of this ONE warp bounds the kernel once the operand pipelines are deep enough (ncu stall sampling:
     // the warp was busy executing descriptor arithmetic, not waiting).  So: the whole warp walks the warp-uniform loop
     // (descriptors and barrier addresses stay in uniform registers), one elected lane issues, and a descriptor is a
@@ -447,6 +460,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     c.b_stage_u = btile_bytes >> 4;
     c.tmem_base = tmem_base;
     c.buf_cols = (uint32_t)(p.BN * MS);
+    c.nbuf = p.nbuf;
     c.bn = (uint32_t)p.BN;
     c.group = p.group;
     c.KB = KB;
@@ -463,19 +477,22 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     c.cmask = cmask;
     c.tap_u[0] = c.rowu;                                   // step between taps of one kernel row
     c.tap_u[1] = (uint32_t)(p.Wt - 2) * c.rowu;            // step from the last tap of a kernel row to the next row
+    const int issuer = warp - 2;
+    c.sub0_a = DUAL ? (uint32_t)issuer * c.sub_u : 0u;
+    c.sub0_d = DUAL ? (uint32_t)issuer * c.bn : 0u;
     // (taps, K slices) are chosen ONCE, outside the tile loop: each combination owns its copy of the loop, so the
     // register allocation of the hot path is not shared between variants
     const IssueTiles tl{(int)cluster_id, (int)num_clusters, (int)tph, (int)total_tiles, n_tiles, rank, KS_SPLIT};
     if (p.k == 3) {
       if (kslices == 2)
-        issue_all_tiles<X3, MS, 9, 2>(p, c, tl);
+        issue_all_tiles<X3, MS, 9, 2, DUAL>(p, c, tl, issuer);
       else
-        issue_all_tiles<X3, MS, 9, 4>(p, c, tl);
+        issue_all_tiles<X3, MS, 9, 4, DUAL>(p, c, tl, issuer);
     } else {
       if (kslices == 2)
-        issue_all_tiles<X3, MS, 1, 2>(p, c, tl);
+        issue_all_tiles<X3, MS, 1, 2, DUAL>(p, c, tl, issuer);
       else
-        issue_all_tiles<X3, MS, 1, 4>(p, c, tl);
+        issue_all_tiles<X3, MS, 1, 4, DUAL>(p, c, tl, issuer);
     }
   } else if (X3 && FUSE) {
     // ===================== warp 3: 1x1 weights + 3x3 bias of every tile -> shared memory (x3 fused heads) =====================
@@ -619,7 +636,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
           tc_fence_before();
           mbar_arrive(smem_u32(&ctl->p_empty[buf]));
           pf ^= 1u << buf;
-          buf ^= 1;
+          if (++buf == p.nbuf) buf = 0;
         }
         if (!FUSE && KS_SPLIT > 1) {
           // split-K: park the partial sums of this K range, [mn tile][split][float4 column group][row] so that the 32
@@ -727,7 +744,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
           }
         }
         pf ^= 1u << buf;
-        buf ^= 1;
+        if (++buf == p.nbuf) buf = 0;
       }
     }
   }
@@ -1019,6 +1036,15 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   q.x3 = x3;
   q.cslab = tma_cslab(p, x3);
   q.group = x3_group_blocks() * (32 / q.cslab);       // same number of MMAs per TMEM accumulation group
+  // x3 hands a buffer to the promoting warps every accumulation group; narrow N tiles leave TMEM columns for more than two
+  // buffers in flight, which hides the commit -> mbarrier -> tcgen05.ld -> arrive round trip (dcn_tma.cu has the numbers)
+  q.nbuf = 2;
+  if (x3) {
+    q.nbuf = 512 / (q.BN * 2);
+    if (q.nbuf > 8) q.nbuf = 8;
+    if (q.nbuf < 2) q.nbuf = 2;
+  }
+  if (const char* e = getenv("CP_TMA_NBUF")) q.nbuf = atoi(e) >= 2 && atoi(e) <= q.nbuf ? atoi(e) : q.nbuf;
   q.k = p.kh;
   q.Wt = p.Win + 2;
   q.tile_m = tma_tile_m(x3);

@@ -47,14 +47,22 @@ def test_run_contract_and_consistency(cplib):
 
 
 def test_run_batch_matches_run(cplib):
-    """run() is run_batch() of one frame + unpacking: the same frame through both gives the same records.  Inside
-    a larger batch the plan deals the K loops of the small maps differently (split-K), so the heads move by fp32
-    round-off (a few 1e-4 of their range, tests/test_gpu_bench_parity.py) and the key points by a fraction of a pixel."""
+    """run() is run_batch() of one frame + unpacking: the same frame through both gives the same records, alone or inside
+    a batch of four (K partition held fixed, see tests/util.py no_splitk)."""
+    from tests.util import no_splitk
     det, opt = _detector()
     frames = synth.synthetic_frames(4, 512, 512, seed=9)
     cam = synth.default_camera(512, 512)
-    poses, n_valid = det.run_batch(frames, cam)
-    assert poses.shape == (4, opt.K, L.CP_POSE_RECORD)
+    with no_splitk():
+        poses, n_valid = det.run_batch(frames, cam)
+        assert poses.shape == (4, opt.K, L.CP_POSE_RECORD)
+        for b in (0, 3):
+            ret = det.run(frames[b], meta_inp={"camera_matrix": cam})
+            assert len(ret["results"]) == n_valid[b]
+            for i, d in enumerate(ret["results"]):
+                assert abs(d["score"] - poses[b, i, L.P_SCORE]) <= 1e-4
+                assert np.abs(d["kps"] - poses[b, i, L.P_KPS:L.P_KPS + 16]).max() <= 0.05
+    # default plan (split-K on): one frame through run() and through run_batch()
     for b in (0, 3):
         ret = det.run(frames[b], meta_inp={"camera_matrix": cam})
         p1, n1 = det.run_batch(frames[b:b + 1], cam)
@@ -62,10 +70,6 @@ def test_run_batch_matches_run(cplib):
         for i, d in enumerate(ret["results"]):
             assert abs(d["score"] - p1[0, i, L.P_SCORE]) <= 1e-4
             assert np.abs(d["kps"] - p1[0, i, L.P_KPS:L.P_KPS + 16]).max() <= 0.05
-        assert len(ret["results"]) == n_valid[b]
-        for i, d in enumerate(ret["results"]):
-            assert abs(d["score"] - poses[b, i, L.P_SCORE]) <= 1e-3
-            assert np.abs(d["kps"] - poses[b, i, L.P_KPS:L.P_KPS + 16]).max() <= 2.0
 
 
 def test_preprocess_is_bit_exact(cplib):

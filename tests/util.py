@@ -137,3 +137,24 @@ def oracle_records(heads_b, prm, cam, width, height, c, s, L):
         d["_status"] = st
         recs.append(result_to_record(d, d["_k"]))
     return dets, (np.stack(recs) if recs else np.zeros((0, L.CP_POSE_RECORD)))
+
+
+import contextlib
+import os
+
+
+@contextlib.contextmanager
+def no_splitk():
+    """The plan picks the split-K factor of the small-map convolutions from the batch size, so a frame's heads move by
+    fp32 round-off (~1e-4 of their range) with the batch it sits in -- enough to flip a threshold in the tracker or to
+    move a key point of a random-weight network by a pixel.  Tests that assert "batch of B == B single calls" hold the K
+    partition fixed (CP_NO_SPLITK is read at every launch); tests/test_gpu_bench_parity.py bounds the effect itself."""
+    old = os.environ.get("CP_NO_SPLITK")
+    os.environ["CP_NO_SPLITK"] = "1"
+    try:
+        yield
+    finally:
+        if old is None:
+            del os.environ["CP_NO_SPLITK"]
+        else:
+            os.environ["CP_NO_SPLITK"] = old

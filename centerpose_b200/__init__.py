@@ -13,5 +13,6 @@ from .detector import ObjectPoseDetector, detector_factory                   # n
 from .engine import Engine, InferGraph, decode_pnp, decode_params, make_meta, dcn_v2_forward, preprocess, conv2d_nhwc  # noqa: F401
 from .opts import default_opt                                                # noqa: F401
 from .tracker import Tracker, track_to_dict, tracks_to_results               # noqa: F401
+from .pipeline import BatchPipeline                                          # noqa: F401
 
 __version__ = "0.1.0"

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcenterpose_b200.so")
+LIB_PATH = os.environ.get("CP_LIB_PATH") or os.path.join(HERE, "libcenterpose_b200.so")      # CP_LIB_PATH: A/B another build
 
 CP_MAX_HEADS = 16
 CP_POSE_RECORD = 192

@@ -470,7 +470,13 @@ class ObjectPoseDetector(object):
             x = frames.to(dev)
             B, _, ih, iw = x.shape
             c, s = np.array([iw / 2., ih / 2.], np.float32), float(max(ih, iw))
-        meta = make_meta(B, c, s, iw, ih, camera_matrix).to(dev, non_blocking=True)
+        # the per-frame meta (centre / scale / size / camera) of a fixed frame shape and camera is uploaded once
+        cam_key = np.asarray(camera_matrix, np.float64).tobytes()
+        mkey = (B, iw, ih, cam_key, str(dev))
+        if getattr(self, "_meta_key", None) != mkey:
+            self._meta_dev = make_meta(B, c, s, iw, ih, camera_matrix).to(dev)
+            self._meta_key = mkey
+        meta = self._meta_dev
         eng = self.model.engine(B, x.shape[2], x.shape[3], x.device)
         prm = decode_params(self.opt)
         if track:

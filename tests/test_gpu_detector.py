@@ -94,3 +94,32 @@ def test_preprocess_is_bit_exact(cplib):
     inp = cv2.warpAffine(fr[0], M, (256, 192), flags=cv2.INTER_LINEAR)
     want = ((inp / 255. - det.mean) / det.std).astype(np.float32).transpose(2, 0, 1)
     assert np.array_equal(got[0], want)
+
+
+def test_batch_pipeline_matches_run_batch(cplib):
+    """centerpose_b200.BatchPipeline (double-buffered upload / compute / download) returns, batch for batch and in
+    submission order, exactly what run_batch() returns -- with pinned and with pageable frames."""
+    det, opt = _detector()
+    cam = synth.default_camera(512, 512)
+    batches = [synth.synthetic_frames(2, 512, 512, seed=40 + i) for i in range(5)]
+    want = [det.run_batch(b, cam) for b in batches]
+    pipe = cpb.BatchPipeline(det, 2, 512, 512, cam, depth=2)
+    got = []
+    for i, b in enumerate(batches):
+        if pipe.in_flight == pipe.depth:
+            p, n = pipe.collect()
+            got.append((p.copy(), n.copy()))
+        t = torch.from_numpy(b)
+        pipe.submit(t.pin_memory() if i % 2 else t)
+    with pytest.raises(RuntimeError):
+        pipe.submit(batches[0]); pipe.submit(batches[0])
+    while pipe.in_flight:
+        p, n = pipe.collect()
+        got.append((p.copy(), n.copy()))
+    got = got[:5]
+    assert len(got) == 5
+    for (p, n), (wp, wn) in zip(got, want):
+        assert (n == wn).all()
+        assert np.array_equal(p, wp)
+    with pytest.raises(ValueError):
+        pipe.submit(np.zeros((2, 100, 100, 3), np.uint8))

@@ -32,7 +32,7 @@ class _Slot(object):
         self.pbuf = PoseBuffer(batch, K, device, world=world)
         self.h2d_done = torch.cuda.Event()
         self.compute_done = torch.cuda.Event()           # the pre-process kernel has consumed `u8`
-        self.gather_done = torch.cuda.Event()
+        self.side_done = torch.cuda.Event()              # all-gather + download of this slot finished
         self.used = False
 
 
@@ -45,7 +45,7 @@ class BatchPipeline(object):
         self.batch, self.height, self.width = int(batch), int(height), int(width)
         with torch.cuda.device(self.device):
             self.copy_stream = torch.cuda.Stream()
-            self.d2h_stream = torch.cuda.Stream()
+            self.side_stream = torch.cuda.Stream()
             self.slots = [_Slot(batch, height, width, det.opt.K, self.device, world) for _ in range(self.depth)]
         self._queue = collections.deque()
         self._next = 0
@@ -67,6 +67,8 @@ class BatchPipeline(object):
         self._next = (self._next + 1) % self.depth
         compute = torch.cuda.current_stream(self.device)
         if not frames.is_pinned():                       # pageable source: stage it, so the upload below is asynchronous
+            if slot.used:
+                slot.h2d_done.synchronize()              # the slot's previous upload has left the staging buffer
             slot.staging.copy_(frames)
             frames = slot.staging
         with torch.cuda.stream(self.copy_stream):
@@ -75,15 +77,19 @@ class BatchPipeline(object):
             slot.u8.copy_(frames, non_blocking=True)
             slot.h2d_done.record(self.copy_stream)
         compute.wait_event(slot.h2d_done)
+        if slot.used:
+            compute.wait_event(slot.side_done)           # the slot's previous gather / download have read its records
         self.det.run_batch(slot.u8, self.cam, to_host=False, out=(slot.pbuf.poses, slot.pbuf.n_valid))
         slot.compute_done.record(compute)
         slot.used = True
-        slot.pbuf.all_gather(self.group)
-        if self.to_host:                                 # download on its own stream: the next batch's kernels do not queue behind it
-            slot.gather_done.record(compute)
-            with torch.cuda.stream(self.d2h_stream):
-                self.d2h_stream.wait_event(slot.gather_done)
+        # the all-gather and the download run on a side stream: the next batch's kernels neither queue behind the copy nor
+        # wait for a slower peer rank (the collective couples the ranks once per batch, not once per kernel queue)
+        with torch.cuda.stream(self.side_stream):
+            self.side_stream.wait_event(slot.compute_done)
+            slot.pbuf.all_gather(self.group)
+            if self.to_host:
                 slot.pbuf.to_host(sync=False)
+            slot.side_done.record(self.side_stream)
         self._queue.append(slot)
 
     def collect(self):
@@ -93,4 +99,5 @@ class BatchPipeline(object):
         if self.to_host:
             slot.pbuf._evt.synchronize()
             return slot.pbuf.host_views()
+        torch.cuda.current_stream(self.device).wait_event(slot.side_done)
         return slot.pbuf.views(slot.pbuf.gathered)

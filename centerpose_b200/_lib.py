@@ -79,6 +79,7 @@ class CpDecodeParams(ctypes.Structure):
         ("visible_thresh", ctypes.c_int32), ("opencv_return", ctypes.c_int32),
         ("apply_sigmoid", ctypes.c_int32), ("use_pnp", ctypes.c_int32),
         ("vis_thresh", ctypes.c_float), ("balance", ctypes.c_float), ("modern_bool_semantics", ctypes.c_int32),
+        ("test_scale", ctypes.c_float), ("num_scales", ctypes.c_int32),
     ]
 
 

@@ -224,16 +224,52 @@ __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
   __shared__ double nb_bbox[KM][4];
   __shared__ double nb_score[KM];
   __shared__ int nb_perm[KM];
+  __shared__ int c_src[KM];       // candidate k of the image = entry (c_src / K, c_src % K) of the per-class top-K lists
   __shared__ int s_n0, s_n1;
 
   float* dets = a.dets + (size_t)b * K * CP_DETS_RECORD;
   float* poses = a.poses + (size_t)b * K * CP_POSE_RECORD;
   const double* meta = a.meta + (size_t)b * CP_META_DOUBLES;
 
+  // ---------------- decode.py:52-68 _topk: the K best of the num_classes x K per-class candidates.  Every per-class list
+  // is sorted (value descending, index ascending), so the rank of a candidate in the merged order (value descending,
+  // flat index class * K + k ascending) is a sum of binary searches; ranks are distinct, the first K fill c_src.
+  if (P.num_classes == 1) {
+    for (int k = tid; k < K; k += NT) c_src[k] = k;
+  } else {
+    const float* pv = a.peak_val + (size_t)b * CH * K;
+    for (int f = tid; f < P.num_classes * K; f += NT) {
+      const int c = f / K, kk = f - c * K;
+      const float v = pv[f];
+      int rank = 0;
+      for (int c2 = 0; c2 < P.num_classes; ++c2) {
+        const float* l = pv + (size_t)c2 * K;
+        int lo = 0, hi = K;                   // number of entries of list c2 that are > v
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (l[mid] > v) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+        if (c2 < c) {                         // equal values of an earlier class come first
+          int lo2 = lo, hi2 = K;
+          while (lo2 < hi2) {
+            const int mid = (lo2 + hi2) >> 1;
+            if (l[mid] >= v) lo2 = mid + 1; else hi2 = mid;
+          }
+          rank += lo2 - lo;
+        } else if (c2 == c) {
+          rank += kk - lo;                    // equal values of the own class with a lower index
+        }
+      }
+      if (rank < K) c_src[rank] = f;
+    }
+  }
+  __syncthreads();
   // ---------------- phase A: centres (decode.py:83-109, 304-345)
   for (int k = tid; k < K; k += NT) {
-    const int ind = a.peak_idx[((size_t)b * CH + 0) * K + k];
-    const float score = a.peak_val[((size_t)b * CH + 0) * K + k];
+    const int src = c_src[k];
+    const int ind = a.peak_idx[(size_t)b * CH * K + src];
+    const float score = a.peak_val[(size_t)b * CH * K + src];
     const float xs = (float)(ind % W), ys = (float)(ind / W);
     float* d = dets + (size_t)k * CP_DETS_RECORD;
     c_score[k] = score;
@@ -258,7 +294,7 @@ __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
       d[CP_D_BBOX + t] = bb[t];
     }
     d[CP_D_SCORE] = score;
-    d[CP_D_CLS] = 0.0f;
+    d[CP_D_CLS] = (float)(src / K);
     d[CP_D_IND] = (float)ind;
     for (int t = 0; t < 3; ++t) {
       d[CP_D_OBJ_SCALE + t] = a.h.scale ? gatherf(a.h.scale, b, 3, t, HW, ind) : 0.0f;
@@ -390,6 +426,11 @@ __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
   const double tx = (double)cxf - aff * (double)d0x, ty = (double)cyf - aff * (double)d0y;
   const float ratio = (float)(meta[2] / (double)max(W, H));   // s / max(w, h), rounded once to float32
   const double img_w = meta[3], img_h = meta[4];
+  // multi-scale testing (object_pose.py:171-177): the image-space coordinates of a scale != 1 pass are divided by the
+  // scale as float32 values, `(np.array(v, np.float32) / scale).tolist()`, before merge_outputs / the PnP see them
+  const float tsc = P.test_scale > 0.0f ? P.test_scale : 1.0f;      // 0 (a zero-initialised struct) means 1
+  const bool rescale = tsc != 1.0f;
+  auto unscale = [&](double v) -> double { return rescale ? (double)__fdiv_rn((float)v, tsc) : v; };
 
   // ---------------- phase D: score filter (object_pose.py:188-191); scores are sorted descending
   if (tid == 0) {
@@ -403,11 +444,11 @@ __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
     for (int p = 0; p < 2; ++p) {
       float x = c_bbox[i][2 * p], y = c_bbox[i][2 * p + 1];
       if (x == SENT && y == SENT) {
-        nb_bbox[i][2 * p] = -10000.0;
-        nb_bbox[i][2 * p + 1] = -10000.0;
+        nb_bbox[i][2 * p] = unscale(-10000.0);
+        nb_bbox[i][2 * p + 1] = unscale(-10000.0);
       } else {
-        nb_bbox[i][2 * p] = aff * (double)x + tx;
-        nb_bbox[i][2 * p + 1] = aff * (double)y + ty;
+        nb_bbox[i][2 * p] = unscale(aff * (double)x + tx);
+        nb_bbox[i][2 * p + 1] = unscale(aff * (double)y + ty);
       }
     }
     nb_score[i] = (double)c_score[i];
@@ -417,7 +458,7 @@ __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
   // ---------------- phase E: Gaussian soft-NMS (sequential by definition)
   if (tid == 0) {
     int n1 = n0;
-    if (P.nms && n0 > 0) n1 = pose::soft_nms(&nb_bbox[0][0], nb_score, nb_perm, n0, (double)P.vis_thresh);
+    if ((P.nms || P.num_scales > 1) && n0 > 0) n1 = pose::soft_nms(&nb_bbox[0][0], nb_score, nb_perm, n0, (double)P.vis_thresh);
     s_n1 = n1;
     a.n_valid[b] = n1;
   }
@@ -433,8 +474,20 @@ __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
     o[CP_P_CLS] = d[CP_D_CLS];
     o[CP_P_SRC_INDEX] = (float)k;
     for (int t = 0; t < 4; ++t) o[CP_P_BBOX + t] = (float)nb_bbox[i][t];
-    o[CP_P_CT] = (float)((nb_bbox[i][0] + nb_bbox[i][2]) / 2.0);
-    o[CP_P_CT + 1] = (float)((nb_bbox[i][1] + nb_bbox[i][3]) / 2.0);
+    if (!rescale) {
+      o[CP_P_CT] = (float)((nb_bbox[i][0] + nb_bbox[i][2]) / 2.0);
+      o[CP_P_CT + 1] = (float)((nb_bbox[i][1] + nb_bbox[i][3]) / 2.0);
+    } else {      // post_process.py:40 computes `ct` from the bbox BEFORE object_pose.py:171-177 divides the bbox
+      double ub[4];
+      for (int p = 0; p < 2; ++p) {
+        const float x = c_bbox[k][2 * p], y = c_bbox[k][2 * p + 1];
+        const bool sent = (x == SENT && y == SENT);
+        ub[2 * p] = sent ? -10000.0 : aff * (double)x + tx;
+        ub[2 * p + 1] = sent ? -10000.0 : aff * (double)y + ty;
+      }
+      o[CP_P_CT] = (float)((ub[0] + ub[2]) / 2.0);
+      o[CP_P_CT + 1] = (float)((ub[1] + ub[3]) / 2.0);
+    }
     double kps[16], dmean[16], hmean[16];
     for (int j = 0; j < J; ++j) {
       const int offs[3] = {CP_D_KPS, CP_D_KPS_DISP_MEAN, CP_D_KPS_HM_MEAN};
@@ -442,11 +495,11 @@ __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
       for (int q = 0; q < 3; ++q) {
         float x = d[offs[q] + 2 * j], y = d[offs[q] + 2 * j + 1];
         if (x == SENT && y == SENT) {
-          dst[q][2 * j] = -10000.0;
-          dst[q][2 * j + 1] = -10000.0;
+          dst[q][2 * j] = unscale(-10000.0);
+          dst[q][2 * j + 1] = unscale(-10000.0);
         } else {
-          dst[q][2 * j] = aff * (double)x + tx;
-          dst[q][2 * j + 1] = aff * (double)y + ty;
+          dst[q][2 * j] = unscale(aff * (double)x + tx);
+          dst[q][2 * j + 1] = unscale(aff * (double)y + ty);
         }
       }
     }
@@ -457,13 +510,20 @@ __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
       o[CP_P_KPS_HM_STD + t] = __fmul_rn(__fmul_rn(d[CP_D_KPS_HM_STD + t], ratio), 0.32f);
       o[CP_P_KPS_DISP_STD + t] = __fmul_rn(__fmul_rn(d[CP_D_KPS_DISP_STD + t], ratio), 0.32f);
       o[CP_P_TRACKING_HP + t] = __fmul_rn(d[CP_D_TRACKING_HP + t], ratio);
+      if (rescale) {
+        o[CP_P_KPS_DISP_STD + t] = __fdiv_rn(o[CP_P_KPS_DISP_STD + t], tsc);
+        o[CP_P_TRACKING_HP + t] = __fdiv_rn(o[CP_P_TRACKING_HP + t], tsc);
+      }
     }
     for (int t = 0; t < J; ++t) o[CP_P_KPS_HM_HEIGHT + t] = d[CP_D_KPS_HM_HEIGHT + t];
     for (int t = 0; t < 3; ++t) {
       o[CP_P_OBJ_SCALE + t] = d[CP_D_OBJ_SCALE + t];
       o[CP_P_OBJ_SCALE_UNC + t] = d[CP_D_OBJ_SCALE_UNC + t];
     }
-    for (int t = 0; t < 2; ++t) o[CP_P_TRACKING + t] = __fmul_rn(d[CP_D_TRACKING + t], ratio);
+    for (int t = 0; t < 2; ++t) {
+      o[CP_P_TRACKING + t] = __fmul_rn(d[CP_D_TRACKING + t], ratio);
+      if (rescale) o[CP_P_TRACKING + t] = __fdiv_rn(o[CP_P_TRACKING + t], tsc);
+    }
   }
   // ---------------- phase G: PnP, one WARP per surviving detection
   {
@@ -491,8 +551,8 @@ __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
             X0 = aff * (double)x + tx;
             Y0 = aff * (double)y + ty;
           }
-          pts[2 * lane] = X0;
-          pts[2 * lane + 1] = Y0;
+          pts[2 * lane] = unscale(X0);
+          pts[2 * lane + 1] = unscale(Y0);
         }
         __syncwarp();
         float sc[3] = {d[CP_D_OBJ_SCALE], d[CP_D_OBJ_SCALE + 1], d[CP_D_OBJ_SCALE + 2]};
@@ -538,7 +598,9 @@ WsLayout ws_layout(const cp_decode_params* p) {
 int validate(const cp_decode_params* p) {
   if (!p) return fail(CP_ERR_INVALID, "decode: null params");
   if (p->batch <= 0 || p->out_h <= 0 || p->out_w <= 0) return fail(CP_ERR_INVALID, "decode: bad shape");
-  if (p->num_classes != 1) return fail(CP_ERR_INVALID, "decode: num_classes must be 1 (Objectron single-category heads)");
+  if (p->num_classes < 1 || p->num_classes > CP_MAX_CLASSES)
+    return fail(CP_ERR_INVALID, "decode: num_classes must be in 1..CP_MAX_CLASSES");
+  if (!(p->test_scale >= 0.0f)) return fail(CP_ERR_INVALID, "decode: test_scale must be > 0 (0 or 1: single-scale testing)");
   if (p->num_joints != 8) return fail(CP_ERR_INVALID, "decode: num_joints must be 8");
   if (p->K <= 0 || p->K > CP_MAX_K) return fail(CP_ERR_INVALID, "decode: K must be in 1..128");
   if ((size_t)p->out_h * p->out_w < (size_t)p->K) return fail(CP_ERR_INVALID, "decode: map smaller than K");

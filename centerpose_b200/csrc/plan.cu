@@ -1035,6 +1035,8 @@ int cp_infer(cp_plan* P, int32_t batch, const float* images, const float* pre_im
   cp_heads hd{};
   for (int h = 0; h < P->cfg.num_heads; ++h) {
     const std::string& n = P->head_names[h];
+    if (n == "hm" && P->cfg.head_channels[h] != prm->num_classes)
+      return fail(CP_ERR_INVALID, "cp_infer: prm->num_classes differs from the plan's hm channels");
     if (n == "hm") hd.hm = hp[h];
     else if (n == "wh") hd.wh = hp[h];
     else if (n == "hps") hd.hps = hp[h];

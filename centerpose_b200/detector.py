@@ -189,7 +189,7 @@ class ObjectPoseDetector(object):
         return make_meta(batch, meta["c"], meta["s"], meta["width"], meta["height"], cam)
 
     def process(self, images, pre_images=None, pre_hms=None, pre_hm_hp=None, pre_inds=None, return_time=False,
-                meta=None):
+                meta=None, scale=1.0):
         """object_pose.py:131-165: network + sigmoid + decode.  Returns
         (output, dets[, forward_time]); the pose records of the fused stage are
         kept on `self._last` (host) / `self._last_dev` (device) for post_process / merge / PnP / tracking."""
@@ -197,7 +197,7 @@ class ObjectPoseDetector(object):
         output = self.model(images, pre_images, pre_hms, pre_hm_hp)[-1]
         torch.cuda.synchronize()
         forward_time = time.time()
-        prm = decode_params(self.opt)
+        prm = decode_params(self.opt, test_scale=float(scale))
         metat = self._meta_tensor(meta if meta is not None else self._dummy_meta(images), images.shape[0]).to(images.device)
         dets, poses, n_valid = decode_pnp(output, metat, prm, want_dets=True)
         output["hm"] = output["hm"].sigmoid_()
@@ -223,9 +223,10 @@ class ObjectPoseDetector(object):
         import cv2
         load_time, pre_time, net_time, dec_time, post_time = 0, 0, 0, 0, 0
         merge_time, track_time, pnp_time, tot_time = 0, 0, 0, 0
-        if len(self.scales) != 1 or self.scales[0] != 1.0:
-            raise NotImplementedError("multi-scale testing merges detections on the host; only test_scales=[1] is supported")
         tracking = bool(getattr(self.opt, "tracking_task", False))
+        if tracking and (len(self.scales) != 1 or self.scales[0] != 1.0):
+            raise NotImplementedError("CenterPoseTrack runs at test_scales=[1] (the reference re-initialises the tracker "
+                                      "state once per scale, base_detector.py:440-449)")
         start_time = time.time()
         pre_processed = preprocessed_flag
         if isinstance(image_or_path_or_tensor, np.ndarray):
@@ -240,35 +241,43 @@ class ObjectPoseDetector(object):
         loaded_time = time.time()
         load_time += loaded_time - start_time
 
-        scale = self.scales[0]
-        if not pre_processed:
-            images, meta = self.pre_process(image, scale, meta_inp)
-        else:
-            images = torch.from_numpy(np.expand_dims(image, axis=0))
-            meta = meta_inp
-        images = self._to_device(images)
+        # base_detector.py:421-497: one pass per test scale.  merge_outputs (object_pose.py:184-197) reads detections[0],
+        # i.e. only the FIRST scale contributes results (with the soft-NMS forced on when several scales are listed); the
+        # other passes still run because run() returns the `output` maps of the last one.
+        first = None
+        for si, scale in enumerate(self.scales):
+            scale_start_time = time.time()
+            if not pre_processed:
+                images, meta = self.pre_process(image, scale, meta_inp)
+            else:
+                images = torch.from_numpy(np.expand_dims(image, axis=0))
+                meta = meta_inp
+            images = self._to_device(images)
 
-        pre_hms, pre_hm_hp, pre_inds = None, None, None
-        if tracking:
-            if self.pre_images is None:                       # base_detector.py:444-449
-                print("Initialize tracking!")
-                self.pre_images = images
-                self.tracker.init_track(meta)
-            if self.opt.pre_hm or self.opt.pre_hm_hp:         # :456-462, rendered on the device from the tracker state
-                if "trans_input" not in meta:
-                    raise ValueError("tracking needs meta['trans_input'] (pre_process provides it)")
-                metat = self._meta_tensor(meta).to(images.device)
-                pre_hms, pre_hm_hp = self.tracker.render(metat, meta["trans_input"], images.shape[2], images.shape[3])
-        torch.cuda.synchronize()
-        pre_process_time = time.time()
-        pre_time += pre_process_time - loaded_time
+            pre_hms, pre_hm_hp, pre_inds = None, None, None
+            if tracking:
+                if self.pre_images is None:                       # base_detector.py:444-449
+                    print("Initialize tracking!")
+                    self.pre_images = images
+                    self.tracker.init_track(meta)
+                if self.opt.pre_hm or self.opt.pre_hm_hp:         # :456-462, rendered on the device from the tracker state
+                    if "trans_input" not in meta:
+                        raise ValueError("tracking needs meta['trans_input'] (pre_process provides it)")
+                    metat = self._meta_tensor(meta).to(images.device)
+                    pre_hms, pre_hm_hp = self.tracker.render(metat, meta["trans_input"], images.shape[2], images.shape[3])
+            torch.cuda.synchronize()
+            pre_process_time = time.time()
+            pre_time += pre_process_time - scale_start_time
 
-        output, dets, forward_time = self.process(images, self.pre_images if tracking else None, pre_hms, pre_hm_hp,
-                                                  pre_inds, return_time=True, meta=meta)
-        torch.cuda.synchronize()
-        net_time += forward_time - pre_process_time
-        decode_time = time.time()
-        dec_time += decode_time - forward_time
+            output, dets, forward_time = self.process(images, self.pre_images if tracking else None, pre_hms, pre_hm_hp,
+                                                      pre_inds, return_time=True, meta=meta, scale=scale)
+            torch.cuda.synchronize()
+            net_time += forward_time - pre_process_time
+            decode_time = time.time()
+            dec_time += decode_time - forward_time
+            if si == 0:
+                first = (self._last, self._last_dev, meta)
+        self._last, self._last_dev, meta = first
 
         # post_process + merge + PnP already happened inside cp_decode_pnp; unpack the records
         poses, n_valid = self._last
@@ -478,7 +487,11 @@ class ObjectPoseDetector(object):
             self._meta_key = mkey
         meta = self._meta_dev
         eng = self.model.engine(B, x.shape[2], x.shape[3], x.device)
-        prm = decode_params(self.opt)
+        # the batched path pre-processes at scale 1 (what every shipped configuration uses); results of a multi-scale
+        # opt are those of test_scales[0] (object_pose.py:188), which run() reproduces frame by frame
+        if float(self.scales[0]) != 1.0:
+            raise NotImplementedError("run_batch pre-processes at scale 1; use run() for test_scales[0] != 1")
+        prm = decode_params(self.opt, test_scale=1.0)
         if track:
             if not getattr(self.opt, "tracking_task", False):
                 raise ValueError("run_batch(track=True) needs a tracking model (opt.tracking_task)")

@@ -28,12 +28,17 @@ def decode_params(opt=None, **over):
     """cp_decode_params from a reference-style `opt` (or keyword overrides)."""
     g = lambda n, d: over.get(n, getattr(opt, n, d) if opt is not None else d)
     p = _lib.CpDecodeParams()
-    p.num_classes = 1
+    p.num_classes = int(g("num_classes", 1))
     p.num_joints = 8
     p.K = int(g("K", 100))
     p.rep_mode = int(g("rep_mode", 1))
     p.use_moments = int(bool(g("tracking_task", False)) or bool(g("refined_Kalman", False)))
-    p.nms = int(bool(g("nms", True)) or len(g("test_scales", [1.0])) > 1)
+    scales = list(g("test_scales", [1.0]))
+    p.nms = int(bool(g("nms", True)))
+    # object_pose.py:188-193: merge_outputs reads detections[0] (the first scale) and forces the soft-NMS when several
+    # scales were requested; `test_scale` is the scale of the pass being decoded (detector.run passes it per pass)
+    p.num_scales = len(scales)
+    p.test_scale = float(over.get("test_scale", scales[0] if scales else 1.0))
     cat = g("c", "chair")
     if cat not in _VISIBLE:
         raise ValueError("unknown category '%s' (cuboid_pnp_shell.py:59-66)" % cat)

@@ -169,7 +169,8 @@ def planted_heads(n_obj=3, seed=0, heads=None, out_h=128, out_w=128, down=4, cam
         taken.append((cx, cy))
         pk = peak - 0.03 * len(truth["R"])
         g = pk * np.exp(-((xx - ix) ** 2 + (yy - iy) ** 2) / (2 * sigma * sigma))
-        out["hm"][0] = np.maximum(out["hm"][0], g)
+        cls = len(truth["R"]) % out["hm"].shape[0]       # multi-class hm (opt.num_classes > 1): objects take classes in turn
+        out["hm"][cls] = np.maximum(out["hm"][cls], g)
         if "reg" in out:
             out["reg"][:, iy, ix] = [cx - ix, cy - iy]
         out["wh"][:, iy, ix] = [(x1 - x0) * 1.1 + 2, (y1 - y0) * 1.1 + 2]

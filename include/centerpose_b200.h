@@ -79,6 +79,7 @@ enum cp_precision {
 #define CP_DETS_RECORD 128  /* floats per candidate slot in `dets`   */
 #define CP_META_DOUBLES 16  /* doubles per image in `meta`           */
 #define CP_MAX_K 128
+#define CP_MAX_CLASSES 80   /* hm channels the decode stage merges (decode.py:52-68 _topk) */
 
 typedef struct cp_plan cp_plan;
 
@@ -161,7 +162,8 @@ typedef struct cp_heads {
 
 typedef struct cp_decode_params {
   int32_t batch, out_h, out_w;
-  int32_t num_classes;     /* 1 (Objectron single-category models, opts.py:434)           */
+  int32_t num_classes;     /* opt.num_classes = hm channels, 1..CP_MAX_CLASSES (Objectron models: 1, opts.py:434): per-class
+                            * top-K, then the K best of the num_classes x K candidates (decode.py:52-68)               */
   int32_t num_joints;      /* 8                                                            */
   int32_t K;               /* opt.K = 100, <= CP_MAX_K                                     */
   int32_t rep_mode;        /* opt.rep_mode: 0,1,3,4 (2 = random GMM sampling, unsupported) */
@@ -179,6 +181,11 @@ typedef struct cp_decode_params {
                             * 1: what the unmodified reference computes on torch >= 1.2 (bool + bool is a logical OR, so
                             * `== 7` is never true): the heat-map keypoint representation is never used, kps_heatmap_* stay
                             * at the -10000 sentinel and the PnP sees the 8 displacement points only.                 */
+  float test_scale;        /* opt.test_scales[0] (1; 0 is read as 1): the scale the frame was resized by in pre_process; != 1 divides bbox,
+                            * kps, kps_displacement_mean / _std, kps_heatmap_mean, tracking and tracking_hp by it in
+                            * float32 before soft-NMS and the PnP (object_pose.py:171-177)                              */
+  int32_t num_scales;      /* len(opt.test_scales): > 1 forces the soft-NMS (object_pose.py:193); merge_outputs keeps the
+                            * detections of test_scales[0] only (object_pose.py:188 reads detections[0])               */
 } cp_decode_params;
 
 /* meta: device fp64 [batch, CP_META_DOUBLES] per image:

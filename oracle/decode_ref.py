@@ -287,8 +287,12 @@ def map_to_image(pts, c, s, out_w, out_h):
     return out
 
 
-def post_process(dets, c, s, out_h, out_w):
-    """utils/post_process.py:12-68 (Inference=True) for one image: list of K dicts."""
+SCALED_KEYS = ("bbox", "kps", "kps_displacement_std", "tracking", "tracking_hp", "kps_displacement_mean", "kps_heatmap_mean")
+
+
+def post_process(dets, c, s, out_h, out_w, scale=1):
+    """utils/post_process.py:12-68 (Inference=True) for one image: list of K dicts, followed by the division of
+    detectors/object_pose.py:171-177 when the pass ran at a test scale != 1 (`ct` and kps_heatmap_std stay as they are)."""
     coefficient = 0.32
     K = dets["scores"].shape[0]
     ssc = (F32(s[0]) if isinstance(s, (np.ndarray, list)) else s)
@@ -312,6 +316,9 @@ def post_process(dets, c, s, out_h, out_w):
         item["kps_heatmap_mean"] = map_to_image(dets["kps_heatmap_mean"][j], c, s, out_w, out_h).reshape(-1)
         item["kps_heatmap_std"] = (dets["kps_heatmap_std"][j] * ratio * coefficient).flatten()
         item["kps_heatmap_height"] = dets["kps_heatmap_height"][j]
+        if scale != 1:
+            for k in SCALED_KEYS:
+                item[k] = (np.array(item[k], np.float32) / scale).tolist()
         preds.append(item)
     return preds
 

@@ -53,6 +53,13 @@ DECODE_CASES = [
     # the same scene as decode_rep1_3obj evaluated by the UNMODIFIED reference on the torch of this image (>= 1.2), i.e.
     # WITHOUT ref_shims.legacy_bool_arith: `mask_2 == 7` is all-False there (cp_decode_params.modern_bool_semantics = 1)
     ("decode_rep1_3obj_modern_torch", False, 1, 3, 0.0, 2, 11, "chair", (), True),
+    # opt.num_classes = 3: per-class top-K, then the K best of the 3 x K candidates (decode.py:52-68), `cls` in the results
+    ("decode_cls3_rep1_6obj", False, 1, 6, 1.0, 2, 71, "chair", (), False, {"num_classes": 3}),
+    # multi-scale testing, opt.test_scales = [0.75, 1]: merge_outputs keeps detections[0] (the 0.75 pass, coordinates divided
+    # by 0.75 as float32) and forces the soft-NMS (object_pose.py:171-197); frame 512 x 512 resized to 384 x 384
+    ("decode_scale075_rep1_3obj", False, 1, 3, 0.5, 2, 81, "chair", (), False, {"test_scales": [0.75, 1.0]}),
+    # a single scale != 1 with --nms off: division only; rep_mode 0 feeds the divided `kps` to the PnP
+    ("decode_scale125_rep0_nonms", False, 0, 4, 1.0, 1, 91, "cup", (), False, {"test_scales": [1.25], "nms": False}),
 ]
 
 
@@ -116,7 +123,7 @@ def result_to_record(d, k_src=-1):
     return r
 
 
-def reference_pipeline(heads_b, opt, cam, width, height, c, s, legacy=True):
+def reference_pipeline(heads_b, opt, cam, width, height, c, s, legacy=True, scale=1):
     """Runs the reference's process()-after-network, post_process, merge_outputs and the
     PnP loop of run() on one image's head tensors."""
     from lib.models.decode import object_pose_decode
@@ -134,13 +141,25 @@ def reference_pipeline(heads_b, opt, cam, width, height, c, s, legacy=True):
             hp_offset=T["hp_offset"], tracking=T.get("tracking"), tracking_hp=T.get("tracking_hp"), opt=opt,
             Inference=True)
     dets = {k: v.detach().cpu().numpy() for k, v in dets.items()}
-    pp = object_pose_post_process(copy.deepcopy(dets), [c], [s], 128, 128, opt, Inference=True)[0]
-    for i, d in enumerate(pp):
-        d["_k"] = i
-    results = np.array([d for d in pp if d["score"] > opt.vis_thresh])
-    if opt.nms and len(results):
-        keep = soft_nms_nvidia(results, Nt=0.5, method=2, threshold=opt.vis_thresh)
-        results = results[keep]
+    if scale != 1 or len(opt.test_scales) > 1:
+        # the reference's own detector methods, unbound (they only read self.opt): post_process incl. the division by the
+        # test scale (object_pose.py:167-182) and merge_outputs on [detections of scale 0] (:184-197)
+        from lib.detectors.object_pose import ObjectPoseDetector as RefDet
+        import types
+        fake = types.SimpleNamespace(opt=opt)
+        m = {"c": c, "s": s, "out_height": 128, "out_width": 128}
+        pp = RefDet.post_process(fake, copy.deepcopy(dets), m, scale)
+        for i, d in enumerate(pp):
+            d["_k"] = i
+        results = RefDet.merge_outputs(fake, [pp]) if any(d["score"] > opt.vis_thresh for d in pp) else np.array([])
+    else:
+        pp = object_pose_post_process(copy.deepcopy(dets), [c], [s], 128, 128, opt, Inference=True)[0]
+        for i, d in enumerate(pp):
+            d["_k"] = i
+        results = np.array([d for d in pp if d["score"] > opt.vis_thresh])
+        if opt.nms and len(results):
+            keep = soft_nms_nvidia(results, Nt=0.5, method=2, threshold=opt.vis_thresh)
+            results = results[keep]
     meta = {"camera_matrix": cam, "width": width, "height": height}
     recs = []
     for d in results:
@@ -166,19 +185,30 @@ def make_decode(only=None):
         name, trk, rep, nobj, dis, B, seed, cat = case[:8]
         drop = tuple(case[8]) if len(case) > 8 else ()
         modern = bool(case[9]) if len(case) > 9 else False
+        extra = dict(case[10]) if len(case) > 10 else {}
         if only and name not in only:
             continue
         opt = ref_shims.make_opt("dla_34", tracking_task=trk, rep_mode=rep, c=cat)
-        heads = synth.TRACKING_HEADS if trk else synth.DEFAULT_HEADS
+        ncls = int(extra.get("num_classes", 1))
+        scales = [float(v) for v in extra.get("test_scales", [1.0])]
+        opt.num_classes = ncls
+        opt.test_scales = scales
+        opt.nms = bool(extra.get("nms", opt.nms))
+        heads = dict(synth.TRACKING_HEADS if trk else synth.DEFAULT_HEADS)
+        heads["hm"] = ncls
         hb, truths = synth.planted_batch(B, n_obj=nobj, seed=seed, heads=heads, disagree_px=dis, drop_joints=drop)
         cam = truths[0]["cam"]
-        c = np.array([256., 256.], np.float32)
+        # base_detector.py:110-114 (fix_res): c = the centre of the RESIZED frame, s = max(height, width) of the original
+        new = int(512 * scales[0])
+        c = np.array([new / 2., new / 2.], np.float32)
         s = 512.0
         out = {"tracking": int(trk), "rep_mode": rep, "n_obj": nobj, "disagree_px": dis, "batch": B, "seed": seed,
                "category": cat, "vis_thresh": float(opt.vis_thresh), "cam": cam,
-               "drop_joints": np.array(drop, np.int64), "modern_bool": int(modern)}
+               "drop_joints": np.array(drop, np.int64), "modern_bool": int(modern), "num_classes": ncls,
+               "test_scales": np.array(scales, np.float64), "nms": int(opt.nms), "c": c, "s": s}
         for b in range(B):
-            dets, recs = reference_pipeline({k: v[b] for k, v in hb.items()}, opt, cam, 512, 512, c, s, legacy=not modern)
+            dets, recs = reference_pipeline({k: v[b] for k, v in hb.items()}, opt, cam, 512, 512, c, s, legacy=not modern,
+                                            scale=scales[0])
             for k, v in dets.items():
                 out["dets%d_%s" % (b, k)] = v[0]
             out["records%d" % b] = recs

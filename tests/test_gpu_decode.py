@@ -10,12 +10,13 @@ from centerpose_b200 import _lib as L
 from centerpose_b200 import synth
 from centerpose_b200.detector import dets_to_dict
 from oracle import decode_ref
-from tests.util import DETS_KEYS, compare_records, decode_case_inputs, golden, oracle_records
+from tests.util import DETS_KEYS, compare_records, decode_case_geometry, decode_case_inputs, golden, oracle_records
 
 pytestmark = pytest.mark.gpu
 
 CASES = ["decode_rep1_3obj", "decode_rep1_10obj_noisy", "decode_rep0_3obj", "decode_rep4_2obj", "decode_rep4_5pts_epnp",
-         "decode_track_rep1_3obj", "decode_rep1_3obj_modern_torch"]
+         "decode_track_rep1_3obj", "decode_rep1_3obj_modern_torch", "decode_cls3_rep1_6obj", "decode_scale075_rep1_3obj",
+         "decode_scale125_rep0_nonms"]
 C512 = np.array([256., 256.], np.float32)
 
 
@@ -34,8 +35,9 @@ def test_matches_reference_golden(name, cplib):
     g = golden(name)
     hb, truths = decode_case_inputs(g)
     modern = bool(int(g["modern_bool"])) if "modern_bool" in g.files else False
-    dets, poses, n_valid = _run(hb, g["cam"], int(g["rep_mode"]), bool(int(g["tracking"])), str(g["category"]),
-                                modern_bool_semantics=modern)
+    c, s, scales, nms = decode_case_geometry(g)
+    dets, poses, n_valid = _run(hb, g["cam"], int(g["rep_mode"]), bool(int(g["tracking"])), str(g["category"]), c=c, s=s,
+                                modern_bool_semantics=modern, num_classes=hb["hm"].shape[1], test_scales=scales, nms=nms)
     dd = dets_to_dict(dets)
     for b in range(int(g["batch"])):
         valid = g["dets%d_scores" % b][:, 0] > 0.05

@@ -46,6 +46,57 @@ def test_run_contract_and_consistency(cplib):
         assert b[0].shape == (9, 2) and b[1].shape == (9, 3) and b[3].shape == (9, 2) and "location" in b[4]
 
 
+def test_run_multi_scale(cplib):
+    """opt.test_scales = [0.75, 1.0] (base_detector.py:421-497, object_pose.py:167-197): run() returns the detections of
+    the FIRST scale -- coordinates divided by 0.75, soft-NMS forced on -- and the head maps of the LAST pass."""
+    det, opt = _detector(head_gain=1.0)
+    img = synth.synthetic_frames(1, 600, 800, seed=3)[0]
+    # (_detector's default weights saturate every score at 1.0: an all-ties scene.  Calibrate the heat-map biases so that
+    # a handful of distinct peaks pass the thresholds -- setup only, as in bench.py)
+    x0, _ = det.pre_process(img, 0.75, {})
+    with torch.no_grad():
+        synth.calibrate_head_bias(det.model, det.model(x0.cuda())[-1], target=6)
+    opt.test_scales = [0.75, 1.0]
+    opt.nms = False
+    det.scales = opt.test_scales
+    cam = np.array([[663.0287679036459, 0, 300.2775065104167], [0, 663.0287679036459, 395.00066121419275], [0, 0, 1]])
+    ret = det.run(img, meta_inp={"camera_matrix": cam})
+    assert set(ret) == KEYS
+    # the heads of the 0.75 pass, recomputed through the public pieces, decoded by the CPU oracle at that scale
+    images, meta = det.pre_process(img, 0.75, {"camera_matrix": cam})
+    assert tuple(meta["c"]) == (300.0, 225.0) and meta["s"] == 800.0
+    out, _ = det.process(images.cuda(), meta=meta, scale=0.75)
+    heads = {k: out[k][0].cpu().numpy() for k in opt.heads}
+    for k in ("hm", "hm_hp"):
+        p = np.clip(heads[k].astype(np.float64), 1e-12, 1 - 1e-7)
+        heads[k] = np.log(p / (1 - p)).astype(np.float32)
+    prm = decode_ref.DecodeParams(rep_mode=1, vis_thresh=opt.vis_thresh, category=opt.c, nms=False, num_scales=2)
+    _, want = oracle_records(heads, prm, cam, 800, 600, meta["c"], meta["s"], L, scale=0.75)
+    assert len(ret["results"]) == want.shape[0] and want.shape[0] > 0
+    # (the maps went through sigmoid and back, so soft-NMS scores agree to ~1e-4 and near-ties may swap places: match
+    # every result to its oracle record instead of relying on the order)
+    left = list(range(want.shape[0]))
+    for d in ret["results"]:
+        j = min(left, key=lambda q: np.abs(np.asarray(d["bbox"]) - want[q, L.P_BBOX:L.P_BBOX + 4]).max())
+        left.remove(j)
+        w = want[j]
+        assert abs(d["score"] - w[L.P_SCORE]) <= 1e-3, (d["score"], w[L.P_SCORE])
+        assert np.abs(np.asarray(d["bbox"]) - w[L.P_BBOX:L.P_BBOX + 4]).max() <= 0.05
+        assert np.abs(np.asarray(d["kps"]) - w[L.P_KPS:L.P_KPS + 16]).max() <= 0.05
+        assert np.abs(np.asarray(d["kps_displacement_mean"]) - w[L.P_KPS_DISP_MEAN:L.P_KPS_DISP_MEAN + 16]).max() <= 0.05
+    # last pass = scale 1.0: the returned maps are those of a plain single-scale run
+    opt.test_scales = [1.0]
+    det.scales = opt.test_scales
+    ret1 = det.run(img, meta_inp={"camera_matrix": cam})
+    assert torch.equal(ret["output"]["hm"], ret1["output"]["hm"])
+    with pytest.raises(NotImplementedError):
+        opt.test_scales = [0.5]
+        det.scales = opt.test_scales
+        det.run_batch(synth.synthetic_frames(1, 512, 512, seed=1), cam)
+    opt.test_scales = [1.0]
+    det.scales = opt.test_scales
+
+
 def test_run_batch_matches_run(cplib):
     """run() is run_batch() of one frame + unpacking: the same frame through both gives the same records, alone or inside
     a batch of four (K partition held fixed, see tests/util.py no_splitk)."""

@@ -9,16 +9,19 @@ import pytest
 from centerpose_b200 import _lib as L
 from centerpose_b200 import synth
 from oracle import decode_ref, pnp_ref
-from tests.util import DETS_KEYS, compare_records, decode_case_inputs, golden, oracle_records
+from tests.util import DETS_KEYS, compare_records, decode_case_geometry, decode_case_inputs, golden, oracle_records
 
 CASES = ["decode_rep1_3obj", "decode_rep1_10obj_noisy", "decode_rep0_3obj", "decode_rep4_2obj", "decode_rep4_5pts_epnp",
-         "decode_track_rep1_3obj", "decode_rep1_3obj_modern_torch"]
+         "decode_track_rep1_3obj", "decode_rep1_3obj_modern_torch", "decode_cls3_rep1_6obj", "decode_scale075_rep1_3obj",
+         "decode_scale125_rep0_nonms"]
 
 
 def _params(g):
+    _, _, scales, nms = decode_case_geometry(g)
     return decode_ref.DecodeParams(K=100, rep_mode=int(g["rep_mode"]), use_moments=bool(int(g["tracking"])),
                                    balance=2.0, vis_thresh=float(g["vis_thresh"]), category=str(g["category"]),
-                                   modern_bool=bool(int(g["modern_bool"])) if "modern_bool" in g.files else False)
+                                   modern_bool=bool(int(g["modern_bool"])) if "modern_bool" in g.files else False,
+                                   nms=nms, num_scales=len(scales))
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -26,9 +29,9 @@ def test_oracle_matches_reference_golden(name):
     g = golden(name)
     hb, truths = decode_case_inputs(g)
     prm = _params(g)
-    c, s = np.array([256., 256.], np.float32), 512.0
+    c, s, scales, _ = decode_case_geometry(g)
     for b in range(int(g["batch"])):
-        dets, recs = oracle_records({k: v[b] for k, v in hb.items()}, prm, g["cam"], 512, 512, c, s, L)
+        dets, recs = oracle_records({k: v[b] for k, v in hb.items()}, prm, g["cam"], 512, 512, c, s, L, scale=scales[0])
         valid = g["dets%d_scores" % b][:, 0] > 0.05          # the tied sub-threshold tail is order-undefined
         for k in DETS_KEYS:
             want = g["dets%d_%s" % (b, k)]

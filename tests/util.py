@@ -54,7 +54,9 @@ def dcn_case_inputs(g):
 
 def decode_case_inputs(g):
     from centerpose_b200 import synth
-    heads = synth.TRACKING_HEADS if int(g["tracking"]) else synth.DEFAULT_HEADS
+    heads = dict(synth.TRACKING_HEADS if int(g["tracking"]) else synth.DEFAULT_HEADS)
+    if "num_classes" in g.files:
+        heads["hm"] = int(g["num_classes"])
     drop = tuple(int(v) for v in g["drop_joints"]) if "drop_joints" in g.files else ()
     hb, truths = synth.planted_batch(int(g["batch"]), n_obj=int(g["n_obj"]), seed=int(g["seed"]), heads=heads,
                                      disagree_px=float(g["disagree_px"]), drop_joints=drop)
@@ -119,14 +121,21 @@ def compare_records(got, want, L, tol_px=TOL_KP_PX, tol_q=TOL_QUAT, check_pnp=Tr
     return err
 
 
-def oracle_records(heads_b, prm, cam, width, height, c, s, L):
+def decode_case_geometry(g):
+    """(c, s, scales, nms) of a decode_*.npz fixture; older fixtures are single-scale 512 x 512 frames with --nms."""
+    if "c" in g.files:
+        return (np.asarray(g["c"], np.float32), float(g["s"]), [float(v) for v in g["test_scales"]], bool(int(g["nms"])))
+    return np.array([256., 256.], np.float32), 512.0, [1.0], True
+
+
+def oracle_records(heads_b, prm, cam, width, height, c, s, L, scale=1):
     """Full oracle pipeline for one image -> (dets dict, [n,192] records)."""
     from oracle import decode_ref, pnp_ref
     import sys
     sys.path.insert(0, ROOT)
     from oracle.make_golden import result_to_record
     dets = decode_ref.decode(decode_ref.process_heads(heads_b), prm)
-    pp = decode_ref.post_process(dets, c, s, heads_b["hm"].shape[1], heads_b["hm"].shape[2])
+    pp = decode_ref.post_process(dets, c, s, heads_b["hm"].shape[1], heads_b["hm"].shape[2], scale=scale)
     for i, d in enumerate(pp):
         d["_k"] = i
     res = decode_ref.merge_outputs(pp, prm)

@@ -44,7 +44,7 @@ EXPORTS = [
     "cp_version", "cp_last_error", "cp_plan_create", "cp_plan_destroy", "cp_plan_load_weights",
     "cp_forward", "cp_plan_bytes", "cp_plan_forward_launches", "cp_decode_workspace_bytes",
     "cp_decode_pnp", "cp_infer", "cp_dcn_v2_forward", "cp_preprocess", "cp_plan_num_ops", "cp_plan_profile",
-    "cp_dcn_v2_forward_ex", "cp_conv2d",
+    "cp_dcn_v2_forward_ex", "cp_conv2d", "cp_dcn_v2_backward",
     "cp_preprocess_affine", "cp_tracker_create", "cp_tracker_destroy", "cp_tracker_reset", "cp_tracker_step", "cp_tracker_render",
 ]
 
@@ -130,6 +130,7 @@ def load():
                            ctypes.POINTER(vp), vp, vp, vp, vp]
     L.cp_dcn_v2_forward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.cp_dcn_v2_forward_ex.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    L.cp_dcn_v2_backward.argtypes = [vp] * 10 + [i32] * 6 + [vp]
     L.cp_conv2d.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     L.cp_preprocess.argtypes = [vp, vp, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_float),
                                 ctypes.POINTER(ctypes.c_float), vp]

@@ -70,6 +70,11 @@ __global__ void preprocess_kernel(const uint8_t* __restrict__ frames, float* __r
 }
 
 }  // namespace
+
+int dcn_v2_backward_impl(const float* input, const float* weight, const float* offset, const float* mask,
+                         const float* grad_output, float* grad_input, float* grad_offset, float* grad_mask,
+                         float* grad_weight, float* grad_bias, int B, int C, int H, int W, int Co, int prec,
+                         cudaStream_t s);      // dcn_bwd.cu
 }  // namespace cp
 
 using namespace cp;
@@ -134,6 +139,12 @@ static int run_igemm(IgemmParams& p, int prec, int Kreal, cudaStream_t s) {
   return rc;
 }
 
+}  // extern "C"
+namespace cp {
+int run_igemm_dispatch(IgemmParams& p, int prec, int Kreal, cudaStream_t s) { return run_igemm(p, prec, Kreal, s); }
+}  // namespace cp
+extern "C" {
+
 int cp_conv2d(const float* x, const float* weight, const float* bias, const float* residual, float* out, int32_t B,
               int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k, int32_t stride, int32_t pad, int32_t relu,
               int32_t precision, void* stream_) {
@@ -183,6 +194,23 @@ int cp_conv2d(const float* x, const float* weight, const float* bias, const floa
   } while (0);
   cudaFreeAsync(scratch, s);
   return rc;
+}
+
+int cp_dcn_v2_backward(const float* input, const float* weight, const float* offset, const float* mask,
+                       const float* grad_output, float* grad_input, float* grad_offset, float* grad_mask,
+                       float* grad_weight, float* grad_bias, int32_t B, int32_t C, int32_t H, int32_t W, int32_t Co,
+                       int32_t precision, void* stream_) {
+  int prec;
+  {
+    int rcp = prec_code(precision, &prec);
+    if (rcp) return rcp;
+  }
+  if (!input || !weight || !offset || !mask || !grad_output || !grad_input || !grad_offset || !grad_mask || !grad_weight ||
+      !grad_bias)
+    return fail(CP_ERR_INVALID, "cp_dcn_v2_backward: null argument");
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || Co <= 0) return fail(CP_ERR_INVALID, "cp_dcn_v2_backward: bad shape");
+  return dcn_v2_backward_impl(input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask, grad_weight,
+                              grad_bias, B, C, H, W, Co, prec, (cudaStream_t)stream_);
 }
 
 int cp_dcn_v2_forward(const float* input, const float* weight, const float* bias, const float* offset,

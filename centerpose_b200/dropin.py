@@ -11,9 +11,10 @@ system consults before it looks at the reference's files:
                                     (reference: src/lib/models/model.py:16-105)
   lib.detectors.detector_factory -> detector_factory = {'object_pose': ObjectPoseDetector}
                                     (reference: src/lib/detectors/detector_factory.py:7-9)
-  _ext                           -> dcn_v2_forward backed by cp_dcn_v2_forward, so that even the
-                                    reference's own DLASeg graph (DCNv2/dcn_v2.py:13,25-31) runs
-                                    our deformable kernel; backward / PSROI raise NotImplementedError
+  _ext                           -> dcn_v2_forward / dcn_v2_backward backed by cp_dcn_v2_forward /
+                                    cp_dcn_v2_backward, so that even the reference's own DLASeg graph and its
+                                    autograd Function (DCNv2/dcn_v2.py:13-76) run our deformable kernels;
+                                    PSROI pooling (unused by CenterPose) raises NotImplementedError
 """
 import sys
 import types
@@ -40,8 +41,8 @@ def install(model=True, detector=True, ext=True):
         e.dcn_v2_forward = _engine.dcn_v2_forward
 
         def _no(*a, **k):
-            raise NotImplementedError("centerpose_b200 `_ext`: only dcn_v2_forward (inference) is provided")
-        e.dcn_v2_backward = _no
+            raise NotImplementedError("centerpose_b200 `_ext`: deformable PSROI pooling is not used by CenterPose and not provided")
+        e.dcn_v2_backward = _engine.dcn_v2_backward
         e.dcn_v2_psroi_pooling_forward = _no
         e.dcn_v2_psroi_pooling_backward = _no
         sys.modules["_ext"] = e

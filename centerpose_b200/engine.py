@@ -371,3 +371,28 @@ def dcn_v2_forward(inp, weight, bias, offset, mask, kh=3, kw=3, sh=1, sw=1, ph=1
     _lib.check(rc, "cp_dcn_v2_forward")
     out._cp_keep = ts
     return out
+
+
+def dcn_v2_backward(inp, weight, bias, offset, mask, grad_output, kh=3, kw=3, sh=1, sw=1, ph=1, pw=1, dh=1, dw=1, dg=1,
+                    precision="fp32"):
+    """`_ext.dcn_v2_backward` signature (DCNv2/src/vision.cpp:11-17, dcn_v2.py:63-76) on top of cp_dcn_v2_backward.
+    Returns (grad_input, grad_offset, grad_mask, grad_weight, grad_bias) as fresh tensors, like the reference."""
+    if (kh, kw, sh, sw, ph, pw, dh, dw, dg) != (3, 3, 1, 1, 1, 1, 1, 1, 1):
+        raise RuntimeError("centerpose_b200 dcn_v2_backward: only 3x3 / stride 1 / pad 1 / dilation 1 / "
+                           "deformable_group 1 is implemented (the configuration CenterPose uses)")
+    if not inp.is_cuda:
+        raise RuntimeError("centerpose_b200 dcn_v2_backward needs CUDA tensors (no CPU fallback)")
+    L = _lib.load()
+    B, C, H, W = inp.shape
+    Co = weight.shape[0]
+    ts = [t.contiguous().float() for t in (inp, weight, offset, mask, grad_output)]
+    for t, shape in zip(ts, ((B, C, H, W), (Co, C, 3, 3), (B, 18, H, W), (B, 9, H, W), (B, Co, H, W))):
+        if tuple(t.shape) != shape or t.device != inp.device:
+            raise ValueError("dcn_v2_backward: expected a %s tensor on %s, got %s on %s" % (shape, inp.device, tuple(t.shape), t.device))
+    grads = [torch.empty_like(ts[0]), torch.empty_like(ts[2]), torch.empty_like(ts[3]), torch.empty_like(ts[1]),
+             torch.empty((Co,), dtype=torch.float32, device=inp.device)]
+    with torch.cuda.device(inp.device):
+        rc = L.cp_dcn_v2_backward(*[_ptr(t) for t in ts], *[_ptr(g) for g in grads], B, C, H, W, Co,
+                                  _lib.PRECISIONS[precision], _stream())
+    _lib.check(rc, "cp_dcn_v2_backward")
+    return tuple(grads)

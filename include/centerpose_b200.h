@@ -337,6 +337,18 @@ int cp_dcn_v2_forward_ex(const float* input, const float* weight, const float* b
                          const float* mask, float* output, int32_t B, int32_t C, int32_t H, int32_t W,
                          int32_t Co, int32_t precision, void* stream);
 
+/* Backward of the same op: replaces `_ext.dcn_v2_backward` (DCNv2/dcn_v2.py:63-76 -> src/cuda/dcn_v2_cuda.cu:206-335,
+ * kernels dcn_v2_im2col_cuda.cu:197-330).  Inputs as in the forward plus grad_output [B,Co,H,W]; the five gradients
+ * (grad_input [B,C,H,W], grad_offset [B,18,H,W], grad_mask [B,9,H,W], grad_weight [Co,C,3,3], grad_bias [Co]) are
+ * OVERWRITTEN (the reference returns fresh tensors).  `precision` selects the kernel family of the column-gradient GEMM
+ * (CP_PREC_FP32: CUDA cores; CP_PREC_TF32X3: tcgen05, fp32-equivalent); the sampling pass and the weight-gradient GEMM
+ * run in fp32.  grad_input is accumulated with float atomics (as in the reference), everything else in a fixed order.
+ * Scratch (about B*H*W*(11*C + Co + 32) floats) comes from the stream-ordered allocator. */
+int cp_dcn_v2_backward(const float* input, const float* weight, const float* offset, const float* mask,
+                       const float* grad_output, float* grad_input, float* grad_offset, float* grad_mask,
+                       float* grad_weight, float* grad_bias, int32_t B, int32_t C, int32_t H, int32_t W, int32_t Co,
+                       int32_t precision, void* stream);
+
 /* ---- single fused convolution (building block of the plan, exposed for layer-level parity tests) ----
  * out = [relu]( conv2d(x, weight, stride, pad) + bias [+ residual] ); x / residual / out are device fp32
  * NHWC ([B,H,W,Cin] / [B,Ho,Wo,Cout]), weight is OIHW like nn.Conv2d (pose_dla_dcn.py:37-44);

@@ -240,6 +240,50 @@ def make_dcn():
         print(name, float(np.abs(out).max()))
 
 
+DCN_BWD_CASES = [
+    # name, B, C, H, W, Co, seed, offset std
+    ("dcn_bwd_small", 2, 16, 9, 11, 8, 17, 2.0),
+    ("dcn_bwd_edge_big_offsets", 1, 32, 6, 5, 24, 18, 6.0),
+    ("dcn_bwd_64ch", 2, 64, 16, 16, 64, 19, 1.0),
+]
+
+
+def dcn_bwd_inputs(B, C, H, W, Co, seed, off_std):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    off = (rng.standard_normal((B, 18, H, W)) * off_std).astype(np.float32)
+    mask = rng.random((B, 9, H, W)).astype(np.float32)
+    w = (rng.standard_normal((Co, C, 3, 3)) / np.sqrt(C * 9)).astype(np.float32)
+    go = rng.standard_normal((B, Co, H, W)).astype(np.float32)
+    return x, off, mask, w, go
+
+
+def ref_dcn_backward(x, off, mask, w, go):
+    """The reference's own C++ CPU backward (oracle/_ref, see oracle/dcn_ref_wrap.cpp)."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(HERE, "_ref", "libdcn_ref.so"))
+    fp = ctypes.POINTER(ctypes.c_float)
+    B, C, H, W = x.shape
+    Co = w.shape[0]
+    out = {"grad_input": np.zeros_like(x), "grad_offset": np.zeros_like(off), "grad_mask": np.zeros_like(mask),
+           "grad_weight": np.zeros_like(w), "grad_bias": np.zeros(Co, np.float32)}
+    a = [np.ascontiguousarray(v) for v in (x, w, off, mask, go)]
+    lib.dcn_ref_backward(*[v.ctypes.data_as(fp) for v in a], *[out[k].ctypes.data_as(fp) for k in
+                         ("grad_input", "grad_offset", "grad_mask", "grad_weight", "grad_bias")], B, C, H, W, Co)
+    return out
+
+
+def make_dcn_bwd():
+    so = os.path.join(HERE, "_ref", "libdcn_ref.so")
+    if not os.path.exists(so):
+        print("oracle/_ref/libdcn_ref.so missing (run `make -C oracle`); skipping dcn backward goldens")
+        return
+    for name, B, C, H, W, Co, seed, off_std in DCN_BWD_CASES:
+        out = ref_dcn_backward(*dcn_bwd_inputs(B, C, H, W, Co, seed, off_std))
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), B=B, C=C, H=H, W=W, Co=Co, seed=seed, off_std=off_std, **out)
+        print(name, {k: float(np.abs(v).max()) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if not ref_shims.reference_available():
         raise SystemExit("reference tree not present: goldens can only be generated in the build container")
@@ -249,6 +293,8 @@ if __name__ == "__main__":
     only = set(sys.argv[1:])
     if not only:
         make_dcn()
+    if not only or "dcn_bwd" in only:
+        make_dcn_bwd()
     make_net(only)
     if not only or any(n.startswith("decode_") for n in only):
         make_decode(only)

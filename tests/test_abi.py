@@ -52,13 +52,19 @@ def test_decode_param_validation(cplib):
     p.K = 200
     assert cplib.cp_decode_workspace_bytes(ctypes.byref(p)) == 0
     p.K = 100
-    p.num_classes = 3
+    p.num_classes = 3         # multi-class heat maps: K candidates per class
+    assert cplib.cp_decode_workspace_bytes(ctypes.byref(p)) > 2 * 3 * 100 * 4
+    p.num_classes = 81        # > CP_MAX_CLASSES
     assert cplib.cp_decode_workspace_bytes(ctypes.byref(p)) == 0
+    p.num_classes = 1
+    p.test_scale = -1.0
+    assert cplib.cp_decode_workspace_bytes(ctypes.byref(p)) == 0
+    assert b"test_scale" in cplib.cp_last_error()
 
 
 def test_struct_sizes_match_header():
     from centerpose_b200 import _lib
-    assert ctypes.sizeof(_lib.CpDecodeParams) == 16 * 4
+    assert ctypes.sizeof(_lib.CpDecodeParams) == 18 * 4
     assert ctypes.sizeof(_lib.CpHeads) == 11 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(_lib.CpConfig) == 10 * 4 + 16 * ctypes.sizeof(ctypes.c_void_p) + 16 * 4
 
@@ -74,6 +80,9 @@ def test_no_cpu_fallback():
     with pytest.raises(RuntimeError):
         cpb.dcn_v2_forward(torch.zeros(1, 16, 4, 4), torch.zeros(8, 16, 3, 3), torch.zeros(8),
                            torch.zeros(1, 18, 4, 4), torch.zeros(1, 9, 4, 4))
+    with pytest.raises(RuntimeError):
+        cpb.dcn_v2_backward(torch.zeros(1, 16, 4, 4), torch.zeros(8, 16, 3, 3), torch.zeros(8),
+                            torch.zeros(1, 18, 4, 4), torch.zeros(1, 9, 4, 4), torch.zeros(1, 8, 4, 4))
 
 
 def test_product_never_imports_oracle():

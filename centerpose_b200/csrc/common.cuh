@@ -135,6 +135,35 @@ int tma_conv_encode(const IgemmParams& p, int Bmax, int x3, void* maps_out /* 4 
 int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, int x3, cudaStream_t stream);
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The forward is ~90 dependent launches; at batch 1 a launch is ~25 us of which the
+// launch latency + the fixed prologue of a tcgen05 CTA (barrier init, TMEM allocation, first weight tiles) is a third.
+// Every kernel of the forward schedule therefore (a) signals `launch_dependents` at its very start, so the NEXT kernel's
+// CTAs are placed on an SM the moment a CTA of this one retires, and (b) executes `griddep_wait()` before its first
+// read of an activation / first global write.  What runs before the wait touches only per-plan constants (weights,
+// biases) and the CTA's own shared memory / TMEM.  Kernels launched without the attribute see both instructions as no-ops.
+// g_pdl is set by run_forward (plan.cu) around the op loop; stand-alone ops (cp_conv2d ...) pack their weights on the
+// stream right before the launch and therefore never use it.  CP_NO_PDL=1 disables it (A/B runs).
+extern thread_local int g_pdl;
+#ifdef __CUDACC__
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 constexpr size_t kSplitkWsFloats = (size_t)160 * 256 * 128;     // >= (#SMs) tile-splits of 256 positions x 128 columns
 
 // Launch attributes (cudaFuncSetAttribute) and the SM count are properties of the CURRENT DEVICE, not of the calling

@@ -301,6 +301,7 @@ template <bool X3, bool FUSE>
 __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmaConvParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   TmaCtl* ctl = reinterpret_cast<TmaCtl*>(smem);
+  if (threadIdx.x == 0) griddep_launch_dependents();      // PDL (common.cuh): the next launch may take this SM when we retire
   // x3 computes TWO 128-row M sub-tiles per weight tile (tile = 256 positions): the weight stream from L2, the measured
   // limiter, is halved per MMA.  The sub-tiles are two accumulators side by side in TMEM and two sets of epilogue warps.
   constexpr int MS = X3 ? 2 : 1;
@@ -364,6 +365,10 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   tc_fence_after();
   if (p.cluster > 1) cluster_sync_all();       // remote arrives / multicast writes need every CTA's barriers initialised
   const uint32_t tmem_base = ctl->tmem_base;
+  // PDL: everything above touched shared memory / TMEM only.  The weight producer (warp 1) reads per-plan constants and
+  // runs ahead; every other role waits here for the previous launch of the stream to finish before it reads an
+  // activation (TMA slabs, residuals) or writes one.
+  if (warp != 1) griddep_wait();
 
   // x3: 512 threads leave 128 registers per thread, but an epilogue thread carries the 128 promoted sums of its row.
   // Warpgroup 0 (control warps) and 3 (splitters) hand registers to warpgroups 1-2 (epilogue) with setmaxnreg; the
@@ -817,6 +822,8 @@ EncodeTiledFn get_encode() {
 // split-K, second half: one thread per (output position, 4 channels) adds the `ksplit` partial sums in split order and
 // applies the epilogue.  Reads are coalesced (row-fastest layout); the whole grid works, not one CTA per tile.
 __global__ void __launch_bounds__(256) conv_tma_splitk_finish(const __grid_constant__ TmaConvParams p, long long mn_tiles) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int G = p.BN >> 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= mn_tiles * G * p.tile_m) return;
@@ -1133,19 +1140,21 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
   cfg.blockDim = dim3(x3 ? TM_THREADS_X3 : TM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl ? 2 : 1;
   CP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, q));
   CP_LAUNCH_CHECK("conv_tma_kernel");
   if (q.ksplit > 1) {
     const long long mn = q.total_tiles / q.ksplit;
     const long long threads = mn * (q.BN / 4) * q.tile_m;
-    conv_tma_splitk_finish<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(q, mn);
+    CP_CUDA_CHECK(launch_kernel(conv_tma_splitk_finish, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, stream, q, mn));
     CP_LAUNCH_CHECK("conv_tma_splitk_finish");
   }
   return CP_OK;

@@ -131,6 +131,7 @@ template <bool X3>
 __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_constant__ DcnTmaParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   DcnCtl* ctl = reinterpret_cast<DcnCtl*>(smem);
+  if (threadIdx.x == 0) griddep_launch_dependents();      // PDL (common.cuh)
   const uint32_t sbase = smem_u32(smem);
   const uint32_t coef0 = sbase + 1024u;
   const uint32_t slabs0 = (coef0 + 2u * DT_COEF_BYTES + 1023u) & ~1023u;
@@ -179,6 +180,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  // PDL: the weight producer (warp 1) reads per-plan constants and runs ahead; every other role waits for the previous
+  // launch (the offset / mask convolution whose output the records are built from) before it touches global memory
+  if (warp != 1) griddep_wait();
 
   // warpgroup 0 (control warps) hands registers to warpgroup 1 (epilogue: 64 running sums + a 32-column TMEM read)
   if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
@@ -614,6 +618,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
 
 // split-K, second half: one thread per (position, 4 channels) adds the partial sums in split order + epilogue
 __global__ void __launch_bounds__(256) dcn_tma_splitk_finish(const __grid_constant__ DcnTmaParams p, long long mn_tiles) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int G = p.BN >> 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= mn_tiles * G * 128) return;
@@ -768,13 +774,13 @@ int launch_dcn_tma(const IgemmParams& p, const void* map, int x3, int round_out_
   }
   const unsigned grid = (unsigned)(q.total_tiles < num_sms ? q.total_tiles : num_sms);
   if (x3)
-    dcn_tma_kernel<true><<<grid, DT_THREADS, smem, stream>>>(q);
+    CP_CUDA_CHECK(launch_kernel(dcn_tma_kernel<true>, dim3(grid), dim3(DT_THREADS), smem, stream, q));
   else
-    dcn_tma_kernel<false><<<grid, DT_THREADS, smem, stream>>>(q);
+    CP_CUDA_CHECK(launch_kernel(dcn_tma_kernel<false>, dim3(grid), dim3(DT_THREADS), smem, stream, q));
   CP_LAUNCH_CHECK("dcn_tma_kernel");
   if (q.ksplit > 1) {
     const long long threads = mn * (q.BN / 4) * 128;
-    dcn_tma_splitk_finish<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(q, mn);
+    CP_CUDA_CHECK(launch_kernel(dcn_tma_splitk_finish, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, stream, q, mn));
     CP_LAUNCH_CHECK("dcn_tma_splitk_finish");
   }
   return CP_OK;

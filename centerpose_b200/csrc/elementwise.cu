@@ -17,6 +17,8 @@ inline int blocks_for(size_t n) {
 // ---- MaxPool2d(2, 2)  (pose_dla_dcn.py:203) ---------------------------------
 __global__ void maxpool2_kernel(const float4* __restrict__ in, float4* __restrict__ out, int B, int H,
                                 int W, int C4) {
+  griddep_launch_dependents();      // PDL (common.cuh)
+  griddep_wait();
   const int Ho = H / 2, Wo = W / 2;
   size_t total = (size_t)B * Ho * Wo * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -43,6 +45,8 @@ __global__ void maxpool2_kernel(const float4* __restrict__ in, float4* __restric
 __global__ void upsample_add_kernel(const float4* __restrict__ in, const float4* __restrict__ w,
                                     const float4* __restrict__ skip, float4* __restrict__ out, int B,
                                     int Hin, int Win, int C4, int f) {
+  griddep_launch_dependents();      // PDL (common.cuh)
+  griddep_wait();
   const int Ho = Hin * f, Wo = Win * f;
   const int k = 2 * f, pad = f / 2;
   size_t total = (size_t)B * Ho * Wo * C4;
@@ -241,7 +245,8 @@ __global__ void gru_gates_kernel(const float* __restrict__ xi, const float* __re
 int launch_maxpool2(const float* in, float* out, int B, int H, int W, int C, cudaStream_t s) {
   if (C % 4 || H % 2 || W % 2) return fail(CP_ERR_INVALID, "maxpool2: C%4, H%2, W%2");
   size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 4);
-  maxpool2_kernel<<<blocks_for(total), TPB, 0, s>>>((const float4*)in, (float4*)out, B, H, W, C / 4);
+  CP_CUDA_CHECK(launch_kernel(maxpool2_kernel, dim3(blocks_for(total)), dim3(TPB), 0, s, (const float4*)in, (float4*)out, B, H, W,
+                              C / 4));
   CP_LAUNCH_CHECK("maxpool2_kernel");
   return CP_OK;
 }
@@ -250,9 +255,8 @@ int launch_upsample_add(const float* in, const float* w, const float* skip, floa
                         int Win, int C, int f, cudaStream_t s) {
   if (C % 4) return fail(CP_ERR_INVALID, "upsample: C%4");
   size_t total = (size_t)B * Hin * f * Win * f * (C / 4);
-  upsample_add_kernel<<<blocks_for(total), TPB, 0, s>>>((const float4*)in, (const float4*)w,
-                                                         (const float4*)skip, (float4*)out, B, Hin, Win,
-                                                         C / 4, f);
+  CP_CUDA_CHECK(launch_kernel(upsample_add_kernel, dim3(blocks_for(total)), dim3(TPB), 0, s, (const float4*)in, (const float4*)w,
+                              (const float4*)skip, (float4*)out, B, Hin, Win, C / 4, f));
   CP_LAUNCH_CHECK("upsample_add_kernel");
   return CP_OK;
 }

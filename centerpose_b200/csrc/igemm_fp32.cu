@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(NT, 2) igemm_fp32_kernel(const IgemmParams p) 
   constexpr int TN = BN / 16;
   __shared__ __align__(16) float As[2][BK][BM + APAD];
   __shared__ __align__(16) float Bs[2][BK][BN];
+  griddep_launch_dependents();      // PDL (common.cuh)
+  griddep_wait();
 
   const int tid = threadIdx.x;
   const int tx = tid & 15;
@@ -296,9 +298,9 @@ int launch_bn(const IgemmParams& p, cudaStream_t stream) {
   const int M = p.B * p.Hout * p.Wout;
   dim3 grid((M + BM - 1) / BM, p.CoutPad / BN);
   switch (p.mode) {
-    case IGEMM_NCHW_SCALAR: igemm_fp32_kernel<BN, IGEMM_NCHW_SCALAR><<<grid, NT, 0, stream>>>(p); break;
-    case IGEMM_NHWC_VEC: igemm_fp32_kernel<BN, IGEMM_NHWC_VEC><<<grid, NT, 0, stream>>>(p); break;
-    case IGEMM_DCN: igemm_fp32_kernel<BN, IGEMM_DCN><<<grid, NT, 0, stream>>>(p); break;
+    case IGEMM_NCHW_SCALAR: CP_CUDA_CHECK(launch_kernel(igemm_fp32_kernel<BN, IGEMM_NCHW_SCALAR>, grid, dim3(NT), 0, stream, p)); break;
+    case IGEMM_NHWC_VEC: CP_CUDA_CHECK(launch_kernel(igemm_fp32_kernel<BN, IGEMM_NHWC_VEC>, grid, dim3(NT), 0, stream, p)); break;
+    case IGEMM_DCN: CP_CUDA_CHECK(launch_kernel(igemm_fp32_kernel<BN, IGEMM_DCN>, grid, dim3(NT), 0, stream, p)); break;
     default: return fail(CP_ERR_INVALID, "igemm: bad mode");
   }
   CP_LAUNCH_CHECK("igemm_fp32_kernel");

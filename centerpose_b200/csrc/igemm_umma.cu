@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(UM_THREADS) igemm_umma_kernel(const IgemmParam
   using T = PrecTraits<PREC>;
   extern __shared__ __align__(1024) unsigned char smem[];
   UmmaSmem* ctl = reinterpret_cast<UmmaSmem*>(smem);
+  if (threadIdx.x == 0) griddep_launch_dependents();      // PDL (common.cuh)
   const uint32_t tiles0 = (smem_u32(smem) + 512u + 4u * kStageFloatsPerWarp * 4u + 1023u) & ~1023u;   // first tile, 1024-aligned
   const uint32_t b_tile_bytes = (uint32_t)BN * ROW_BYTES * T::kTilesA; // hi (+ lo) weight tiles of one stage
   const uint32_t a_bytes = A_TILE_BYTES * T::kTilesA;
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(UM_THREADS) igemm_umma_kernel(const IgemmParam
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  griddep_wait();      // PDL: the prologue above is private to the CTA; activations are read from here on
 
   if (warp < UM_PROD_WARPS) {
     // =========================== A producers: two threads per tile row, four 16-byte chunks each ===============
@@ -592,7 +594,7 @@ int launch_igemm_umma(const IgemmParams& p, int prec, cudaStream_t stream) {
   }
   // tf32x3: K blocks (12 MMAs each) per TMEM accumulation group, promoted into fp32 sums by the promoter warps
   const int nacc = prec == 1 ? x3_group_blocks() : 1;
-  kern<<<grid, UM_THREADS, smem, stream>>>(p, bn, stages, nacc);
+  CP_CUDA_CHECK(launch_kernel(kern, grid, dim3(UM_THREADS), smem, stream, p, bn, stages, nacc));
   CP_LAUNCH_CHECK("igemm_umma_kernel");
   return CP_OK;
 }

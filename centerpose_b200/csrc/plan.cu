@@ -24,6 +24,7 @@ namespace cp {
 thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 thread_local long long g_launch_counter = 0;
+thread_local int g_pdl = 0;
 
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -815,10 +816,24 @@ struct ProfCtx {
   std::vector<cudaEvent_t> ev;
 };
 
+// PDL pays at small batches, where a launch is ~20 us and the hidden latency + prologue a tenth of it (forward at batch 1:
+// 2.18 -> 2.00 ms); at batch 32 the kernels run for 100s of us and the early CTAs of the next launch only add scheduling
+// work (27.17 -> 27.42 ms, measured), so it is switched on by the amount of work.  CP_PDL=1 / CP_NO_PDL=1 force it.
+static bool pdl_wanted(long long pixels) {
+  if (getenv("CP_NO_PDL")) return false;
+  if (const char* e = getenv("CP_PDL")) return atoi(e) != 0;
+  return pixels <= 4ll * 512 * 512;
+}
+
 static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* const* head_out, cudaStream_t s,
                        ProfCtx* prof = nullptr) {
   int rc;
   const long long launches0 = g_launch_counter;
+  // programmatic dependent launch for the whole schedule (common.cuh); off while profiling (events sit between the ops)
+  struct PdlScope {
+    explicit PdlScope(int on) { g_pdl = on; }
+    ~PdlScope() { g_pdl = 0; }
+  } pdl_scope(!prof && pdl_wanted((long long)batch * P->H * P->W));
   for (auto& op : P->ops) {
     if (prof) {
       cudaEvent_t e;

@@ -24,7 +24,9 @@ __global__ void __launch_bounds__(ST_TX* ST_TY)
   const int n = blockIdx.z;
   const int x0 = blockIdx.x * ST_W, y0 = blockIdx.y * ST_TY;
   const int nw = 49 * Cin * 16;
+  if (tid == 0) griddep_launch_dependents();      // PDL (common.cuh): weights are constants, the image is not
   for (int i = tid; i < nw; i += ST_TX * ST_TY) ws[i] = __ldg(wgt + i);
+  griddep_wait();
   const int nt = Cin * ST_HALO_H * ST_HALO_W;
   for (int i = tid; i < nt; i += ST_TX * ST_TY) {
     int xx = i % ST_HALO_W;
@@ -127,7 +129,9 @@ __global__ void __launch_bounds__(C3_TX* C3_TY, 2)
   const int tid = threadIdx.y * C3_TX + threadIdx.x;
   const int n = blockIdx.z;
   const int x0 = blockIdx.x * C3_W, y0 = blockIdx.y * C3_TY;
+  if (tid == 0) griddep_launch_dependents();      // PDL (common.cuh)
   for (int i = tid; i < 9 * 16 * 16; i += C3_TX * C3_TY) ws[i] = __ldg(wgt + i);
+  griddep_wait();
   for (int i = tid; i < C3_HH * C3_HW * 4; i += C3_TX * C3_TY) {
     const int q = i & 3, pix = i >> 2;
     const int xx = pix % C3_HW, yy = pix / C3_HW;
@@ -225,8 +229,8 @@ int launch_conv3_c16(const IgemmParams& p, cudaStream_t s) {
   }
   dim3 grid((p.Win + C3_W - 1) / C3_W, (p.Hin + C3_TY - 1) / C3_TY, p.B);
   dim3 block(C3_TX, C3_TY);
-  conv3_c16_kernel<<<grid, block, smem, s>>>(p.src[0], p.srcStride[0], p.wgt, p.bias, p.out, p.outStride, p.B, p.Hin, p.Win,
-                                             p.relu);
+  CP_CUDA_CHECK(launch_kernel(conv3_c16_kernel, grid, block, smem, s, p.src[0], p.srcStride[0], p.wgt, p.bias, p.out, p.outStride,
+                              p.B, p.Hin, p.Win, p.relu));
   CP_LAUNCH_CHECK("conv3_c16_kernel");
   return CP_OK;
 }
@@ -247,8 +251,8 @@ int launch_stem_conv(const IgemmParams& p, cudaStream_t s) {
   }
   dim3 grid((p.Win + ST_W - 1) / ST_W, (p.Hin + ST_TY - 1) / ST_TY, p.B);
   dim3 block(ST_TX, ST_TY);
-  stem_conv7_kernel<<<grid, block, smem, s>>>(p.src[0], p.wgt, p.bias, p.residual, p.out, p.B, p.Cin, p.Hin, p.Win,
-                                              p.relu);
+  CP_CUDA_CHECK(launch_kernel(stem_conv7_kernel, grid, block, smem, s, p.src[0], p.wgt, p.bias, p.residual, p.out, p.B, p.Cin,
+                              p.Hin, p.Win, p.relu));
   CP_LAUNCH_CHECK("stem_conv7_kernel");
   return CP_OK;
 }

@@ -31,7 +31,8 @@ OBJECT_KEYS = {"class", "ct", "bbox", "confidence", "kps_displacement_mean", "kp
                "kps_heatmap_height", "obj_scale", "location", "quaternion_xyzw", "kps_pnp", "kps_3d_cam"}
 
 
-def _oracle_process(self, images, pre_images=None, pre_hms=None, pre_hm_hp=None, pre_inds=None, return_time=False, meta=None):
+def _oracle_process(self, images, pre_images=None, pre_hms=None, pre_hm_hp=None, pre_inds=None, return_time=False, meta=None,
+                    scale=1.0):
     """CPU stand-in for the two device stages of ObjectPoseDetector.process (network + fused decode / PnP)."""
     import time
     from centerpose_b200.detector import dets_to_dict
@@ -40,12 +41,13 @@ def _oracle_process(self, images, pre_images=None, pre_hms=None, pre_hm_hp=None,
     sd = {k: v.detach().cpu() for k, v in self.model.state_dict().items()}
     heads = net_ref.forward(images.cpu(), sd, self.opt.heads, "dla_34")
     forward_time = time.time()
-    prm = decode_ref.DecodeParams(rep_mode=self.opt.rep_mode, vis_thresh=self.opt.vis_thresh, category=self.opt.c)
+    prm = decode_ref.DecodeParams(rep_mode=self.opt.rep_mode, vis_thresh=self.opt.vis_thresh, category=self.opt.c,
+                                  nms=self.opt.nms, num_scales=len(self.opt.test_scales))
     hb = {k: v[0].numpy() for k, v in heads.items()}
     s = meta["s"]
     s = float(s[0]) if isinstance(s, np.ndarray) and s.ndim else float(s)
     dets, recs = oracle_records(hb, prm, np.asarray(meta["camera_matrix"], np.float64), meta["width"], meta["height"],
-                                np.asarray(meta["c"], np.float32), s, L)
+                                np.asarray(meta["c"], np.float32), s, L, scale=scale)
     poses = np.zeros((1, self.opt.K, L.CP_POSE_RECORD), np.float32)
     poses[0, :recs.shape[0]] = recs
     self._last = (poses, np.array([recs.shape[0]], np.int32))

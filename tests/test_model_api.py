@@ -79,8 +79,9 @@ def test_dropin_registers_reference_module_names():
         assert sys.modules["lib.models.model"].create_model is cpb.create_model
         assert sys.modules["lib.detectors.detector_factory"].detector_factory["object_pose"] is cpb.ObjectPoseDetector
         assert sys.modules["_ext"].dcn_v2_forward is cpb.dcn_v2_forward
+        assert sys.modules["_ext"].dcn_v2_backward is cpb.dcn_v2_backward
         with pytest.raises(NotImplementedError):
-            sys.modules["_ext"].dcn_v2_backward()
+            sys.modules["_ext"].dcn_v2_psroi_pooling_forward()
     finally:
         for k, v in saved.items():
             if v is None:

@@ -21,56 +21,141 @@ __device__ void dlt_init_warp(const double* X, const double* uv, int n, double f
                               double* R, double* t, double* sm, int lane) {
   double* A = sm;
   double* V = sm + 144;
-  for (int e = lane; e < 144; e += 32) {
-    const int a = e / 12, b = e - a * 12;
-    double acc = 0.0;
-    for (int i = 0; i < n; ++i) {
-      const double x = (uv[2 * i] - cx) / fx, y = (uv[2 * i + 1] - cy) / fy;
-      const double h[4] = {X[3 * i], X[3 * i + 1], X[3 * i + 2], 1.0};
-      const double r1a = a < 4 ? h[a] : (a < 8 ? 0.0 : -x * h[a - 8]);
-      const double r1b = b < 4 ? h[b] : (b < 8 ? 0.0 : -x * h[b - 8]);
-      const double r2a = a < 4 ? 0.0 : (a < 8 ? h[a - 4] : -y * h[a - 8]);
-      const double r2b = b < 4 ? 0.0 : (b < 8 ? h[b - 4] : -y * h[b - 8]);
-      acc += r1a * r1b + r2a * r2b;
-    }
-    A[e] = acc;
-    V[e] = (a == b) ? 1.0 : 0.0;
+  // M^T M of the 2n x 12 DLT matrix (rows [h 0 -x h], [0 h -y h], h = (X, Y, Z, 1), (x, y) the normalised image point)
+  // is a 3 x 3 arrangement of 4 x 4 weighted moment matrices of h:  [H 0 -Hx; 0 H -Hy; -Hx -Hy Hxx+yy].  The points are
+  // staged once in shared memory and the 4 x 16 moments summed by 2 entries per lane -- the first version evaluated all
+  // 144 entries with per-entry conditionals on local arrays (6.9 K of the 57 K instructions of a solve).
+  double* P = V;                        // [n][6]: X, Y, Z, 1, x, y (consumed before V is initialised)
+  double* S = sm + 240;                 // [4][4][4]: weights 1, x, y, x^2 + y^2
+  if (lane < n) {
+    P[6 * lane + 0] = X[3 * lane];
+    P[6 * lane + 1] = X[3 * lane + 1];
+    P[6 * lane + 2] = X[3 * lane + 2];
+    P[6 * lane + 3] = 1.0;
+    P[6 * lane + 4] = (uv[2 * lane] - cx) / fx;
+    P[6 * lane + 5] = (uv[2 * lane + 1] - cy) / fy;
   }
   __syncwarp();
-  const int k = lane < 12 ? lane : lane - 12;       // lanes 0-11 rotate A, lanes 12-23 rotate V
+  for (int e = lane; e < 64; e += 32) {
+    const int w = e >> 4, i = (e >> 2) & 3, j = e & 3;
+    double acc = 0.0;
+    for (int k = 0; k < n; ++k) {
+      const double* pk = P + 6 * k;
+      const double x = pk[4], y = pk[5];
+      const double wt = w == 0 ? 1.0 : (w == 1 ? x : (w == 2 ? y : x * x + y * y));
+      acc += wt * (pk[i] * pk[j]);
+    }
+    S[e] = acc;
+  }
+  __syncwarp();
+  for (int e = lane; e < 144; e += 32) {
+    const int a = e / 12, b = e - a * 12;
+    const int ba = a >> 2, bb = b >> 2, ij = (a & 3) * 4 + (b & 3);
+    double v = 0.0;
+    if (ba == bb)
+      v = S[(ba == 2 ? 48 : 0) + ij];
+    else if (ba == 2 || bb == 2)
+      v = -S[((ba == 2 ? bb : ba) == 0 ? 16 : 32) + ij];
+    A[e] = v;
+  }
+  __syncwarp();
+  for (int e = lane; e < 144; e += 32) V[e] = (e / 12 == e % 12) ? 1.0 : 0.0;
+  __syncwarp();
+  // Cyclic Jacobi in the ROUND-ROBIN order: the 66 index pairs of a sweep are 11 rounds of 6 disjoint pairs, and the six
+  // rotations of a round commute, so a round is ONE parallel step -- lanes 0-5 compute the six angles, then 144 lane-tasks
+  // rotate the columns of A and V (A J, V J) and 72 the rows of A (J^T A).  The row-cyclic order of pose::dlt_init (the
+  // host-tested statement, pose_core.h) converges to the same eigenvectors; the device needs ~2 K instead of ~9.2 K
+  // dependent instructions per sweep (ncu: the serial sweep was 80 % of the 100 K instructions of a PnP solve, each
+  // stalled ~7 cycles on its predecessor).  The lane -> (pair slot, row) assignment of a task is fixed, so it is decoded
+  // once; angles use rsqrt / reciprocal (1 ulp; Jacobi is self-correcting) instead of two divisions and two square roots.
+  double* rcs = sm + 288;                               // [6][2]: c, s of the round (the image points were consumed above)
+  int* rpq = reinterpret_cast<int*>(sm + 300);          // [6][2]: p, q
+  int c_off[5], r_pr[3], r_k[3];
+  bool c_on[5], r_on[3];
+#pragma unroll
+  for (int it = 0; it < 5; ++it) {
+    const int task = lane + 32 * it;
+    c_on[it] = task < 144;
+    const int pr = (task % 72) / 12, k = task % 12;
+    c_off[it] = (task < 72 ? 0 : 144) + k * 12 + (pr << 16);      // element offset of row k in A | V, pair slot in the high half
+  }
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int task = lane + 32 * it;
+    r_on[it] = task < 72;
+    r_pr[it] = (task % 72) / 12;
+    r_k[it] = task % 12;
+  }
   for (int sweep = 0; sweep < 60; ++sweep) {
     double off = 0.0, diag = 0.0;
-    for (int i = 0; i < 12; ++i) {
-      diag += A[i * 12 + i] * A[i * 12 + i];
-      for (int j = i + 1; j < 12; ++j) off += A[i * 12 + j] * A[i * 12 + j];
+    for (int e = lane; e < 144; e += 32) {
+      const int a = e / 12, b = e - a * 12;
+      const double v = A[e] * A[e];
+      if (a == b) diag += v;
+      else if (a < b) off += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      off += __shfl_xor_sync(0xffffffffu, off, o);
+      diag += __shfl_xor_sync(0xffffffffu, diag, o);
     }
     if (off <= 1e-60 * diag || off == 0.0) break;
-    for (int p = 0; p < 11; ++p)
-      for (int q = p + 1; q < 12; ++q) {
+    for (int r = 0; r < 11; ++r) {
+      if (lane < 6) {
+        // round r of the tournament on 12 players: (11, r) and ((r + i) mod 11, (r - i) mod 11), i = 1..5
+        int p = lane == 0 ? 11 : (r + lane) % 11, q = lane == 0 ? r : (r - lane + 11) % 11;
+        if (p > q) {
+          const int t0 = p;
+          p = q;
+          q = t0;
+        }
         const double apq = A[p * 12 + q];
-        if (apq == 0.0) continue;
-        const double app = A[p * 12 + p], aqq = A[q * 12 + q];
-        const double theta = (aqq - app) / (2.0 * apq);
-        const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
-        __syncwarp();                                 // everybody has read A[p][q], A[p][p], A[q][q]
-        if (lane < 12) {
-          const double akp = A[k * 12 + p], akq = A[k * 12 + q];
-          A[k * 12 + p] = c * akp - s * akq;
-          A[k * 12 + q] = s * akp + c * akq;
-        } else if (lane < 24) {
-          const double vkp = V[k * 12 + p], vkq = V[k * 12 + q];
-          V[k * 12 + p] = c * vkp - s * vkq;
-          V[k * 12 + q] = s * vkp + c * vkq;
+        double c = 1.0, s = 0.0;
+        if (apq != 0.0) {
+          const double app = A[p * 12 + p], aqq = A[q * 12 + q];
+          const double theta = (aqq - app) / (2.0 * apq);
+          double tt;
+          if (fabs(theta) > 1e100) {
+            tt = 0.5 / theta;                          // 1 / (|theta| + sqrt(theta^2 + 1)) without the overflow
+          } else {
+            const double r1 = theta * theta + 1.0;
+            tt = copysign(__drcp_rn(fabs(theta) + r1 * rsqrt(r1)), theta);
+          }
+          c = rsqrt(tt * tt + 1.0);
+          s = tt * c;
         }
-        __syncwarp();
-        if (lane < 12) {
-          const double apk = A[p * 12 + k], aqk = A[q * 12 + k];
-          A[p * 12 + k] = c * apk - s * aqk;
-          A[q * 12 + k] = s * apk + c * aqk;
-        }
-        __syncwarp();
+        rpq[lane * 2] = p;
+        rpq[lane * 2 + 1] = q;
+        rcs[lane * 2] = c;
+        rcs[lane * 2 + 1] = s;
       }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 5; ++it) {                  // columns p, q of A (tasks 0-71) and of V (72-143)
+        if (c_on[it]) {
+          const int pr = c_off[it] >> 16;
+          double* row = sm + (c_off[it] & 0xffff);
+          const int p = rpq[pr * 2], q = rpq[pr * 2 + 1];
+          const double c = rcs[pr * 2], s = rcs[pr * 2 + 1];
+          const double xp = row[p], xq = row[q];
+          row[p] = c * xp - s * xq;
+          row[q] = s * xp + c * xq;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 3; ++it) {                  // rows p, q of A
+        if (r_on[it]) {
+          const int pr = r_pr[it], k = r_k[it];
+          const int p = rpq[pr * 2], q = rpq[pr * 2 + 1];
+          const double c = rcs[pr * 2], s = rcs[pr * 2 + 1];
+          const double xp = A[p * 12 + k], xq = A[q * 12 + k];
+          A[p * 12 + k] = c * xp - s * xq;
+          A[q * 12 + k] = s * xp + c * xq;
+        }
+      }
+      __syncwarp();
+    }
   }
   int m = 0;
   for (int i = 1; i < 12; ++i)

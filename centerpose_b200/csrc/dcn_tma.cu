@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tma_kernel(const __grid_con
       uint32_t slab = 0;
       float4 rec_next = ld_shared_v4f(crow + (uint32_t)(half % 9) * 16u);      // tap of this group's first K block
       for (int kb = half; kb < KB; kb += p.NG) {
-        const int s = kb / 9, t = kb - s * 9;
+        const int s = kb / 9;
         if (s != cur) {
           if (cur >= 0) {                     // done with the previous slab
             __syncwarp();

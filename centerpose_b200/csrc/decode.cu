@@ -217,7 +217,6 @@ __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
   const float th = 0.1f;
 
   __shared__ float c_score[KM];
-  __shared__ int c_ind[KM];
   __shared__ float c_bbox[KM][4];
   __shared__ float c_disp[KM][16];
   __shared__ float hmx[8][KM], hmy[8][KM], hms[8][KM];
@@ -273,7 +272,6 @@ __global__ void __launch_bounds__(256, 1) group_pose_kernel(const GroupArgs a) {
     const float xs = (float)(ind % W), ys = (float)(ind / W);
     float* d = dets + (size_t)k * CP_DETS_RECORD;
     c_score[k] = score;
-    c_ind[k] = ind;
     for (int j = 0; j < 2 * J; ++j) {
       float v = gatherf(a.h.hps, b, 2 * J, j, HW, ind) + ((j & 1) ? ys : xs);
       c_disp[k][j] = v;

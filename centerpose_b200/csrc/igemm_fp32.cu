@@ -37,7 +37,6 @@ struct DcnTap {
   int o1, o2, o3, o4;  // pixel offsets (in pixels, not floats) of the 4 corners, clamped in-bounds
 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 template <int BN, int MODE>
 __global__ void __launch_bounds__(NT, 2) igemm_fp32_kernel(const IgemmParams p) {

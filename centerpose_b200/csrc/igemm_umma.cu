@@ -73,11 +73,11 @@ template <int PREC>
 struct PrecTraits;
 template <>
 struct PrecTraits<0> {   // bf16
-  static constexpr int kElems = 64, kChunkCh = 8, kTilesA = 1, kTf32 = 0, kFmt = 1;
+  static constexpr int kElems = 64, kChunkCh = 8, kTilesA = 1, kFmt = 1;
 };
 template <>
 struct PrecTraits<1> {   // tf32 x 3
-  static constexpr int kElems = 32, kChunkCh = 4, kTilesA = 2, kTf32 = 1, kFmt = 2;
+  static constexpr int kElems = 32, kChunkCh = 4, kTilesA = 2, kFmt = 2;
 };
 
 // ------------------------------------------------------------------ the kernel
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(UM_THREADS) igemm_umma_kernel(const IgemmParam
   extern __shared__ __align__(1024) unsigned char smem[];
   UmmaSmem* ctl = reinterpret_cast<UmmaSmem*>(smem);
   if (threadIdx.x == 0) griddep_launch_dependents();      // PDL (common.cuh)
-  const uint32_t tiles0 = (smem_u32(smem) + 512u + 4u * kStageFloatsPerWarp * 4u + 1023u) & ~1023u;   // first tile, 1024-aligned
+  const uint32_t tiles0 = (smem_u32(smem) + 512u + 1023u) & ~1023u;   // first tile, 1024-aligned
   const uint32_t b_tile_bytes = (uint32_t)BN * ROW_BYTES * T::kTilesA; // hi (+ lo) weight tiles of one stage
   const uint32_t a_bytes = A_TILE_BYTES * T::kTilesA;
   const uint32_t stage_bytes = a_bytes + b_tile_bytes;
@@ -294,7 +294,6 @@ __global__ void __launch_bounds__(UM_THREADS) igemm_umma_kernel(const IgemmParam
     mbar_wait(smem_u32(&ctl->accum_full), 0u);
     tc_fence_after();
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float* stage = reinterpret_cast<float*>(smem + 512) + warp * kStageFloatsPerWarp;
     EpiParams ep;
     ep.bias = p.bias;
     ep.residual = p.residual;
@@ -328,7 +327,7 @@ __global__ void __launch_bounds__(UM_THREADS) igemm_umma_kernel(const IgemmParam
 #pragma unroll
         for (int j = 0; j < 32; ++j) vv[j] += __uint_as_float(rr[j]);
       }
-      epilogue_sub_tile(ep, stage, vv, lane, valid, m, n, oy, ox, n_tile * BN + c0, col_end);
+      epilogue_sub_tile(ep, nullptr, vv, lane, valid, m, n, oy, ox, n_tile * BN + c0, col_end);
     }
     }
   } else if (warp == UM_PROD_WARPS) {
@@ -578,7 +577,7 @@ int launch_igemm_umma(const IgemmParams& p, int prec, cudaStream_t stream) {
   // up to 36 samples); a small pipeline leaves most of the 228 KB for L1 so those re-reads hit on chip
   if (p.mode == IGEMM_DCN && stages > 2) stages = 2;
   if (stages < 2) return fail(CP_ERR_INVALID, "igemm_umma: tile does not fit shared memory");
-  const size_t smem = 512 + 4 * umma::kStageFloatsPerWarp * 4 + 2048 + stages * stage_bytes;
+  const size_t smem = 512 + 2048 + stages * stage_bytes;
   const int M = p.B * p.Hout * p.Wout;
   dim3 grid((unsigned)((size_t)(p.CoutPad / bn) * ((M + UM_BM - 1) / UM_BM)));
   void (*kern)(const IgemmParams, const int, const int, const int) = nullptr;

@@ -616,7 +616,6 @@ int build_graph(cp_plan* P) {
   return CP_OK;
 }
 
-const float* act_ptr(const cp_plan* P, const Act& a) { return P->act + a.off; }
 
 }  // namespace
 }  // namespace cp

@@ -202,86 +202,9 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Epilogue store of a [32 rows x 32 columns] sub-tile owned by ONE warp (lane == row, tcgen05.ld layout) to an NHWC
-// tensor.  A lane holding its row in registers would issue 16-byte stores 32 rows apart (32 sectors per request);
-// instead the warp transposes through a private [32][36]-float staging area so that every store instruction writes
-// four full 128-byte row segments.  Must be called by all 32 lanes.
-//   stage    : this warp's staging area (32 * 36 floats, 16-byte aligned)
-//   vv       : the lane's 32 values, columns col0 .. col0+31 of its row
-//   valid, m : row validity and flattened output pixel of the lane's row
-//   col_end  : first column that must NOT be written (min(Cout, end of this CTA's N tile))
-constexpr int kStagePitch = 36;
-constexpr int kStageFloatsPerWarp = 32 * kStagePitch;
-
-__device__ __forceinline__ void warp_store_rows32(float* stage, const float (&vv)[32], int lane, bool valid, int m,
-                                                  float* __restrict__ out, int outStride, int col0, int col_end) {
-  const uint32_t sbase = smem_u32(stage);
-  const uint32_t srow = sbase + (uint32_t)lane * kStagePitch * 4u;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) st_shared_v4f(srow + q * 16, vv[4 * q], vv[4 * q + 1], vv[4 * q + 2], vv[4 * q + 3]);
-  __syncwarp();
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + (lane >> 3);
-    const int j4 = lane & 7;
-    const float4 v = ld_shared_v4f(sbase + (uint32_t)(r * kStagePitch + 4 * j4) * 4u);
-    const int mo = __shfl_sync(0xffffffffu, m, r);
-    const int vo = __shfl_sync(0xffffffffu, (int)valid, r);
-    const int col = col0 + 4 * j4;
-    if (vo && col < col_end) {
-      float* o = out + (size_t)mo * outStride + col;
-      if (col + 3 < col_end) {
-        *reinterpret_cast<float4*>(o) = v;
-      } else {
-        o[0] = v.x;
-        if (col + 1 < col_end) o[1] = v.y;
-        if (col + 2 < col_end) o[2] = v.z;
-      }
-    }
-  }
-  __syncwarp();
-}
-
-// Coalesced read of the residual rows of the same [32 x 32] sub-tile: afterwards res[j] holds residual[m][col0 + j] of
-// the lane's own row (0 where the row / column is not valid).
-__device__ __forceinline__ void warp_load_rows32(float* stage, float (&res)[32], int lane, bool valid, int m,
-                                                 const float* __restrict__ src, int srcStride, int col0, int col_end) {
-  const uint32_t sbase = smem_u32(stage);
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + (lane >> 3);
-    const int j4 = lane & 7;
-    const int mo = __shfl_sync(0xffffffffu, m, r);
-    const int vo = __shfl_sync(0xffffffffu, (int)valid, r);
-    const int col = col0 + 4 * j4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (vo && col < col_end) {
-      const float* s = src + (size_t)mo * srcStride + col;
-      if (col + 3 < col_end) {
-        v = __ldg(reinterpret_cast<const float4*>(s));
-      } else {
-        v.x = __ldg(s);
-        if (col + 1 < col_end) v.y = __ldg(s + 1);
-        if (col + 2 < col_end) v.z = __ldg(s + 2);
-      }
-    }
-    st_shared_v4f(sbase + (uint32_t)(r * kStagePitch + 4 * j4) * 4u, v.x, v.y, v.z, v.w);
-  }
-  __syncwarp();
-  const uint32_t srow = sbase + (uint32_t)lane * kStagePitch * 4u;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 v = ld_shared_v4f(srow + q * 16);
-    res[4 * q] = v.x;
-    res[4 * q + 1] = v.y;
-    res[4 * q + 2] = v.z;
-    res[4 * q + 3] = v.w;
-  }
-  __syncwarp();
-}
-
 // The fused epilogue of one [32 x 32] sub-tile: bias, residual (before or after the ReLU), ReLU, optional tf32
-// rounding, then an NHWC (transposed, coalesced) or NCHW (already coalesced across lanes) store.
+// rounding, then an NHWC store (every lane streams its own row with 16-byte stores; routing the tile through shared
+// memory for fully coalesced stores was measured SLOWER) or an NCHW store (coalesced across lanes).
 struct EpiParams {
   const float* bias;
   const float* residual;

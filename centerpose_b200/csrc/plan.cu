@@ -815,13 +815,14 @@ struct ProfCtx {
   std::vector<cudaEvent_t> ev;
 };
 
-// PDL pays at small batches, where a launch is ~20 us and the hidden latency + prologue a tenth of it (forward at batch 1:
-// 2.18 -> 2.00 ms); at batch 32 the kernels run for 100s of us and the early CTAs of the next launch only add scheduling
-// work (27.17 -> 27.42 ms, measured), so it is switched on by the amount of work.  CP_PDL=1 / CP_NO_PDL=1 force it.
+// PDL hides ~2 us of launch latency + prologue per kernel: a constant ~0.19 ms of the forward (scripts/pdl_sweep.py, ms with /
+// without: batch 1 1.99 / 2.18, 2 2.77 / 2.97, 4 4.45 / 4.64, 8 7.73 / 7.83, 16 14.70 / 14.65, 32 27.42 / 27.17).  Beyond
+// batch 8 the kernels run for 100s of us and the early CTAs of the next launch only add scheduling work, so it is switched
+// on by the amount of work.  CP_PDL=1 / CP_NO_PDL=1 force it.
 static bool pdl_wanted(long long pixels) {
   if (getenv("CP_NO_PDL")) return false;
   if (const char* e = getenv("CP_PDL")) return atoi(e) != 0;
-  return pixels <= 4ll * 512 * 512;
+  return pixels <= 8ll * 512 * 512;
 }
 
 static int run_forward(cp_plan* P, int batch, const float* const ext[4], float* const* head_out, cudaStream_t s,

@@ -82,6 +82,25 @@ def test_non_square_image_affine(cplib):
         compare_records(poses[b, :n_valid[b]], want, L)
 
 
+@pytest.mark.parametrize("oh,ow,K,nobj", [(96, 128, 100, 3), (128, 128, 128, 5), (64, 64, 20, 2), (160, 96, 100, 3)])
+def test_map_shapes_and_K(oh, ow, K, nobj, cplib):
+    """Ragged shapes: non-square head maps (keep_res / fix_short inputs), K at CP_MAX_K and a small K, vs the oracle."""
+    B = 2
+    w, h = ow * 4, oh * 4
+    hb, truths = synth.planted_batch(B, n_obj=nobj, seed=900 + K, out_h=oh, out_w=ow, disagree_px=0.5)
+    cam = truths[0]["cam"]
+    c, s = np.array([w / 2., h / 2.], np.float32), float(max(w, h))
+    dets, poses, n_valid = _run(hb, cam, 1, False, "chair", c=c, s=s, w=w, h=h, K=K)
+    assert poses.shape == (B, K, L.CP_POSE_RECORD)
+    prm = decode_ref.DecodeParams(K=K, rep_mode=1, vis_thresh=0.3, category="chair")
+    for b in range(B):
+        _, want = oracle_records({k: v[b] for k, v in hb.items()}, prm, cam, w, h, c, s, L)
+        assert n_valid[b] == want.shape[0] == len(truths[b]["R"])
+        got = poses[b, :n_valid[b]]
+        assert (got[:, L.P_SRC_INDEX] == want[:, L.P_SRC_INDEX]).all()
+        compare_records(got, want, L)
+
+
 def test_empty_scene_and_no_pnp(cplib):
     hb, _ = synth.planted_batch(2, n_obj=0, seed=500)
     dets, poses, n_valid = _run(hb, synth.default_camera(), 1, False, "chair")

@@ -70,7 +70,8 @@ CP_HD void rodrigues(const double* w, double* R) {
     for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
     return;
   }
-  double kx = w[0] / th, ky = w[1] / th, kz = w[2] / th;
+  const double ith = 1.0 / th;
+  double kx = w[0] * ith, ky = w[1] * ith, kz = w[2] * ith;
   double s = sin(th), c1 = 1.0 - cos(th);
   double K[9] = {0, -kz, ky, kz, 0, -kx, -ky, kx, 0};
   double K2[9];
@@ -184,7 +185,9 @@ CP_HDN void jacobi_min_eigvec(double* A, double* V, double* vmin) {
 
 // solve the symmetric positive-definite 6x6 system (A + lam*diag(A)) d = -g by Cholesky; false if not SPD
 CP_HDN bool solve6(const double* A, const double* g, double lam, double* d) {
-  double L[36];
+  // one reciprocal per pivot instead of a division per entry: on the GPU an fp64 division is a ~20-instruction dependent
+  // sequence and this routine sits inside the LM loop of every object (27 divisions -> 6)
+  double L[36], inv[6];
   for (int i = 0; i < 6; ++i)
     for (int j = 0; j <= i; ++j) {
       double s = A[i * 6 + j];
@@ -193,20 +196,21 @@ CP_HDN bool solve6(const double* A, const double* g, double lam, double* d) {
       if (i == j) {
         if (!(s > 0.0)) return false;
         L[i * 6 + i] = sqrt(s);
+        inv[i] = 1.0 / L[i * 6 + i];
       } else {
-        L[i * 6 + j] = s / L[j * 6 + j];
+        L[i * 6 + j] = s * inv[j];
       }
     }
   double y[6];
   for (int i = 0; i < 6; ++i) {
     double s = -g[i];
     for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * y[k];
-    y[i] = s / L[i * 6 + i];
+    y[i] = s * inv[i];
   }
   for (int i = 5; i >= 0; --i) {
     double s = y[i];
     for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * d[k];
-    d[i] = s / L[i * 6 + i];
+    d[i] = s * inv[i];
   }
   return true;
 }

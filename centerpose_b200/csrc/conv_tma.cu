@@ -69,6 +69,7 @@ struct TmaConvParams {
   int x3;             // 3-term split (fp32-equivalent): hi/lo slabs + hi/lo weight tiles, BN <= 128
   int group;          // x3: K blocks per TMEM accumulation group (promoted into fp32 registers after each group)
   int nbuf;           // TMEM accumulation buffers of tile_m x BN (2; x3 with narrow N tiles: up to 8, all 512 columns)
+  int cat;            // x3, N tile <= 64: hi and lo weight tiles are ONE 2 BN-row B operand (see issue_tile)
   const unsigned char* wtiles;
   // split-K (x3, not fused): the K loop of a tile is dealt to `ksplit` CTAs (slab-aligned ranges of `sps` slabs); every
   // CTA stores its promoted partial sums and conv_tma_splitk_finish adds them in split order (deterministic) and runs
@@ -168,6 +169,8 @@ __device__ __forceinline__ void fused_part_smem(const float (&sums)[128], float 
 // ---- MMA issue loop (one warp; see the comment at its call site) --------------------------------------------------------
 struct IssueCtx {
   uint32_t idesc, dhi, rowu, a_lo_u, b_lo_u, sub_u, a0_u, a_stage_u, b0_u, b_stage_u, tmem_base, buf_cols, bn;
+  uint32_t idesc2, sub_cols;      // cat: instruction descriptor with N = 2 BN; TMEM columns of one sub-tile (BN or 2 BN)
+  int cat;
   uint32_t bar_a, bar_a_empty, bar_b_full, bar_b_empty, bar_p_full, bar_p_empty;
   uint32_t tap_u[2];
   int group, KB, SA, SB, nslab, cluster, nbuf;
@@ -208,7 +211,29 @@ __device__ __forceinline__ void issue_tile(const IssueCtx& c, IssueState& st, ui
       const uint32_t d_tmem = c.tmem_base + (uint32_t)st.buf * c.buf_cols + c.sub0_d;
       const bool last = X3 ? (gk == c.group - 1 || kbi == c.KB - 1) : (kbi == c.KB - 1);
       if (elect_one()) {
-        if (X3) {
+        if (X3 && c.cat) {
+          // N tile <= 64.  Measured (scripts/mma_rate.cu): below N = 128 a tf32 MMA is bound by the fetch of its 4 KB A
+          // operand -- 45.5 clk at N = 32, 48 at N = 64 -- so the hi and lo weight tiles, which sit back to back in shared
+          // memory, are read as ONE B operand of 2 BN rows: a_hi x [b_hi | b_lo] costs what a_hi x b_hi cost, and the
+          // 3-term product is two instructions instead of three.  Columns [0, BN) of the accumulator hold
+          // a_lo b_hi + a_hi b_hi (promoted every group), columns [BN, 2 BN) the cross term a_hi b_lo, which is 2^-11 of
+          // the main term: its truncation is harmless, so it keeps accumulating and is drained once per tile.  The
+          // epilogue zeroes what it drains (tcgen05.st), every MMA accumulates.
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int sub = 0; sub < MSL; ++sub)
+              umma_tf32_lohi(d_tmem + (uint32_t)sub * c.sub_cols, da + (uint32_t)sub * c.sub_u + 2u * ks + c.a_lo_u, db + 2u * ks,
+                             c.dhi, c.idesc, 1u);
+          }
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int sub = 0; sub < MSL; ++sub)
+              umma_tf32_lohi(d_tmem + (uint32_t)sub * c.sub_cols, da + (uint32_t)sub * c.sub_u + 2u * ks, db + 2u * ks, c.dhi,
+                             c.idesc2, 1u);
+          }
+        } else if (X3) {
           // The accumulator truncates every add (error ~ its magnitude x chain length): the two cross terms of all K
           // slices go first, while the accumulator still holds small values, the hi x hi terms last.
 #pragma unroll
@@ -217,7 +242,7 @@ __device__ __forceinline__ void issue_tile(const IssueCtx& c, IssueState& st, ui
 #pragma unroll
             for (int sub = 0; sub < MSL; ++sub) {         // rows [128 sub, 128 sub + 128) of the tile
               const uint32_t das = da + (uint32_t)sub * c.sub_u + 2u * ks;
-              const uint32_t dt = d_tmem + (uint32_t)sub * c.bn;
+              const uint32_t dt = d_tmem + (uint32_t)sub * c.sub_cols;
               umma_tf32_lohi(dt, das + c.a_lo_u, db + 2u * ks, c.dhi, c.idesc, acc);
               umma_tf32_lohi(dt, das, db + c.b_lo_u + 2u * ks, c.dhi, c.idesc, 1u);
             }
@@ -226,7 +251,7 @@ __device__ __forceinline__ void issue_tile(const IssueCtx& c, IssueState& st, ui
           for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
             for (int sub = 0; sub < MSL; ++sub)
-              umma_tf32_lohi(d_tmem + (uint32_t)sub * c.bn, da + (uint32_t)sub * c.sub_u + 2u * ks, db + 2u * ks, c.dhi,
+              umma_tf32_lohi(d_tmem + (uint32_t)sub * c.sub_cols, da + (uint32_t)sub * c.sub_u + 2u * ks, db + 2u * ks, c.dhi,
                              c.idesc, 1u);
           }
         } else {
@@ -354,8 +379,9 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     fence_mbar_init();
   }
   // two TMEM accumulator buffers of BN columns: x1 ping-pongs whole tiles, x3 ping-pongs accumulation groups
+  const bool cat = X3 && !FUSE && p.cat;
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.BN * p.nbuf * MS) tmem_cols <<= 1;
+  while ((int)tmem_cols < p.BN * p.nbuf * MS * (cat ? 2 : 1)) tmem_cols <<= 1;
   if (warp == 2) {
     tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     tmem_relinquish();
@@ -365,6 +391,19 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
   tc_fence_after();
   if (p.cluster > 1) cluster_sync_all();       // remote arrives / multicast writes need every CTA's barriers initialised
   const uint32_t tmem_base = ctl->tmem_base;
+  if (cat) {
+    // cat: every MMA accumulates and the epilogue zeroes what it has drained, so the accumulators start from zero
+    if (warp >= 4 && warp < 8) {
+      uint32_t z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) z[j] = 0u;
+      for (uint32_t col = 0; col < tmem_cols; col += 32) tmem_st32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + col, z);
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   // PDL: everything above touched shared memory / TMEM only.  The weight producer (warp 1) reads per-plan constants and
   // runs ahead; every other role waits here for the previous launch of the stream to finish before it reads an
   // activation (TMA slabs, residuals) or writes one.
@@ -464,7 +503,10 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     c.b0_u = dlo0 + (btiles0 >> 4);
     c.b_stage_u = btile_bytes >> 4;
     c.tmem_base = tmem_base;
-    c.buf_cols = (uint32_t)(p.BN * MS);
+    c.cat = X3 ? p.cat : 0;
+    c.idesc2 = make_idesc_tf32(2 * p.BN);
+    c.sub_cols = (uint32_t)(p.BN * (c.cat ? 2 : 1));
+    c.buf_cols = c.sub_cols * (uint32_t)MS;
     c.nbuf = p.nbuf;
     c.bn = (uint32_t)p.BN;
     c.group = p.group;
@@ -484,7 +526,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     c.tap_u[1] = (uint32_t)(p.Wt - 2) * c.rowu;            // step from the last tap of a kernel row to the next row
     const int issuer = warp - 2;
     c.sub0_a = DUAL ? (uint32_t)issuer * c.sub_u : 0u;
-    c.sub0_d = DUAL ? (uint32_t)issuer * c.bn : 0u;
+    c.sub0_d = DUAL ? (uint32_t)issuer * c.sub_cols : 0u;
     // (taps, K slices) are chosen ONCE, outside the tile loop: each combination owns its copy of the loop, so the
     // register allocation of the hot path is not shared between variants
     const IssueTiles tl{(int)cluster_id, (int)num_clusters, (int)tph, (int)total_tiles, n_tiles, rank, KS_SPLIT};
@@ -565,7 +607,9 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
     const int sub = (warp - 4) >> 2;              // M sub-tile (x3 only: 0 / 1)
     const int i = sub * TM_BM + q * 32 + lane;    // position inside the tile
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * p.BN);
+    const uint32_t sub_cols = (uint32_t)(p.BN * (cat ? 2 : 1));      // TMEM columns of one sub-tile of one buffer
+    const uint32_t buf_cols = sub_cols * (uint32_t)MS;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)sub * sub_cols;
     float* stage = nullptr;                       // (the direct store path needs no scratch)
     EpiParams ep;
     ep.bias = p.bias;
@@ -622,6 +666,36 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
           tc_fence_after();
           // 32 columns per tcgen05.ld: with one accumulation group = 12 MMAs the drain of a TMEM buffer has to finish inside
           // the ~1500 clk the tensor pipe needs for the next group, and every ld + wait round trip costs ~150 clk
+          if (cat) {
+            // main half [0, BN): promoted and zeroed every group; cross half [BN, 2 BN): only when this is the last group
+            // of the tile that uses this buffer (the last nbuf groups touch every buffer once)
+            const int halves = (gi >= ngroups - p.nbuf) ? 2 : 1;
+            for (int hf = 0; hf < halves; ++hf) {
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                if (c * 32 < p.BN) {
+                  const uint32_t ta = lane_base + (uint32_t)buf * buf_cols + (uint32_t)(hf * p.BN + c * 32);
+                  uint32_t rr[32], z[32];
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) z[j] = 0u;
+                  if (c * 32 + 16 < p.BN) {
+                    tmem_ld32(ta, rr);
+                    tmem_ld_wait();
+                    tmem_st32(ta, z);
+                  } else {
+                    tmem_ld16(ta, rr);
+#pragma unroll
+                    for (int j = 16; j < 32; ++j) rr[j] = 0u;
+                    tmem_ld_wait();
+                    tmem_st16(ta, z);
+                  }
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) sums[(X3 ? c * 32 + j : 0)] += __uint_as_float(rr[j]);
+                }
+              }
+            }
+            tmem_st_wait();
+          } else {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if (c * 32 < p.BN) {
@@ -637,6 +711,7 @@ __global__ void __launch_bounds__(X3 ? TM_THREADS_X3 : TM_THREADS, 1) conv_tma_k
 #pragma unroll
               for (int j = 0; j < 32; ++j) sums[(X3 ? c * 32 + j : 0)] += __uint_as_float(rr[j]);
             }
+          }
           }
           tc_fence_before();
           mbar_arrive(smem_u32(&ctl->p_empty[buf]));
@@ -1050,6 +1125,13 @@ int launch_conv_tma(const IgemmParams& p, const void* maps, int round_out_tf32, 
     q.nbuf = 512 / (q.BN * 2);
     if (q.nbuf > 8) q.nbuf = 8;
     if (q.nbuf < 2) q.nbuf = 2;
+  }
+  // x3, N tile <= 64 and no fused 1x1: hi | lo weight tiles as one 2 BN-row operand (issue_tile); a buffer is then 2 BN
+  // columns per sub-tile
+  q.cat = (x3 && q.BN <= 64 && p.fuse_n == 0 && !getenv("CP_NO_CAT")) ? 1 : 0;
+  if (q.cat) {
+    q.nbuf = 512 / (q.BN * 4);
+    if (q.nbuf > 8) q.nbuf = 8;
   }
   if (const char* e = getenv("CP_TMA_NBUF")) q.nbuf = atoi(e) >= 2 && atoi(e) <= q.nbuf ? atoi(e) : q.nbuf;
   q.k = p.kh;

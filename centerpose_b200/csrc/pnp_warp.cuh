@@ -17,50 +17,11 @@ namespace {
 // statement of the math.
 constexpr int PNP_SCRATCH = 320;      // doubles per warp: [0,288) Jacobi A|V or LM workspace, [288,320) image points
 
-__device__ void dlt_init_warp(const double* X, const double* uv, int n, double fx, double fy, double cx, double cy,
-                              double* R, double* t, double* sm, int lane) {
+// Eigen-decomposition of the symmetric 12 x 12 matrix A = sm[0,144) (destroyed: eigenvalues end on the diagonal), eigenvectors
+// in the columns of V = sm[144,288) (must hold the identity on entry), by one warp.  sm[288,306) is scratch.
+__device__ void jacobi12_warp(double* sm, int lane) {
   double* A = sm;
   double* V = sm + 144;
-  // M^T M of the 2n x 12 DLT matrix (rows [h 0 -x h], [0 h -y h], h = (X, Y, Z, 1), (x, y) the normalised image point)
-  // is a 3 x 3 arrangement of 4 x 4 weighted moment matrices of h:  [H 0 -Hx; 0 H -Hy; -Hx -Hy Hxx+yy].  The points are
-  // staged once in shared memory and the 4 x 16 moments summed by 2 entries per lane -- the first version evaluated all
-  // 144 entries with per-entry conditionals on local arrays (6.9 K of the 57 K instructions of a solve).
-  double* P = V;                        // [n][6]: X, Y, Z, 1, x, y (consumed before V is initialised)
-  double* S = sm + 240;                 // [4][4][4]: weights 1, x, y, x^2 + y^2
-  if (lane < n) {
-    P[6 * lane + 0] = X[3 * lane];
-    P[6 * lane + 1] = X[3 * lane + 1];
-    P[6 * lane + 2] = X[3 * lane + 2];
-    P[6 * lane + 3] = 1.0;
-    P[6 * lane + 4] = (uv[2 * lane] - cx) / fx;
-    P[6 * lane + 5] = (uv[2 * lane + 1] - cy) / fy;
-  }
-  __syncwarp();
-  for (int e = lane; e < 64; e += 32) {
-    const int w = e >> 4, i = (e >> 2) & 3, j = e & 3;
-    double acc = 0.0;
-    for (int k = 0; k < n; ++k) {
-      const double* pk = P + 6 * k;
-      const double x = pk[4], y = pk[5];
-      const double wt = w == 0 ? 1.0 : (w == 1 ? x : (w == 2 ? y : x * x + y * y));
-      acc += wt * (pk[i] * pk[j]);
-    }
-    S[e] = acc;
-  }
-  __syncwarp();
-  for (int e = lane; e < 144; e += 32) {
-    const int a = e / 12, b = e - a * 12;
-    const int ba = a >> 2, bb = b >> 2, ij = (a & 3) * 4 + (b & 3);
-    double v = 0.0;
-    if (ba == bb)
-      v = S[(ba == 2 ? 48 : 0) + ij];
-    else if (ba == 2 || bb == 2)
-      v = -S[((ba == 2 ? bb : ba) == 0 ? 16 : 32) + ij];
-    A[e] = v;
-  }
-  __syncwarp();
-  for (int e = lane; e < 144; e += 32) V[e] = (e / 12 == e % 12) ? 1.0 : 0.0;
-  __syncwarp();
   // Cyclic Jacobi in the ROUND-ROBIN order: the 66 index pairs of a sweep are 11 rounds of 6 disjoint pairs, and the six
   // rotations of a round commute, so a round is ONE parallel step -- lanes 0-5 compute the six angles, then 144 lane-tasks
   // rotate the columns of A and V (A J, V J) and 72 the rows of A (J^T A).  The row-cyclic order of pose::dlt_init (the
@@ -157,6 +118,53 @@ __device__ void dlt_init_warp(const double* X, const double* uv, int n, double f
       __syncwarp();
     }
   }
+}
+
+__device__ void dlt_init_warp(const double* X, const double* uv, int n, double fx, double fy, double cx, double cy,
+                              double* R, double* t, double* sm, int lane) {
+  double* A = sm;
+  double* V = sm + 144;
+  // M^T M of the 2n x 12 DLT matrix (rows [h 0 -x h], [0 h -y h], h = (X, Y, Z, 1), (x, y) the normalised image point)
+  // is a 3 x 3 arrangement of 4 x 4 weighted moment matrices of h:  [H 0 -Hx; 0 H -Hy; -Hx -Hy Hxx+yy].  The points are
+  // staged once in shared memory and the 4 x 16 moments summed by 2 entries per lane -- the first version evaluated all
+  // 144 entries with per-entry conditionals on local arrays (6.9 K of the 57 K instructions of a solve).
+  double* P = V;                        // [n][6]: X, Y, Z, 1, x, y (consumed before V is initialised)
+  double* S = sm + 240;                 // [4][4][4]: weights 1, x, y, x^2 + y^2
+  if (lane < n) {
+    P[6 * lane + 0] = X[3 * lane];
+    P[6 * lane + 1] = X[3 * lane + 1];
+    P[6 * lane + 2] = X[3 * lane + 2];
+    P[6 * lane + 3] = 1.0;
+    P[6 * lane + 4] = (uv[2 * lane] - cx) / fx;
+    P[6 * lane + 5] = (uv[2 * lane + 1] - cy) / fy;
+  }
+  __syncwarp();
+  for (int e = lane; e < 64; e += 32) {
+    const int w = e >> 4, i = (e >> 2) & 3, j = e & 3;
+    double acc = 0.0;
+    for (int k = 0; k < n; ++k) {
+      const double* pk = P + 6 * k;
+      const double x = pk[4], y = pk[5];
+      const double wt = w == 0 ? 1.0 : (w == 1 ? x : (w == 2 ? y : x * x + y * y));
+      acc += wt * (pk[i] * pk[j]);
+    }
+    S[e] = acc;
+  }
+  __syncwarp();
+  for (int e = lane; e < 144; e += 32) {
+    const int a = e / 12, b = e - a * 12;
+    const int ba = a >> 2, bb = b >> 2, ij = (a & 3) * 4 + (b & 3);
+    double v = 0.0;
+    if (ba == bb)
+      v = S[(ba == 2 ? 48 : 0) + ij];
+    else if (ba == 2 || bb == 2)
+      v = -S[((ba == 2 ? bb : ba) == 0 ? 16 : 32) + ij];
+    A[e] = v;
+  }
+  __syncwarp();
+  for (int e = lane; e < 144; e += 32) V[e] = (e / 12 == e % 12) ? 1.0 : 0.0;
+  __syncwarp();
+  jacobi12_warp(sm, lane);
   int m = 0;
   for (int i = 1; i < 12; ++i)
     if (A[i * 12 + i] < A[m * 12 + m]) m = i;
@@ -272,6 +280,41 @@ __device__ double refine_lm_warp(const double* X, const double* uv, int n, doubl
   return cost;
 }
 
+// pose::pnp_few_points (EPnP, 4 - 5 valid points) by a whole warp.  The serial version spent 2.4 ms per solve in the
+// 12 x 12 Jacobi on per-lane local arrays (measured: decode 0.18 -> 2.5 ms per frame when every object had 5 key points;
+// in tracking the filter confidence hides key points regularly).  Here M^T M is built 4.5 entries per lane in shared
+// memory and decomposed by jacobi12_warp; the small dependent rest (betas, Gauss-Newton, absolute orientation) is
+// evaluated by every lane from identical inputs.  The null space of M is degenerate below 6 points, so -- exactly as
+// between pose_core.h and LAPACK -- the basis, and with noisy points the pose, depends on the
+// rotation order; consistent points give the unique answer.
+__device__ void pnp_few_points_warp(const double* V, const double* X, const double* uv, int n, const double* Kc, double width,
+                                    double height, int visible_thresh, int opencv_return, pose::PnPOut* o, double* sm,
+                                    int lane) {
+  pose::EpnpPre P;
+  if (!pose::epnp_prepare(X, n, &P)) {
+    o->status = CP_PNP_SOLVER_FAIL;
+    return;
+  }
+  __syncwarp();
+  for (int e = lane; e < 144; e += 32) {
+    const int a = e / 12, b = e - a * 12;
+    sm[e] = pose::epnp_mtm_entry(P, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], a, b);
+    sm[144 + e] = (a == b) ? 1.0 : 0.0;
+  }
+  __syncwarp();
+  jacobi12_warp(sm, lane);
+  __syncwarp();
+  double R[9], t[3];
+  const double err = pose::epnp_finish(X, uv, n, Kc[0], Kc[4], Kc[2], Kc[5], P, sm, sm + 144, R, t);
+  __syncwarp();
+  if (!(err < 1e299)) {
+    o->status = CP_PNP_SOLVER_FAIL;
+    return;
+  }
+  pose::pnp_finish(V, R, t, pose::reproj_cost(X, uv, n, R, t, Kc[0], Kc[4], Kc[2], Kc[5]), n, Kc, width, height, visible_thresh,
+                   opencv_return, o);
+}
+
 // pose::solve_and_shell, executed by a whole warp; every lane ends with the same PnPOut
 __device__ void solve_and_shell_warp(const double* pts, int n_in, const float* obj_scale, const double* Kc, double width,
                                      double height, int visible_thresh, int opencv_return, pose::PnPOut* o, double* sm,
@@ -281,8 +324,8 @@ __device__ void solve_and_shell_warp(const double* pts, int n_in, const float* o
   o->n_pts = n;
   o->status = CP_PNP_FEW_POINTS;
   if (n < 4) return;
-  if (n < 6) {          // EPnP (rare path): evaluated redundantly by every lane, identical results
-    pose::pnp_few_points(V, X, uv, n, Kc, width, height, visible_thresh, opencv_return, o);
+  if (n < 6) {          // EPnP: 4 - 5 valid points (frequent in tracking, where the filter confidence gates key points)
+    pnp_few_points_warp(V, X, uv, n, Kc, width, height, visible_thresh, opencv_return, o, sm, lane);
     return;
   }
   double R[9], t[3];
@@ -300,8 +343,8 @@ __device__ void solve_and_shell_warp_v(const double* pts, int n_in, const double
   o->n_pts = n;
   o->status = CP_PNP_FEW_POINTS;
   if (n < 4) return;
-  if (n < 6) {          // EPnP (rare path): evaluated redundantly by every lane, identical results
-    pose::pnp_few_points(V, X, uv, n, Kc, width, height, visible_thresh, opencv_return, o);
+  if (n < 6) {
+    pnp_few_points_warp(V, X, uv, n, Kc, width, height, visible_thresh, opencv_return, o, sm, lane);
     return;
   }
   double R[9], t[3];

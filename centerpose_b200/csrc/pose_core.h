@@ -462,11 +462,20 @@ CP_HDN void epnp_rt(const double* X, const double* pcs, int n, double* R, double
   for (int k = 0; k < 3; ++k) t[k] = pc0[k] - (R[k * 3] * pw0[0] + R[k * 3 + 1] * pw0[1] + R[k * 3 + 2] * pw0[2]);
 }
 
-// X: n x 3 object points, uv: n x 2 pixels (4 <= n <= 16).  Returns the mean reprojection error (pixels) of the chosen pose.
-CP_HDN double epnp_solve(const double* X, const double* uv, int n, double fx, double fy, double cx, double cy, double* Rout,
-                         double* tout) {
-  // control points: centroid + principal directions scaled by sqrt(eigenvalue / n)
+// EPnP in three steps, so that the CUDA kernels can run the 12 x 12 eigen-decomposition warp-cooperatively (pnp_warp.cuh)
+// while the host runs the serial chain epnp_solve below:
+//   epnp_prepare    control points (centroid + principal directions) and barycentric coordinates of the object points
+//   epnp_mtm_entry  one entry of M^T M (12 x 12), accumulated over the points in order
+//   epnp_finish     from the eigen-decomposition of M^T M to the pose (betas, Gauss-Newton, absolute orientation)
+struct EpnpPre {
   double cws[4][3];
+  double al[16][4];
+};
+
+CP_HDN bool epnp_prepare(const double* X, int n, EpnpPre* P) {
+  // control points: centroid + principal directions scaled by sqrt(eigenvalue / n)
+  double (*cws)[3] = P->cws;
+  double (*al)[4] = P->al;
   for (int k = 0; k < 3; ++k) {
     cws[0][k] = 0.0;
     for (int i = 0; i < n; ++i) cws[0][k] += X[3 * i + k] / n;
@@ -493,31 +502,38 @@ CP_HDN double epnp_solve(const double* X, const double* uv, int n, double fx, do
   double CC[9], CCit[9];
   for (int i = 0; i < 3; ++i)
     for (int j = 1; j < 4; ++j) CC[3 * i + j - 1] = cws[j][i] - cws[0][i];
-  if (fabs(mat3_det(CC)) < 1e-300) return 1e300;      // coplanar object points: EPnP's general case does not apply
+  if (fabs(mat3_det(CC)) < 1e-300) return false;      // coplanar object points: EPnP's general case does not apply
   mat3_inv_t(CC, CCit);                               // CCit = (CC^-1)^T
-  double al[16][4];
   for (int i = 0; i < n; ++i) {
     const double d[3] = {X[3 * i] - cws[0][0], X[3 * i + 1] - cws[0][1], X[3 * i + 2] - cws[0][2]};
     for (int j = 0; j < 3; ++j) al[i][1 + j] = CCit[0 * 3 + j] * d[0] + CCit[1 * 3 + j] * d[1] + CCit[2 * 3 + j] * d[2];
     al[i][0] = 1.0 - al[i][1] - al[i][2] - al[i][3];
   }
-  // M^T M (12 x 12) accumulated row pair by row pair
-  double MtM[144], V[144];
-  for (int i = 0; i < 144; ++i) MtM[i] = 0.0;
+  return true;
+}
+
+// entry (a, b) of M^T M: rows r1 = [al_j fx, 0, al_j (cx - u)], r2 = [0, al_j fy, al_j (cy - v)] (j = 0..3) per point
+CP_HDN double epnp_mtm_entry(const EpnpPre& P, const double* uv, int n, double fx, double fy, double cx, double cy, int a,
+                             int b) {
+  const int ja = a / 3, ka = a - 3 * ja, jb = b / 3, kb = b - 3 * jb;
+  double acc = 0.0;
   for (int i = 0; i < n; ++i) {
-    double r1[12], r2[12];
-    for (int j = 0; j < 4; ++j) {
-      r1[3 * j] = al[i][j] * fx;
-      r1[3 * j + 1] = 0.0;
-      r1[3 * j + 2] = al[i][j] * (cx - uv[2 * i]);
-      r2[3 * j] = 0.0;
-      r2[3 * j + 1] = al[i][j] * fy;
-      r2[3 * j + 2] = al[i][j] * (cy - uv[2 * i + 1]);
-    }
-    for (int a = 0; a < 12; ++a)
-      for (int b = 0; b < 12; ++b) MtM[a * 12 + b] += r1[a] * r1[b] + r2[a] * r2[b];
+    const double du = cx - uv[2 * i], dv = cy - uv[2 * i + 1];
+    const double r1a = ka == 0 ? P.al[i][ja] * fx : (ka == 1 ? 0.0 : P.al[i][ja] * du);
+    const double r1b = kb == 0 ? P.al[i][jb] * fx : (kb == 1 ? 0.0 : P.al[i][jb] * du);
+    const double r2a = ka == 0 ? 0.0 : (ka == 1 ? P.al[i][ja] * fy : P.al[i][ja] * dv);
+    const double r2b = kb == 0 ? 0.0 : (kb == 1 ? P.al[i][jb] * fy : P.al[i][jb] * dv);
+    acc += r1a * r1b + r2a * r2b;
   }
-  jacobi_eig<12>(MtM, V);
+  return acc;
+}
+
+// MtM: the 12 x 12 matrix after its Jacobi eigen-decomposition (eigenvalues on the diagonal), V: eigenvectors in columns.
+// Returns the mean reprojection error (pixels) of the chosen pose.
+CP_HDN double epnp_finish(const double* X, const double* uv, int n, double fx, double fy, double cx, double cy,
+                          const EpnpPre& P, const double* MtM, const double* V, double* Rout, double* tout) {
+  const double (*cws)[3] = P.cws;
+  const double (*al)[4] = P.al;
   int ord[12];
   for (int i = 0; i < 12; ++i) ord[i] = i;
   for (int a = 0; a < 4; ++a)                    // the four smallest eigenvalues, ascending
@@ -640,6 +656,18 @@ CP_HDN double epnp_solve(const double* X, const double* uv, int n, double fx, do
     }
   }
   return best;
+}
+
+// X: n x 3 object points, uv: n x 2 pixels (4 <= n <= 16).  Returns the mean reprojection error (pixels) of the chosen pose.
+CP_HDN double epnp_solve(const double* X, const double* uv, int n, double fx, double fy, double cx, double cy, double* Rout,
+                         double* tout) {
+  EpnpPre P;
+  if (!epnp_prepare(X, n, &P)) return 1e300;
+  double MtM[144], V[144];
+  for (int a = 0; a < 12; ++a)
+    for (int b = 0; b < 12; ++b) MtM[a * 12 + b] = epnp_mtm_entry(P, uv, n, fx, fy, cx, cy, a, b);
+  jacobi_eig<12>(MtM, V);
+  return epnp_finish(X, uv, n, fx, fy, cx, cy, P, MtM, V, Rout, tout);
 }
 
 // solve_pnp + pnp_shell for one detection, in three steps so that the CUDA decode kernel can run the two heavy ones

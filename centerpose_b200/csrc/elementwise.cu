@@ -42,21 +42,24 @@ __global__ void maxpool2_kernel(const float4* __restrict__ in, float4* __restric
 // ---- depthwise ConvTranspose2d(C, C, 2f, stride f, pad f/2, groups C) + skip add
 //      (pose_dla_dcn.py:402-405, :415-417).  Every output pixel receives exactly
 //      2 x 2 taps; weights are packed [ky][kx][C].
+// IDX = unsigned for every shape the network uses (< 2^32 float4 elements): the three divisions of the index decode are
+// then 32-bit (the 64-bit ones were ~100 instructions per 16 bytes moved and held the kernel at half the HBM rate).
+template <typename IDX>
 __global__ void upsample_add_kernel(const float4* __restrict__ in, const float4* __restrict__ w,
                                     const float4* __restrict__ skip, float4* __restrict__ out, int B,
                                     int Hin, int Win, int C4, int f) {
   griddep_launch_dependents();      // PDL (common.cuh)
   griddep_wait();
-  const int Ho = Hin * f, Wo = Win * f;
+  const IDX Ho = (IDX)(Hin * f), Wo = (IDX)(Win * f), C4u = (IDX)C4;
   const int k = 2 * f, pad = f / 2;
-  size_t total = (size_t)B * Ho * Wo * C4;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int c = i % C4;
-    size_t t = i / C4;
-    int ox = t % Wo;
+  const IDX total = (IDX)B * Ho * Wo * C4u;
+  for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4u);
+    IDX t = i / C4u;
+    const int ox = (int)(t % Wo);
     t /= Wo;
-    int oy = t % Ho;
-    int n = t / Ho;
+    const int oy = (int)(t % Ho);
+    const int n = (int)(t / Ho);
     float4 acc = skip ? __ldg(skip + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 up = make_float4(0.f, 0.f, 0.f, 0.f);
     int iy_hi = (oy + pad) / f, ky_lo = (oy + pad) - iy_hi * f;
@@ -255,8 +258,12 @@ int launch_upsample_add(const float* in, const float* w, const float* skip, floa
                         int Win, int C, int f, cudaStream_t s) {
   if (C % 4) return fail(CP_ERR_INVALID, "upsample: C%4");
   size_t total = (size_t)B * Hin * f * Win * f * (C / 4);
-  CP_CUDA_CHECK(launch_kernel(upsample_add_kernel, dim3(blocks_for(total)), dim3(TPB), 0, s, (const float4*)in, (const float4*)w,
-                              (const float4*)skip, (float4*)out, B, Hin, Win, C / 4, f));
+  if (total < (1ull << 31))
+    CP_CUDA_CHECK(launch_kernel(upsample_add_kernel<unsigned>, dim3(blocks_for(total)), dim3(TPB), 0, s, (const float4*)in,
+                                (const float4*)w, (const float4*)skip, (float4*)out, B, Hin, Win, C / 4, f));
+  else
+    CP_CUDA_CHECK(launch_kernel(upsample_add_kernel<size_t>, dim3(blocks_for(total)), dim3(TPB), 0, s, (const float4*)in,
+                                (const float4*)w, (const float4*)skip, (float4*)out, B, Hin, Win, C / 4, f));
   CP_LAUNCH_CHECK("upsample_add_kernel");
   return CP_OK;
 }
